@@ -1,0 +1,160 @@
+// Generic fp32 CUDA-core implicit-GEMM convolution over channels-last voxel tensors.  This is the exact-fp32
+// path: it covers every shape the UNet can ask for (3^3 / 1^3 kernels, stride 1|2, fused nearest x2 upsample
+// of the input, two-source channel concat, bias + residual epilogue) and is the fallback for shapes the
+// tcgen05 kernel (conv_tc.cu) does not take.
+//
+// Reference ops replaced (relative to /root/reference/holo_diffusion/guided_diffusion/unet.py):
+//   nn.Conv3d 3^3 s1 p1  :185,211,657,792 and Upsample.conv :89 (after F.interpolate nearest x2 :94-97)
+//   nn.Conv3d 3^3 s2 p1  Downsample.op :129-131
+//   nn.Conv3d 1^3        ResBlock.skip_connection :222 (on the concatenated input, th.cat :829)
+//   nn.Conv1d k=1        AttentionBlock.qkv :383 / proj_out :392 (+ residual x + h :406)
+#include "common.cuh"
+#include "../../include/holo_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
+
+struct ConvParams {
+    const float* x1;
+    const float* x2;
+    int C1, C2;
+    int Din, Hin, Win;     // stored input dims
+    int Dout, Hout, Wout;
+    int ksize, stride, ups;
+    const float* w;        // [ksize^3][Cin][Cout]
+    const float* bias;     // [Cout] or null
+    const float* residual; // [Vout][Cout] or null
+    float* out;            // [Vout][Cout]
+    int Cout;
+};
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvParams P) {
+    __shared__ __align__(16) float As[BK][BM + APAD];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int Cin = P.C1 + P.C2;
+    const long long Vout = (long long)P.Dout * P.Hout * P.Wout;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int pad = P.ksize / 2;
+    const int kvol = P.ksize * P.ksize * P.ksize;
+    const int Dl = P.ups ? P.Din * 2 : P.Din, Hl = P.ups ? P.Hin * 2 : P.Hin, Wl = P.ups ? P.Win * 2 : P.Win;
+
+    // A-load role: two (voxel, float4-of-channels) slots per thread
+    int a_m[2], a_kq[2], a_od[2], a_oh[2], a_ow[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int idx = tid + r * 256;
+        a_m[r] = idx / 4, a_kq[r] = idx % 4;
+        long long v = m0 + a_m[r];
+        a_ok[r] = v < Vout;
+        long long vv = a_ok[r] ? v : 0;
+        a_ow[r] = (int)(vv % P.Wout);
+        a_oh[r] = (int)((vv / P.Wout) % P.Hout);
+        a_od[r] = (int)(vv / ((long long)P.Wout * P.Hout));
+    }
+    // B-load role: one float4 per thread (16 rows x 16 float4)
+    const int b_k = tid / 16, b_n4 = tid % 16;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < kvol; ++tap) {
+        const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
+        long long a_off[2];
+        bool a_in[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int id = a_od[r] * P.stride + kd - pad, ih = a_oh[r] * P.stride + kh - pad, iw = a_ow[r] * P.stride + kw - pad;
+            a_in[r] = a_ok[r] && id >= 0 && id < Dl && ih >= 0 && ih < Hl && iw >= 0 && iw < Wl;
+            if (P.ups) id >>= 1, ih >>= 1, iw >>= 1;
+            a_off[r] = ((long long)id * P.Hin + ih) * P.Win + iw;
+        }
+        for (int c0 = 0; c0 < Cin; c0 += BK) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int c = c0 + a_kq[r] * 4;
+                float4 v = make_float4(0, 0, 0, 0);
+                if (a_in[r] && c < Cin) {
+                    v = (c < P.C1) ? __ldg(reinterpret_cast<const float4*>(P.x1 + a_off[r] * P.C1 + c))
+                                   : __ldg(reinterpret_cast<const float4*>(P.x2 + a_off[r] * P.C2 + (c - P.C1)));
+                }
+                As[a_kq[r] * 4 + 0][a_m[r]] = v.x;
+                As[a_kq[r] * 4 + 1][a_m[r]] = v.y;
+                As[a_kq[r] * 4 + 2][a_m[r]] = v.z;
+                As[a_kq[r] * 4 + 3][a_m[r]] = v.w;
+            }
+            {
+                int c = c0 + b_k, n = n0 + b_n4 * 4;
+                float4 v = make_float4(0, 0, 0, 0);
+                if (c < Cin && n < P.Cout)
+                    v = __ldg(reinterpret_cast<const float4*>(P.w + ((size_t)tap * Cin + c) * P.Cout + n));
+                *reinterpret_cast<float4*>(&Bs[b_k][b_n4 * 4]) = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+                float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+                float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    const int n = n0 + tx * 4;
+    if (n < P.Cout) {
+        float4 bv = P.bias ? *reinterpret_cast<const float4*>(P.bias + n) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            long long v = m0 + ty * 8 + i;
+            if (v < Vout) {
+                float4 r = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+                if (P.residual) {
+                    float4 q = *reinterpret_cast<const float4*>(P.residual + v * P.Cout + n);
+                    r.x += q.x, r.y += q.y, r.z += q.z, r.w += q.w;
+                }
+                *reinterpret_cast<float4*>(P.out + v * P.Cout + n) = r;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, int Hin, int Win,
+                                int ksize, int stride, int upsample2x, const float* w_tap_cin_cout,
+                                const float* bias, const float* residual, int Cout, float* out, void* stream) {
+    HOLO_CHECK_ARG(x1 && w_tap_cin_cout && out, "holo_conv3d_simt: null arg");
+    HOLO_CHECK_ARG(ksize == 1 || ksize == 3, "holo_conv3d_simt: ksize must be 1 or 3");
+    HOLO_CHECK_ARG(stride == 1 || stride == 2, "holo_conv3d_simt: stride must be 1 or 2");
+    HOLO_CHECK_ARG(!(upsample2x && stride != 1), "holo_conv3d_simt: upsample with stride 2 unsupported");
+    HOLO_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 % 4 == 0 && Cout % 4 == 0, "holo_conv3d_simt: channels must be multiples of 4");
+    HOLO_CHECK_ARG(C2 == 0 || x2, "holo_conv3d_simt: second source missing");
+    ConvParams P;
+    P.x1 = x1, P.x2 = x2, P.C1 = C1, P.C2 = C2;
+    P.Din = Din, P.Hin = Hin, P.Win = Win;
+    int Dl = upsample2x ? 2 * Din : Din, Hl = upsample2x ? 2 * Hin : Hin, Wl = upsample2x ? 2 * Win : Win;
+    int pad = ksize / 2;
+    P.Dout = (Dl + 2 * pad - ksize) / stride + 1;
+    P.Hout = (Hl + 2 * pad - ksize) / stride + 1;
+    P.Wout = (Wl + 2 * pad - ksize) / stride + 1;
+    P.ksize = ksize, P.stride = stride, P.ups = upsample2x;
+    P.w = w_tap_cin_cout, P.bias = bias, P.residual = residual, P.out = out, P.Cout = Cout;
+    long long Vout = (long long)P.Dout * P.Hout * P.Wout;
+    dim3 grid(holo_cdiv(Vout, BM), holo_cdiv(Cout, BN));
+    conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    HOLO_CHECK_LAUNCH("holo_conv3d_simt");
+    return HOLO_OK;
+}

@@ -1,0 +1,433 @@
+// Streaming (HBM-bound) kernels of the denoiser: layout changes, GroupNorm(32) statistics / affine+SiLU,
+// timestep embedding + small linears, the fused DDPM ancestral step, tanh + range check.
+//
+// Reference path replaced (relative to /root/reference/holo_diffusion):
+//   guided_diffusion/nn.py:23-25,99-106      GroupNorm32(32, C), eps 1e-5
+//   guided_diffusion/unet.py:184,208,248-252 GN -> SiLU, FiLM  out_norm(h) * (1 + scale) + shift
+//   guided_diffusion/nn.py:109-127           timestep_embedding
+//   guided_diffusion/unet.py:646-650,199-205 time_embed / emb_layers linears
+//   guided_diffusion/gaussian_diffusion.py:318,229-251,498-506  clamp, posterior mean, ancestral sample
+//   holo_diffusion_model.py:424-428          tanh + range asserts
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include "../../include/holo_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// layout: (C, V) channels-first <-> (V, C) channels-last, smem-tiled transpose
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    // src is (rows, cols) row-major, dst is (cols, rows)
+    __shared__ float tile[32][33];
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+extern "C" int holo_transpose2d(const float* src, float* dst, int rows, int cols, void* stream) {
+    HOLO_CHECK_ARG(src && dst && rows > 0 && cols > 0, "holo_transpose2d: bad args");
+    dim3 grid(holo_cdiv(cols, 32), holo_cdiv(rows, 32));
+    HOLO_CHECK_ARG(grid.y <= 65535, "holo_transpose2d: too many rows (%d); put the long axis in cols", rows);
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, rows, cols);
+    HOLO_CHECK_LAUNCH("holo_transpose2d");
+    return HOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics over a channels-last tensor made of up to two sources (the skip concat, unet.py:829).
+// Every block reduces a slab of voxels; per-channel partials in fp32, combined per group and accumulated
+// into global fp64 (sum, sumsq).  acc must be zeroed (holo_gn_finalize re-zeroes it after use).
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                long long V, int vox_per_block, double* __restrict__ acc) {
+    extern __shared__ float sh[];  // 2 * C
+    const int C = C1 + C2;
+    const int cq = C / 4;  // float4 lanes per voxel
+    float* s_sum = sh;
+    float* s_sq = sh + C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    long long v0 = (long long)blockIdx.x * vox_per_block;
+    long long v1 = v0 + vox_per_block;
+    if (v1 > V) v1 = V;
+    // thread t owns float4 lane (t % cq) and walks voxels with stride blockDim/cq
+    const int lane = threadIdx.x % cq;
+    const int vstep = blockDim.x / cq;
+    const int c = lane * 4;
+    if (threadIdx.x < vstep * cq) {
+        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+        for (long long v = v0 + threadIdx.x / cq; v < v1; v += vstep) {
+            float4 a = (c < C1) ? *reinterpret_cast<const float4*>(x1 + v * C1 + c)
+                                : *reinterpret_cast<const float4*>(x2 + v * C2 + (c - C1));
+            s.x += a.x, s.y += a.y, s.z += a.z, s.w += a.w;
+            q.x += a.x * a.x, q.y += a.y * a.y, q.z += a.z * a.z, q.w += a.w * a.w;
+        }
+        atomicAdd(&s_sum[c + 0], s.x), atomicAdd(&s_sum[c + 1], s.y);
+        atomicAdd(&s_sum[c + 2], s.z), atomicAdd(&s_sum[c + 3], s.w);
+        atomicAdd(&s_sq[c + 0], q.x), atomicAdd(&s_sq[c + 1], q.y);
+        atomicAdd(&s_sq[c + 2], q.z), atomicAdd(&s_sq[c + 3], q.w);
+    }
+    __syncthreads();
+    const int cpg = C / 32;
+    if (threadIdx.x < 32) {
+        double s = 0, q = 0;
+        for (int k = 0; k < cpg; ++k) s += (double)s_sum[threadIdx.x * cpg + k], q += (double)s_sq[threadIdx.x * cpg + k];
+        atomicAdd(&acc[threadIdx.x * 2], s);
+        atomicAdd(&acc[threadIdx.x * 2 + 1], q);
+    }
+}
+
+extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64,
+                             void* stream) {
+    int C = C1 + C2;
+    HOLO_CHECK_ARG(x1 && acc64 && V > 0, "holo_gn_stats: bad args");
+    HOLO_CHECK_ARG(C % 32 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 1024, "holo_gn_stats: C=%d+%d unsupported", C1, C2);
+    HOLO_CHECK_ARG(C2 == 0 || x2, "holo_gn_stats: second source missing");
+    int threads = 256;
+    if (C / 4 > threads) threads = C / 4;
+    // aim for >= 4 waves of 148 SMs but at least 64 voxels per block
+    long long vpb = (V + 148 * 8 - 1) / (148 * 8);
+    if (vpb < 64) vpb = 64;
+    int blocks = holo_cdiv(V, vpb);
+    gn_stats_kernel<<<blocks, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb,
+                                                                                    acc64);
+    HOLO_CHECK_LAUNCH("holo_gn_stats");
+    return HOLO_OK;
+}
+
+// per-channel affine from the statistics:  y = x * a[c] + b[c]
+//   plain GN : a = rstd*gamma,            b = beta - mean*rstd*gamma
+//   FiLM     : a *= (1+scale[c]),         b = b*(1+scale[c]) + shift[c]      (unet.py:248-252)
+__global__ void gn_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ film, int C,
+                                   double count, float eps, float* __restrict__ a, float* __restrict__ b) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int cpg = C / 32;
+    if (c < C) {
+        int g = c / cpg;
+        double mean = acc[g * 2] / count;
+        double var = acc[g * 2 + 1] / count - mean * mean;
+        if (var < 0) var = 0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float aa = rstd * gamma[c];
+        float bb = beta[c] - (float)mean * aa;
+        if (film) {
+            float sc = 1.f + film[c], sh = film[C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        a[c] = aa, b[c] = bb;
+    }
+}
+__global__ void zero_f64_kernel(double* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+extern "C" int holo_gn_finalize(double* acc64, const float* gamma, const float* beta, const float* film_scale_shift,
+                                int C, long long V, float eps, float* a, float* b, void* stream) {
+    HOLO_CHECK_ARG(acc64 && gamma && beta && a && b && C % 32 == 0, "holo_gn_finalize: bad args");
+    double count = (double)V * (double)(C / 32);
+    gn_finalize_kernel<<<holo_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(acc64, gamma, beta, film_scale_shift, C,
+                                                                           count, eps, a, b);
+    zero_f64_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(acc64, 64);
+    HOLO_CHECK_LAUNCH("holo_gn_finalize");
+    return HOLO_OK;
+}
+
+// y = act(x*a+b) over the (possibly concatenated) channels-last tensor.  Optional bf16 hi/lo split outputs
+// feed the tensor-core convolution (x = hi + lo + O(2^-17 x)).
+template <bool SILU>
+__global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                long long V, const float* __restrict__ a, const float* __restrict__ b,
+                                float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
+    const int C = C1 + C2;
+    const long long total4 = V * (C / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long v = i / (C / 4);
+        int c = (int)(i % (C / 4)) * 4;
+        float4 xv = (c < C1) ? *reinterpret_cast<const float4*>(x1 + v * C1 + c)
+                             : *reinterpret_cast<const float4*>(x2 + v * C2 + (c - C1));
+        float4 av = *reinterpret_cast<const float4*>(a + c);
+        float4 bv = *reinterpret_cast<const float4*>(b + c);
+        float4 r;
+        r.x = xv.x * av.x + bv.x, r.y = xv.y * av.y + bv.y, r.z = xv.z * av.z + bv.z, r.w = xv.w * av.w + bv.w;
+        if (SILU) r.x = holo_silu(r.x), r.y = holo_silu(r.y), r.z = holo_silu(r.z), r.w = holo_silu(r.w);
+        if (y) *reinterpret_cast<float4*>(y + v * C + c) = r;
+        if (y_hi) {
+            float rr[4] = {r.x, r.y, r.z, r.w};
+            uint16_t hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat16 h = __float2bfloat16_rn(rr[k]);
+                __nv_bfloat16 l = __float2bfloat16_rn(rr[k] - __bfloat162float(h));
+                hi[k] = *reinterpret_cast<uint16_t*>(&h);
+                lo[k] = *reinterpret_cast<uint16_t*>(&l);
+            }
+            *reinterpret_cast<uint2*>(y_hi + v * C + c) =
+                make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+            *reinterpret_cast<uint2*>(y_lo + v * C + c) =
+                make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+        }
+    }
+}
+
+extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a,
+                             const float* b, int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream) {
+    int C = C1 + C2;
+    HOLO_CHECK_ARG(x1 && a && b && (y || y_hi_bf16) && V > 0, "holo_gn_apply: bad args");
+    HOLO_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "holo_gn_apply: channel counts must be multiples of 4");
+    HOLO_CHECK_ARG((y_hi_bf16 == nullptr) == (y_lo_bf16 == nullptr), "holo_gn_apply: hi/lo must come together");
+    long long total4 = V * (C / 4);
+    int blocks = holo_cdiv(total4, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (silu)
+        gn_apply_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, a, b, y, (uint16_t*)y_hi_bf16,
+                                                                        (uint16_t*)y_lo_bf16);
+    else
+        gn_apply_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, a, b, y,
+                                                                         (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16);
+    HOLO_CHECK_LAUNCH("holo_gn_apply");
+    return HOLO_OK;
+}
+
+// fp32 -> bf16 hi/lo split of a plain tensor (operands that do not come out of a GroupNorm)
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n4, uint16_t* __restrict__ hi,
+                                  uint16_t* __restrict__ lo) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 r = reinterpret_cast<const float4*>(x)[i];
+        float rr[4] = {r.x, r.y, r.z, r.w};
+        uint16_t h4[4], l4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h = __float2bfloat16_rn(rr[k]);
+            __nv_bfloat16 l = __float2bfloat16_rn(rr[k] - __bfloat162float(h));
+            h4[k] = *reinterpret_cast<uint16_t*>(&h);
+            l4[k] = *reinterpret_cast<uint16_t*>(&l);
+        }
+        reinterpret_cast<uint2*>(hi)[i] =
+            make_uint2((uint32_t)h4[0] | ((uint32_t)h4[1] << 16), (uint32_t)h4[2] | ((uint32_t)h4[3] << 16));
+        reinterpret_cast<uint2*>(lo)[i] =
+            make_uint2((uint32_t)l4[0] | ((uint32_t)l4[1] << 16), (uint32_t)l4[2] | ((uint32_t)l4[3] << 16));
+    }
+}
+
+extern "C" int holo_split_bf16(const float* x, long long n, void* hi_bf16, void* lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(x && hi_bf16 && lo_bf16 && n > 0 && n % 4 == 0, "holo_split_bf16: n must be a positive multiple of 4");
+    int blocks = holo_cdiv(n / 4, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n / 4, (uint16_t*)hi_bf16, (uint16_t*)lo_bf16);
+    HOLO_CHECK_LAUNCH("holo_split_bf16");
+    return HOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding + small dense layers (M = batch of timesteps, tiny)
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int half = dim / 2;
+    if (i < n * half) {
+        int b = i / half, k = i % half;
+        // th.exp(-log(10000) * arange(half) / half), then args = t.float() * freqs
+        float f = expf(-logf(10000.0f) * (float)k / (float)half);
+        float arg = (float)t[b] * f;
+        out[b * dim + k] = cosf(arg);
+        out[b * dim + half + k] = sinf(arg);
+    }
+}
+
+extern "C" int holo_timestep_embedding(const long long* t_i64, int n, int dim, float* out, void* stream) {
+    HOLO_CHECK_ARG(t_i64 && out && n > 0 && dim > 0 && dim % 2 == 0, "holo_timestep_embedding: bad args");
+    timestep_embedding_kernel<<<holo_cdiv(n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t_i64, n, dim, out);
+    HOLO_CHECK_LAUNCH("holo_timestep_embedding");
+    return HOLO_OK;
+}
+
+// out[m][o] = act_out( b[o] + sum_i W[o][i] * act_in(x[m][i]) ); one warp per (m, o)
+__global__ void linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                   const float* __restrict__ b, int M, int in_dim, int out_dim, int silu_in,
+                                   int silu_out, float* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    int lane = threadIdx.x % 32;
+    if (warp >= M * out_dim) return;
+    int m = warp / out_dim, o = warp % out_dim;
+    float acc = 0.f;
+    for (int i = lane; i < in_dim; i += 32) {
+        float xv = x[(size_t)m * in_dim + i];
+        if (silu_in) xv = holo_silu(xv);
+        acc = fmaf(W[(size_t)o * in_dim + i], xv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        acc += b ? b[o] : 0.f;
+        out[(size_t)m * out_dim + o] = silu_out ? holo_silu(acc) : acc;
+    }
+}
+
+extern "C" int holo_linear_rows(const float* x, const float* W, const float* b, int M, int in_dim, int out_dim,
+                                int silu_in, int silu_out, float* out, void* stream) {
+    HOLO_CHECK_ARG(x && W && out && M > 0 && in_dim > 0 && out_dim > 0, "holo_linear_rows: bad args");
+    long long warps = (long long)M * out_dim;
+    linear_rows_kernel<<<holo_cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, W, b, M, in_dim, out_dim,
+                                                                                     silu_in, silu_out, out);
+    HOLO_CHECK_LAUNCH("holo_linear_rows");
+    return HOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DDPM ancestral step (START_X / FIXED_SMALL): tables are device fp32 copies of the fp64 schedule,
+// indexed by the device-resident timestep (no host round trip, no per-step H2D of the tables).
+//   x0 = clamp(model_out, -1, 1);  mean = c1[t]*x0 + c2[t]*x_t;  x_{t-1} = mean + [t!=0]*exp(0.5*logvar[t])*eps
+// ------------------------------------------------------------------------------------------------
+__global__ void ddpm_step_kernel(const float* __restrict__ model_out, const float* __restrict__ x_t,
+                                 const float* __restrict__ noise, const long long* __restrict__ t,
+                                 const float* __restrict__ coef1, const float* __restrict__ coef2,
+                                 const float* __restrict__ logvar, long long per_sample4, int n_batch, int clip,
+                                 float* __restrict__ x_prev, float* __restrict__ pred_x0) {
+    long long total = per_sample4 * n_batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int bidx = (int)(i / per_sample4);
+        long long tt = t[bidx];
+        float c1 = coef1[tt], c2 = coef2[tt];
+        float sd = (tt != 0) ? expf(0.5f * logvar[tt]) : 0.f;
+        float4 m = reinterpret_cast<const float4*>(model_out)[i];
+        float4 x = reinterpret_cast<const float4*>(x_t)[i];
+        float4 e = noise ? reinterpret_cast<const float4*>(noise)[i] : make_float4(0, 0, 0, 0);
+        if (clip) {
+            m.x = fminf(fmaxf(m.x, -1.f), 1.f), m.y = fminf(fmaxf(m.y, -1.f), 1.f);
+            m.z = fminf(fmaxf(m.z, -1.f), 1.f), m.w = fminf(fmaxf(m.w, -1.f), 1.f);
+        }
+        float4 r;
+        r.x = (c1 * m.x + c2 * x.x) + sd * e.x;
+        r.y = (c1 * m.y + c2 * x.y) + sd * e.y;
+        r.z = (c1 * m.z + c2 * x.z) + sd * e.z;
+        r.w = (c1 * m.w + c2 * x.w) + sd * e.w;
+        reinterpret_cast<float4*>(x_prev)[i] = r;
+        if (pred_x0) reinterpret_cast<float4*>(pred_x0)[i] = m;
+    }
+}
+
+extern "C" int holo_ddpm_step(const float* model_out, const float* x_t, const float* noise, const long long* t_i64,
+                              const float* coef1, const float* coef2, const float* logvar, long long per_sample,
+                              int n_batch, int clip_denoised, float* x_prev, float* pred_xstart, void* stream) {
+    HOLO_CHECK_ARG(model_out && x_t && t_i64 && coef1 && coef2 && logvar && x_prev, "holo_ddpm_step: null arg");
+    HOLO_CHECK_ARG(per_sample > 0 && per_sample % 4 == 0 && n_batch > 0, "holo_ddpm_step: per_sample must be a multiple of 4");
+    long long total = per_sample / 4 * n_batch;
+    int blocks = holo_cdiv(total, 256 * 2);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ddpm_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(model_out, x_t, noise, t_i64, coef1, coef2, logvar,
+                                                               per_sample / 4, n_batch, clip_denoised, x_prev,
+                                                               pred_xstart);
+    HOLO_CHECK_LAUNCH("holo_ddpm_step");
+    return HOLO_OK;
+}
+
+// q_sample: x_t = sqrt_ac[t]*x0 + sqrt_1m_ac[t]*eps   (gaussian_diffusion.py:209-227)
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ sa,
+                                const float* __restrict__ s1, long long per_sample, int n_batch,
+                                float* __restrict__ out) {
+    long long total = per_sample * n_batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long tt = t[i / per_sample];
+        out[i] = sa[tt] * x0[i] + s1[tt] * noise[i];
+    }
+}
+extern "C" int holo_q_sample(const float* x0, const float* noise, const long long* t_i64, const float* sqrt_ac,
+                             const float* sqrt_1m_ac, long long per_sample, int n_batch, float* out, void* stream) {
+    HOLO_CHECK_ARG(x0 && noise && t_i64 && sqrt_ac && sqrt_1m_ac && out && per_sample > 0 && n_batch > 0, "holo_q_sample: bad args");
+    int blocks = holo_cdiv(per_sample * n_batch, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    q_sample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x0, noise, t_i64, sqrt_ac, sqrt_1m_ac, per_sample, n_batch, out);
+    HOLO_CHECK_LAUNCH("holo_q_sample");
+    return HOLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise activation + range statistics, both layouts written in one pass.
+//   act: 0 none, 1 tanh, 2 clamp[-1,1].  stats (device, 4 ints): ordered-int min, ordered-int max, nan count, unused.
+// Input is channels-last (V,C); outputs: channels-last (for the renderer) and/or channels-first (for the API).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+__global__ void act_range_kernel(const float* __restrict__ x, long long V, int C, int act,
+                                 float* __restrict__ y_cl, float* __restrict__ y_cf, int* __restrict__ stats) {
+    __shared__ float tile[32][33];
+    float mn = INFINITY, mx = -INFINITY;
+    int nan = 0;
+    // tile: 32 voxels x 32 channels; blockDim (32, 8)
+    long long v0 = (long long)blockIdx.x * 32;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            long long v = v0 + i;
+            int c = c0 + threadIdx.x;
+            if (v < V && c < C) {
+                float a = x[v * C + c];
+                if (act == 1) a = tanhf(a);
+                else if (act == 2) a = fminf(fmaxf(a, -1.f), 1.f);
+                if (a != a) nan++;
+                mn = fminf(mn, a), mx = fmaxf(mx, a);
+                if (y_cl) y_cl[v * C + c] = a;
+                tile[i][threadIdx.x] = a;
+            }
+        }
+        __syncthreads();
+        if (y_cf) {
+            for (int i = threadIdx.y; i < 32; i += 8) {
+                int c = c0 + i;
+                long long v = v0 + threadIdx.x;
+                if (v < V && c < C) y_cf[(size_t)c * V + v] = tile[threadIdx.x][i];
+            }
+        }
+        __syncthreads();
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            nan += __shfl_xor_sync(0xffffffffu, nan, o);
+        }
+        if (threadIdx.x == 0) {
+            if (mn != INFINITY) atomicMin(&stats[0], float_to_ordered(mn));
+            if (mx != -INFINITY) atomicMax(&stats[1], float_to_ordered(mx));
+            if (nan) atomicAdd(&stats[2], nan);
+        }
+    }
+}
+
+__global__ void range_init_kernel(int* stats) {
+    stats[0] = 0x7fffffff;            // +max ordered
+    stats[1] = (int)0x80000000;       // min ordered
+    stats[2] = 0;
+    stats[3] = 0;
+}
+
+extern "C" int holo_range_init(int* stats4, void* stream) {
+    HOLO_CHECK_ARG(stats4, "holo_range_init: null");
+    range_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(stats4);
+    HOLO_CHECK_LAUNCH("holo_range_init");
+    return HOLO_OK;
+}
+
+extern "C" int holo_act_range(const float* x_cl, long long V, int C, int act, float* y_cl, float* y_cf, int* stats4,
+                              void* stream) {
+    HOLO_CHECK_ARG(x_cl && V > 0 && C > 0 && act >= 0 && act <= 2, "holo_act_range: bad args");
+    act_range_kernel<<<holo_cdiv(V, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(x_cl, V, C, act, y_cl, y_cf, stats4);
+    HOLO_CHECK_LAUNCH("holo_act_range");
+    return HOLO_OK;
+}

@@ -1,0 +1,197 @@
+"""Torch-tensor front end of the C-ABI (device pointers + sizes go straight to libholo_b200.so).
+
+PyTorch is used for device memory and streams only; every arithmetic op on the hot path is one of the CUDA
+kernels behind ``include/holo_b200.h``.  All tensors must be CUDA, contiguous and of the stated dtype --
+violations raise instead of silently copying.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import HoloError, lib
+
+_f = ctypes.c_float
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name: str = "tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HoloError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise HoloError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise HoloError(f"{name}: expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _host3(v: Sequence[float]):
+    return (ctypes.c_float * 3)(*[float(x) for x in v])
+
+
+# ------------------------------------------------------------------ renderer
+def raygen(R, T, focal, pp, xy, S: int, scene_extent: float, scene_center=(0.0, 0.0, 0.0)):
+    n_cam, n_rays = R.shape[0], xy.shape[0]
+    dev = R.device
+    origins = torch.empty(n_cam, n_rays, 3, device=dev)
+    dirs = torch.empty(n_cam, n_rays, 3, device=dev)
+    lengths = torch.empty(n_cam, n_rays, S, device=dev)
+    lib().call("holo_raygen", _ptr(R), _ptr(T), _ptr(focal), _ptr(pp), _ptr(xy), n_cam, n_rays, S,
+               float(scene_extent), ctypes.cast(_host3(scene_center), ctypes.c_void_p), _ptr(origins), _ptr(dirs),
+               _ptr(lengths), _stream())
+    return origins, dirs, lengths
+
+
+def collapse_and_pack_render_mlp(density_layers, skips, radiance_w, radiance_b, C: int):
+    """density_layers: list of (weight, bias) fp32 CUDA tensors; returns the packed fp32 buffer."""
+    dev = radiance_w.device
+    A = c = None
+    rows = 0
+    for li, (W, b) in enumerate(density_layers):
+        out_dim, in_total = W.shape
+        skip = 1 if (li in skips and li > 0) else 0
+        A_out = torch.empty(out_dim, C, dtype=torch.float64, device=dev)
+        c_out = torch.empty(out_dim, dtype=torch.float64, device=dev)
+        lib().call("holo_affine_compose_f64", _ptr(W), _ptr(b), out_dim, in_total,
+                   _ptr(A, torch.float64), _ptr(c, torch.float64), rows, C, skip,
+                   _ptr(A_out, torch.float64), _ptr(c_out, torch.float64), _stream())
+        A, c, rows = A_out, c_out, out_dim
+    H = rows - 1
+    E = radiance_w.shape[1] - H
+    n = lib().cdll.holo_render_mlp_packed_floats(H, C, E)
+    packed = torch.empty(n, device=dev)
+    lib().call("holo_pack_render_mlp", _ptr(A, torch.float64), _ptr(c, torch.float64), _ptr(radiance_w),
+               _ptr(radiance_b), H, C, E, _ptr(packed), _stream())
+    return packed, H, E
+
+
+def render_fwd(grid_dhwc, volume_extent: float, packed_mlp, hidden: int, n_harmonic: int, origins, dirs, lengths,
+               n_passes: int = 1, n_fine: int = 0, add_input_samples: bool = True, bg=(1.0, 1.0, 1.0),
+               background_opacity: float = 1e10, return_weights: bool = False, return_prev: bool = True):
+    D, H, W, C = grid_dhwc.shape
+    n_rays, S = lengths.shape
+    dev = grid_dhwc.device
+    S_last = S if n_passes == 1 else (S + n_fine if add_input_samples else n_fine)
+    out = {
+        "features": torch.empty(n_rays, 3, device=dev),
+        "depths": torch.empty(n_rays, 1, device=dev),
+        "masks": torch.empty(n_rays, 1, device=dev),
+        "weights": torch.empty(n_rays, S_last, device=dev) if return_weights else None,
+        "lengths": torch.empty(n_rays, S_last, device=dev) if n_passes > 1 else lengths,
+    }
+    prev = None
+    if n_passes > 1 and return_prev:
+        prev = {
+            "features": torch.empty(n_rays, 3, device=dev),
+            "depths": torch.empty(n_rays, 1, device=dev),
+            "masks": torch.empty(n_rays, 1, device=dev),
+            "weights": torch.empty(n_rays, S, device=dev) if return_weights else None,
+            "lengths": lengths,
+        }
+    lib().call("holo_render_fwd", _ptr(grid_dhwc), D, H, W, C, float(volume_extent), _ptr(packed_mlp), hidden,
+               n_harmonic, _ptr(origins), _ptr(dirs), _ptr(lengths), n_rays, S, n_passes, n_fine,
+               1 if add_input_samples else 0, ctypes.cast(_host3(bg), ctypes.c_void_p), float(background_opacity),
+               _ptr(out["features"]), _ptr(out["depths"]), _ptr(out["masks"]), _ptr(out["weights"]),
+               _ptr(out["lengths"]) if n_passes > 1 else None,
+               _ptr(prev["features"]) if prev else None, _ptr(prev["depths"]) if prev else None,
+               _ptr(prev["masks"]) if prev else None, _ptr(prev["weights"]) if prev else None, _stream())
+    out["prev"] = prev
+    return out
+
+
+# ------------------------------------------------------------------ denoiser
+def transpose2d(src, rows: int, cols: int, out=None):
+    if out is None:
+        out = torch.empty(cols * rows, device=src.device)
+    lib().call("holo_transpose2d", _ptr(src), _ptr(out), rows, cols, _stream())
+    return out
+
+
+def gn_stats(x1, C1, x2, C2, V, acc):
+    lib().call("holo_gn_stats", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64), _stream())
+
+
+def gn_finalize(acc, gamma, beta, film, C, V, a, b, eps=1e-5):
+    lib().call("holo_gn_finalize", _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta), _ptr(film), C, V, float(eps),
+               _ptr(a), _ptr(b), _stream())
+
+
+def gn_apply(x1, C1, x2, C2, V, a, b, silu: bool, y=None, y_hi=None, y_lo=None):
+    lib().call("holo_gn_apply", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(a), _ptr(b), 1 if silu else 0, _ptr(y),
+               _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16), _stream())
+
+
+def split_bf16(x, hi, lo):
+    lib().call("holo_split_bf16", _ptr(x), x.numel(), _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
+
+
+def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, w, bias, residual, Cout, out):
+    lib().call("holo_conv3d_simt", _ptr(x1), C1, _ptr(x2), C2, dims[0], dims[1], dims[2], ksize, stride,
+               1 if ups else 0, _ptr(w), _ptr(bias), _ptr(residual), Cout, _ptr(out), _stream())
+
+
+def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None) -> int:
+    """Returns the library status (0 ok, -3 unsupported shape); other errors raise."""
+    rc = lib().try_call("holo_conv3d_tc", _ptr(x_hi, torch.bfloat16), _ptr(x_lo, torch.bfloat16), Cin, dims[0],
+                        dims[1], dims[2], ksize, _ptr(w_hi, torch.bfloat16), _ptr(w_lo, torch.bfloat16), _ptr(bias),
+                        _ptr(residual), Cout, _ptr(out), _ptr(out_hi, torch.bfloat16), _ptr(out_lo, torch.bfloat16),
+                        _stream())
+    if rc not in (0, -3):
+        raise HoloError(f"holo_conv3d_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
+    return rc
+
+
+def attention_simt(qkv, T, heads, ch, out):
+    lib().call("holo_attention_simt", _ptr(qkv), T, heads, ch, _ptr(out), _stream())
+
+
+def timestep_embedding(t, dim, out):
+    lib().call("holo_timestep_embedding", _ptr(t, torch.int64), t.numel(), dim, _ptr(out), _stream())
+
+
+def linear_rows(x, W, b, M, in_dim, out_dim, silu_in, silu_out, out):
+    lib().call("holo_linear_rows", _ptr(x), _ptr(W), _ptr(b), M, in_dim, out_dim, 1 if silu_in else 0,
+               1 if silu_out else 0, _ptr(out), _stream())
+
+
+def ddpm_step(model_out, x_t, noise, t, coef1, coef2, logvar, clip: bool, x_prev, pred_x0=None):
+    n_batch = t.numel()
+    per = model_out.numel() // n_batch
+    lib().call("holo_ddpm_step", _ptr(model_out), _ptr(x_t), _ptr(noise), _ptr(t, torch.int64), _ptr(coef1),
+               _ptr(coef2), _ptr(logvar), per, n_batch, 1 if clip else 0, _ptr(x_prev), _ptr(pred_x0), _stream())
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1m_ac, out):
+    n_batch = t.numel()
+    lib().call("holo_q_sample", _ptr(x0), _ptr(noise), _ptr(t, torch.int64), _ptr(sqrt_ac), _ptr(sqrt_1m_ac),
+               x0.numel() // n_batch, n_batch, _ptr(out), _stream())
+
+
+def range_init(stats):
+    lib().call("holo_range_init", _ptr(stats, torch.int32), _stream())
+
+
+def act_range(x_cl, V, C, act: int, y_cl, y_cf, stats):
+    lib().call("holo_act_range", _ptr(x_cl), V, C, act, _ptr(y_cl), _ptr(y_cf), _ptr(stats, torch.int32), _stream())
+
+
+def decode_range(stats_host) -> Tuple[float, float, int]:
+    """stats4 (int32, host) -> (min, max, nan_count)."""
+    import struct
+
+    def dec(i):
+        i = int(i)
+        if i < 0:
+            i ^= 0x7FFFFFFF
+        return struct.unpack("f", struct.pack("i", i))[0]
+
+    return dec(stats_host[0]), dec(stats_host[1]), int(stats_host[2])

@@ -1,0 +1,141 @@
+/* holo_b200.h -- C-ABI of the B200-native HoloDiffusion hot path (libholo_b200.so).
+ *
+ * The reference (facebookresearch/holo_diffusion) has no FFI: its Python calls torch / pytorch3d ops directly.
+ * Every entry point below therefore names the reference Python call site (relative to /root/reference) whose
+ * arithmetic it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer, the
+ *     library never allocates; sizes of packed buffers are reported by the *_floats / *_bytes helpers.
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on that stream, no hidden syncs,
+ *     CUDA-graph capturable (holo_conv3d_tc additionally encodes TMA descriptors on the host per call).
+ *   - return 0 on success, negative on error; holo_last_error() gives the thread-local message.
+ *   - activations are fp32 channels-last: a (D,H,W) voxel grid with C channels is float[D*H*W][C]
+ *     ("DHWC"); V = D*H*W.  N (batch) is looped by the caller (the reference renders one grid per process,
+ *     holo_diffusion_model.py:326).
+ */
+#ifndef HOLO_B200_H
+#define HOLO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOLO_B200_VERSION 100
+
+int holo_version(void);
+const char* holo_last_error(void);
+int holo_device_info(int* sm_major, int* sm_minor, int* n_sm);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Renderer
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Full-grid evaluation rays for n_cam NDC perspective cameras.
+ * Replaces self.raysampler(target_cameras, evaluation_mode) -- holo_diffusion_model.py:442-448
+ * (pytorch3d AdaptiveRaySampler / NDCMultinomialRaysampler, configs/base.yaml:129-140).
+ * R (n_cam,3,3) row-vector convention X_cam = X_world R + T; xy (n_rays,2) NDC pixel centres, ray r = h*W + w.
+ * origins/dirs (n_cam,n_rays,3), lengths (n_cam,n_rays,S). */
+int holo_raygen(const float* R, const float* T, const float* focal, const float* pp, const float* xy, int n_cam,
+                int n_rays, int S, float scene_extent, const float* scene_center3_host, float* origins, float* dirs,
+                float* lengths, void* stream);
+
+/* One composition step of the density-net collapse in fp64 (y = A x + c through a Linear, optional skip concat).
+ * Replaces MLPWithInputSkips.forward for the activation-free layers -- custom_modules.py:108-112,133-160.
+ * A_in == NULL: first layer (A_out = W, c_out = b). */
+int holo_affine_compose_f64(const float* W, const float* b, int out_dim, int in_total, const double* A_in,
+                            const double* c_in, int rows, int C, int skip, double* A_out, double* c_out,
+                            void* stream);
+
+/* Pack collapsed density net (A_eff (H+1,C), c_eff (H+1)) + radiance layer Wr (3, H+E), br (3) for the render
+ * kernel.  RenderMLP parameters: holo_voxel_grid_implicit_function.py:62-105. */
+long long holo_render_mlp_packed_floats(int H, int C, int E);
+int holo_pack_render_mlp(const double* A_eff, const double* c_eff, const float* Wr, const float* br, int H, int C,
+                         int E, float* packed, void* stream);
+
+/* The fused renderer: per ray, n_passes x (trilinear sample -> RenderMLP -> emission-absorption compositing),
+ * with importance re-sampling of the ray depths between passes.
+ * Replaces HoloMultiPassEmissionAbsorptionRenderer._run_raymarcher (holo_multipass_ea.py:79-125) including
+ *   HoloVoxelGridImplicitFunction.forward (holo_voxel_grid_implicit_function.py:182-269),
+ *   EmissionAbsorptionRaymarcher (configs/base.yaml:149-159) and RayPointRefiner (configs/base.yaml:142-146),
+ * and the GenericModel._render chunk loop (holo_diffusion_model.py:451-457): one launch covers all rays.
+ * grid_dhwc (D,H,W,C); origins/dirs (n_rays,3); lengths (n_rays,S).
+ * Outputs of the last pass: features (n_rays,3), depths (n_rays), masks (n_rays), optional weights
+ * (n_rays,S_last), optional lengths_out (n_rays,S_last).  prev_* = outputs of pass 0 when n_passes == 2
+ * (RendererOutput.prev_stage); any of them may be NULL.  S_last = S (+ n_fine if add_input_samples). */
+int holo_render_fwd(const float* grid_dhwc, int D, int H, int W, int C, float volume_extent,
+                    const float* packed_mlp, int hidden, int n_harmonic, const float* origins, const float* dirs,
+                    const float* lengths, int n_rays, int S, int n_passes, int n_fine, int add_input_samples,
+                    const float* bg3_host, float background_opacity, float* features, float* depths, float* masks,
+                    float* weights, float* lengths_out, float* prev_features, float* prev_depths, float* prev_masks,
+                    float* prev_weights, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Denoiser (guided_diffusion UNetModel, unet.py:566-837) building blocks
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* (rows, cols) -> (cols, rows); NCDHW <-> DHWC is transpose2d over (C, V). */
+int holo_transpose2d(const float* src, float* dst, int rows, int cols, void* stream);
+
+/* GroupNorm32(32, C) -- nn.py:23-25,99-106 -- over channels-last x = cat(x1 (V,C1), x2 (V,C2)) (th.cat, unet.py:829).
+ * stats accumulates (sum, sumsq) per group in acc64[32][2] (must start zeroed; finalize re-zeroes it);
+ * finalize turns them into the per-channel affine y = x*a + b, folding gamma/beta and, when
+ * film_scale_shift (2C: scale then shift) is given, the FiLM h*(1+scale)+shift of unet.py:248-252;
+ * apply writes act(x*a+b) (act = SiLU, unet.py:184,208) as fp32 and/or as a bf16 hi/lo pair. */
+int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64, void* stream);
+int holo_gn_finalize(double* acc64, const float* gamma, const float* beta, const float* film_scale_shift, int C,
+                     long long V, float eps, float* a, float* b, void* stream);
+int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a, const float* b,
+                  int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
+int holo_split_bf16(const float* x, long long n, void* hi_bf16, void* lo_bf16, void* stream);
+
+/* Exact-fp32 implicit-GEMM convolution (nn.Conv3d 3^3/1^3, stride 1|2, padding k/2; nn.Conv1d k=1):
+ * unet.py:185,211,222,657,792 / Downsample :129-131 / Upsample :89-97 (upsample2x folds F.interpolate nearest x2)
+ * / AttentionBlock qkv, proj_out :383,392.  Weights pre-packed as [tap][Cin][Cout]; out = conv + bias (+ residual). */
+int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, int Hin, int Win, int ksize,
+                     int stride, int upsample2x, const float* w_tap_cin_cout, const float* bias,
+                     const float* residual, int Cout, float* out, void* stream);
+
+/* tcgen05 (5th-gen tensor core) implicit-GEMM convolution, 3xBF16 split operands, fp32 TMEM accumulation.
+ * Same contract as holo_conv3d_simt for ksize 1|3, stride 1, no upsample, one source; operands are bf16 hi/lo
+ * pairs: x_hi/x_lo (V,Cin) channels-last, w_hi/w_lo [Cout][tap][Cin] (K-major).  Cin % 64 == 0, Cout % 16 == 0,
+ * Cout <= 256 per call.  Returns HOLO_ERR_UNSUPPORTED (-3) for shapes it does not take. */
+int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, const void* w_hi,
+                   const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
+                   void* out_hi_bf16, void* out_lo_bf16, void* stream);
+
+/* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
+int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);
+
+/* timestep_embedding -- nn.py:109-127 -- and the small Linear layers (time_embed unet.py:646-650, emb_layers :199-205):
+ * out[m][o] = act_out(b[o] + sum_i W[o][i] * act_in(x[m][i])) with act = SiLU when the flag is set. */
+int holo_timestep_embedding(const long long* t_i64, int n, int dim, float* out, void* stream);
+int holo_linear_rows(const float* x, const float* W, const float* b, int M, int in_dim, int out_dim, int silu_in,
+                     int silu_out, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Diffusion (gaussian_diffusion.py) and model glue (holo_diffusion_model.py)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* p_sample for ModelMeanType.START_X / ModelVarType.FIXED_SMALL -- gaussian_diffusion.py:459-508 (+ :318,:229-251).
+ * coef1/coef2/logvar: device fp32 copies of posterior_mean_coef1/2 and posterior_log_variance_clipped (:150-187),
+ * indexed on the device by t (n_batch int64).  noise may be NULL (treated as 0). */
+int holo_ddpm_step(const float* model_out, const float* x_t, const float* noise, const long long* t_i64,
+                   const float* coef1, const float* coef2, const float* logvar, long long per_sample, int n_batch,
+                   int clip_denoised, float* x_prev, float* pred_xstart, void* stream);
+/* q_sample -- gaussian_diffusion.py:209-227. */
+int holo_q_sample(const float* x0, const float* noise, const long long* t_i64, const float* sqrt_ac,
+                  const float* sqrt_1m_ac, long long per_sample, int n_batch, float* out, void* stream);
+
+/* tanh / clamp + the range statistics behind `assert voxel_features.min() >= -1 and ...max() <= 1`
+ * (holo_diffusion_model.py:381,424-428): one pass writes the channels-last copy (renderer input), the
+ * channels-first copy (API tensor) and min/max/nan-count into stats4 (ordered-int encoding; see range_init). */
+int holo_range_init(int* stats4, void* stream);
+int holo_act_range(const float* x_cl, long long V, int C, int act, float* y_cl, float* y_cf, int* stats4,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLO_B200_H */

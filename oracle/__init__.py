@@ -1,0 +1,29 @@
+"""CPU oracle for the HoloDiffusion hot path (TEST INFRASTRUCTURE ONLY).
+
+This package restates, op for op in plain PyTorch-CPU fp32 (fp64 on request), the
+arithmetic of the reference path named in SURVEY.md section 8:
+
+  * ``render_oracle``    -- ray generation, trilinear voxel sampling, RenderMLP,
+                            emission-absorption ray marching, importance refinement,
+                            multi-pass + chunked rendering.
+  * ``unet_oracle``      -- the guided-diffusion 3-D UNet as a pure function of a
+                            reference-named state dict.
+  * ``diffusion_oracle`` -- the DDPM schedule tables and the ancestral step.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and only as the checker / CPU baseline.
+The product package ``holo_diffusion_b200`` never imports it.
+
+Pinning status
+--------------
+* UNet / diffusion: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified
+  reference modules from ``/root/reference`` (pure torch, importable) and the oracle is
+  checked against their outputs; the vectors are committed under ``tests/golden``.
+* Renderer: **parity unpinned**.  Its arithmetic lives in the un-vendored dependency
+  ``pytorch3d==0.7.4`` (reference ``environment.yaml:139``), absent from this image and
+  from ``/root/reference``; the reference's own tests only check for NaNs
+  (``holo_diffusion/tests/test_voxel_grid_implicit_function.py:55,77,93,117``).  The
+  restatement follows the published pytorch3d 0.7.4 algorithm and the reference call sites
+  cited per function.  An optional ``importorskip("pytorch3d")`` tier checks it against the
+  real thing wherever pytorch3d is installed.
+"""
