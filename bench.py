@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: rendered views/sec for a 64^3 x 32ch grid at 256^2, 64 pts/ray (BASELINE.json).
+
+One "step" = what the reference does per rendered view in generate_samples.py
+(/root/reference/holo_diffusion/holo_diffusion_model.py:420-457): g = tanh(UNet(g, t=0)), range asserts,
+ray sampling, and the multi-pass emission-absorption render of one 256x256 view (configs/base.yaml sampling:
+64 coarse + 16 importance samples per ray, 2 passes).  Synthetic grid / random-init weights (no network).
+
+  python bench.py --gpus N --steps K --warmup W          # our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host cores (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+METRIC = "rendered views/sec for 64^3 x 32ch grid @ 256^2, 64 pts/ray"
+UNET_ARGS = dict(model_channels=64, num_res_blocks=2, num_heads=2, channel_mult=[1, 1, 2, 4, 8], attention_resolutions=[4, 8])
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--passes", type=int, default=2)
+    ap.add_argument("--resol", type=int, default=64)
+    ap.add_argument("--channels", type=int, default=32)
+    ap.add_argument("--image", type=int, default=256)
+    ap.add_argument("--pts", type=int, default=64)
+    ap.add_argument("--fine", type=int, default=16)
+    ap.add_argument("--no-tc", action="store_true", help="force the exact-fp32 CUDA-core convolutions")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"cfg#2: tanh(UNet(g,t=0)) + {a.passes}-pass EA render of one view per step; "
+                    f"grid {a.resol}^3 x {a.channels}ch, base UNet args (configs/base.yaml:93-98), image {a.image}^2, "
+                    f"{a.pts}{'+' + str(a.fine) if a.passes > 1 else ''} pts/ray",
+        "passes": a.passes, "global_batch_views_per_step": n_gpus,
+        "parallelism": f"replica x{n_gpus} (one view per GPU per step" + (", NCCL gather of images to rank 0)" if n_gpus > 1 else ")"),
+        "l2": "explicit L2 flush (256 MiB memset) between timed iterations, outside the event brackets",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(a, rows_sample: int, seed=0):
+    """One bounded sample of the step on the CPU: full UNet forward + tanh, render of `rows_sample` image rows
+    (chunked like configs/teddybear.yaml:112), scaled to the full image.  Returns (seconds_per_view, detail)."""
+    from fixtures import make_grid, make_mlp
+    from oracle import render_oracle as ro
+    from oracle import unet_oracle as uo
+    torch.set_num_threads(os.cpu_count())
+    C, R, HW, S = a.channels, a.resol, a.image, a.pts
+    sd = uo.make_unet_state_dict(C, C, seed=2)
+    mlp = make_mlp(C)
+    grid = make_grid(C, R, seed)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        g = torch.tanh(uo.unet_forward(sd, grid, torch.zeros(1, dtype=torch.long)))
+    t_unet = time.perf_counter() - t0
+    cams = ro.simple_360_cameras(8)
+    b = ro.sample_rays(cams[0], HW, HW, S)
+    rows = list(range(0, HW, max(1, HW // rows_sample)))[:rows_sample]
+    sub = ro.OracleRayBundle(b.origins[:, rows], b.directions[:, rows], b.lengths[:, rows], b.xys[:, rows])
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        ro.render_chunked(mlp, g, sub, R, 8.0, a.passes, a.fine, chunk_size_grid=163840)
+    t_render = (time.perf_counter() - t1) * (HW / len(rows))
+    return t_unet + t_render, {"t_unet_s": round(t_unet, 3), "t_render_full_est_s": round(t_render, 3), "rows": len(rows)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = max(4, a.image // 16)
+    for _ in range(min(a.warmup, 1)):
+        cpu_reference_step(a, rows)
+    ts, det = [], None
+    for _ in range(a.steps):
+        t, det = cpu_reference_step(a, rows)
+        ts.append(t)
+    sec = sum(ts) / len(ts)
+    v = 1.0 / sec
+    sample = f"full UNet fwd + {det['rows']}/{a.image} image rows rendered (chunk 163840), render time scaled to the full view"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "views/s", "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+           "cpu_baseline": {"value": v, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "detail": det}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index: int):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.2] or [s for (_, s) in self.samples[-3:]]
+        sm, mx, reasons = [], 0, set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def build_model(a, dev):
+    import holo_diffusion_b200 as hd
+    from fixtures import make_mlp
+    from oracle import unet_oracle as uo  # only for the seeded state-dict FIXTURE (weights), not for compute
+    un = dict(UNET_ARGS)
+    un["use_tensor_cores"] = not a.no_tc
+    model = hd.HoloDiffusionModel(
+        resol=a.resol, feature_size=a.channels, num_passes=a.passes, render_image_width=a.image, render_image_height=a.image,
+        net_3d_SimpleUnet3D_args=un, raysampler_AdaptiveRaySampler_args=dict(n_pts_per_ray_evaluation=a.pts),
+        renderer_HoloMultiPassEmissionAbsorptionRenderer_args=dict(
+            n_pts_per_ray_fine_evaluation=a.fine, raymarcher_EmissionAbsorptionRaymarcher_args=dict(bg_color=(1.0, 1.0, 1.0))))
+    model.net_3d._net.load_state_dict(uo.make_unet_state_dict(a.channels, a.channels, seed=2), strict=True)
+    model._implicit_functions[0]._fn.render_mlp.load_state_dict(make_mlp(a.channels), strict=True)
+    return model.to(dev)
+
+
+def run_ours(a):
+    import holo_diffusion_b200 as hd
+    from holo_diffusion_b200 import _lib
+    from fixtures import make_grid
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    # count kernel launches made through the C-ABI
+    counter = {"n": 0}
+    L = _lib.lib()
+    orig_call, orig_try = L.call, L.try_call
+
+    def call(name, *args):
+        counter["n"] += 1
+        return orig_call(name, *args)
+
+    def try_call(name, *args):
+        counter["n"] += 1
+        return orig_try(name, *args)
+
+    L.call, L.try_call = call, try_call
+
+    model = build_model(a, dev)
+    C, R, HW = a.channels, a.resol, a.image
+    grid_host = make_grid(C, R, seed=100 + rank).pin_memory()
+    cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, (-0.0396, -0.8306, -0.5554), 3.2)
+    cam_host = cams[[rank % 8]]
+    grid_dev = grid_host.to(dev)
+    cam_dev = cams[[rank % 8]].to(dev)
+    img_host = torch.empty(5, HW, HW).pin_memory()
+    gather_buf = torch.empty(world, 5, HW, HW, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def pack_images(preds):
+        return torch.cat([preds["images_render"][0], preds["depths_render"][0], preds["masks_render"][0]], 0).contiguous()
+
+    def step_device():
+        preds = model(camera=cam_dev, voxel_features=grid_dev)
+        img = pack_images(preds)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, img)
+        return img
+
+    def step_e2e():
+        g = grid_host.to(dev, non_blocking=True)
+        c = hd.PerspectiveCameras(cam_host.focal_length, cam_host.principal_point, cam_host.R, cam_host.T).to(dev)
+        preds = model(camera=c, voxel_features=g)
+        img = pack_images(preds)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, img)
+        img_host.copy_(img, non_blocking=True)
+        return img
+
+    def timed(fn, steps, warmup, clocks=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        counter["n"] = 0
+        t0 = time.perf_counter()
+        if clocks:
+            clocks.start()
+            time.sleep(0.25)
+            t0 = time.perf_counter()
+        for s, e in ev:
+            flush.zero_()  # L2 flush, outside the event bracket
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        clk = clocks.stop(t0, t1) if clocks else None
+        launches = counter["n"]
+        if dist:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clk
+
+    clocks = Clocks(local) if rank == 0 else None
+    ms_dev, launches, clk = timed(step_device, a.steps, max(a.warmup, 3), clocks)
+    ms_e2e, _, _ = timed(step_e2e, a.steps, 2)
+    views = a.steps * world
+    value = views / (ms_dev / 1e3)
+    e2e = views / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 convolution): events around every launch, separate pass
+    roof = None
+    ex = model.net_3d._exec
+    if rank == 0:
+        from holo_diffusion_b200 import ops
+        rec = []
+        orig_tc, orig_simt = ops.conv3d_tc, ops.conv3d_simt
+
+        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo)
+            e.record()
+            rec.append(("tc", 2.0 * dims[0] * dims[1] * dims[2] * Cout * Cin * k ** 3, s, e))
+            return rc
+
+        def simt(x1, C1, x2, C2, dims, k, stride, ups, w, bias, res, Cout, out):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig_simt(x1, C1, x2, C2, dims, k, stride, ups, w, bias, res, Cout, out)
+            e.record()
+            rec.append(("simt", 2.0 * out.shape[0] * Cout * (C1 + C2) * k ** 3, s, e))
+
+        ops.conv3d_tc, ops.conv3d_simt = tc, simt
+        for _ in range(3):
+            step_device()
+        torch.cuda.synchronize()
+        ops.conv3d_tc, ops.conv3d_simt = orig_tc, orig_simt
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        by = {}
+        for kind, fl, s, e in rec:
+            d = by.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += fl
+            d[1] += s.elapsed_time(e)
+            d[2] += 1
+        kind = "tc" if "tc" in by else "simt"
+        fl, ms, n = by[kind]
+        ach = fl / (ms / 1e3) / 1e12
+        roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3d, 3xBF16)" if kind == "tc" else "conv_simt_kernel (fp32 CUDA cores)",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "launches_per_step": n // 3, "avg_launch_us": ms * 1e3 / n,
+                "algorithmic_flops_per_launch_avg": fl / n,
+                "executed_tensor_tflops": ach * 3 if kind == "tc" else None,
+                "executed_frac": ach * 3 / peak_tf if kind == "tc" else None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
+                "share_of_step_ms": {k: v[1] / 3 for k, v in by.items()},
+                "note": "achieved counts ALGORITHMIC conv FLOPs (2*V*Cout*Cin*k^3); the kernel executes 3 bf16 MMAs per "
+                        "product (hi*hi + hi*lo + lo*hi), see executed_*"}
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        sec, det = cpu_reference_step(a, max(4, a.image // 16))
+        cpu = {"value": 1.0 / sec, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"full UNet fwd + {det['rows']}/{a.image} image rows rendered, render time scaled to the full view", **det}
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": a.steps,
+               "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16x3 (3-term bf16 split, fp32 accumulate) convs; f32 elsewhere" if ex.tc_calls else "f32",
+               "data": "synthetic", "config": workload_config(a, world),
+               "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / a.steps,
+                       "h2d_bytes_per_step": grid_host.numel() * 4 + 4 * (9 + 3 + 2 + 2), "d2h_bytes_per_step": img_host.numel() * 4 + 16},
+               "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "tc_convs_per_step": ex.tc_calls // max(1, (ex.tc_calls + ex.simt_calls) and 1) if False else None}
+        out.pop("tc_convs_per_step")
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -232,22 +232,24 @@ extern "C" int holo_split_bf16(const float* x, long long n, void* hi_bf16, void*
 // ------------------------------------------------------------------------------------------------
 // timestep embedding + small dense layers (M = batch of timesteps, tiny)
 // ------------------------------------------------------------------------------------------------
-__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim,
+                                          const float* __restrict__ freqs, float* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int half = dim / 2;
     if (i < n * half) {
         int b = i / half, k = i % half;
-        // th.exp(-log(10000) * arange(half) / half), then args = t.float() * freqs
-        float f = expf(-logf(10000.0f) * (float)k / (float)half);
-        float arg = (float)t[b] * f;
+        // freqs = th.exp(-log(10000) * arange(half) / half) is built on the host exactly as the reference does
+        // (nn.py:119-121, a CPU tensor moved to the device); args = t.float() * freqs
+        float arg = (float)t[b] * freqs[k];
         out[b * dim + k] = cosf(arg);
         out[b * dim + half + k] = sinf(arg);
     }
 }
 
-extern "C" int holo_timestep_embedding(const long long* t_i64, int n, int dim, float* out, void* stream) {
-    HOLO_CHECK_ARG(t_i64 && out && n > 0 && dim > 0 && dim % 2 == 0, "holo_timestep_embedding: bad args");
-    timestep_embedding_kernel<<<holo_cdiv(n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t_i64, n, dim, out);
+extern "C" int holo_timestep_embedding(const long long* t_i64, int n, int dim, const float* freqs, float* out,
+                                       void* stream) {
+    HOLO_CHECK_ARG(t_i64 && out && freqs && n > 0 && dim > 0 && dim % 2 == 0, "holo_timestep_embedding: bad args");
+    timestep_embedding_kernel<<<holo_cdiv(n * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t_i64, n, dim, freqs, out);
     HOLO_CHECK_LAUNCH("holo_timestep_embedding");
     return HOLO_OK;
 }

@@ -503,12 +503,12 @@ extern "C" int holo_render_fwd(const float* grid_dhwc, int D, int H, int W, int 
                                float* features, float* depths, float* masks, float* weights, float* lengths_out,
                                float* prev_features, float* prev_depths, float* prev_masks, float* prev_weights,
                                void* stream) {
+    if (n_rays == 0) return HOLO_OK;
     HOLO_CHECK_ARG(grid_dhwc && packed_mlp && origins && dirs && lengths, "holo_render_fwd: null input");
     HOLO_CHECK_ARG(features && depths && masks, "holo_render_fwd: null output");
     HOLO_CHECK_ARG(n_passes == 1 || n_passes == 2, "holo_render_fwd: n_passes must be 1 or 2 (got %d)", n_passes);
     HOLO_CHECK_ARG(S >= 2 && (n_passes == 1 || (n_fine >= 1 && S >= 3)), "holo_render_fwd: bad S/n_fine");
     HOLO_CHECK_ARG(D > 1 && H > 1 && W > 1, "holo_render_fwd: grid must be at least 2^3");
-    if (n_rays == 0) return HOLO_OK;
     RenderParams P;
     P.grid = grid_dhwc;
     P.D = D, P.Hh = H, P.Ww = W;

@@ -1,0 +1,141 @@
+"""``HoloDiffusionModel`` -- the sampling / evaluation branch of the reference model on the CUDA kernels.
+
+Mirrors /root/reference/holo_diffusion/holo_diffusion_model.py: constructor fields (:47-75 + GenericModel's
+render_image_width/height, raysampler/renderer argument groups), ``sample_random_voxel_features[_progressive]``
+:173-199 and the keyword-only ``forward`` :201-214 for the path ``generate_samples.py`` drives
+(image_rgb=None, voxel_features given, evaluation_mode=EVALUATION):
+    asserts on the grid range :381 -> ``voxel_features = tanh(net_3d(voxel_features, t=0))`` :420-428 ->
+    bind ``voxel_grid_features`` :431-438 -> ray sampler :442-448 -> ``_render`` :451-457 -> preds :469-523.
+The view-pooling encoder, the training branch and the losses are out of this round's scope and raise.
+Parameter names follow the reference so that checkpoints load: ``net_3d._net.*``,
+``_implicit_functions.{i}._fn.render_mlp.*``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .cameras import AdaptiveRaySampler, ImplicitronRayBundle, PerspectiveCameras
+from .diffusion import ImplicitronGaussianDiffusion
+from .renderer import (EvaluationMode, HoloMultiPassEmissionAbsorptionRenderer, HoloVoxelGridImplicitFunction,
+                       ImplicitFunctionWrapper, RendererOutput)
+from .unet import SimpleUnet3D
+
+
+@dataclass
+class ImplicitronRender:
+    image_render: Optional[torch.Tensor] = None
+    depth_render: Optional[torch.Tensor] = None
+    mask_render: Optional[torch.Tensor] = None
+
+
+class HoloDiffusionModel(nn.Module):
+    def __init__(self, resol: int = 16, volume_extent: float = 8.0, feature_size: int = 64, num_passes: int = 2,
+                 render_image_width: int = 256, render_image_height: int = 256, net_3d_enabled: bool = True,
+                 net_3d_class_type: str = "SimpleUnet3D", net_3d_SimpleUnet3D_args: Optional[dict] = None,
+                 diffusion_enabled: bool = True, diffusion_args: Optional[dict] = None,
+                 raysampler_class_type: str = "AdaptiveRaySampler", raysampler_AdaptiveRaySampler_args: Optional[dict] = None,
+                 renderer_class_type: str = "HoloMultiPassEmissionAbsorptionRenderer",
+                 renderer_HoloMultiPassEmissionAbsorptionRenderer_args: Optional[dict] = None,
+                 implicit_function_class_type: str = "HoloVoxelGridImplicitFunction",
+                 implicit_function_HoloVoxelGridImplicitFunction_args: Optional[dict] = None, **unused):
+        super().__init__()
+        if implicit_function_class_type != "HoloVoxelGridImplicitFunction":
+            raise ValueError(f"{type(self)} supports only HoloVoxelGridImplicitFunction!")
+        if net_3d_class_type != "SimpleUnet3D" or raysampler_class_type != "AdaptiveRaySampler" or \
+                renderer_class_type != "HoloMultiPassEmissionAbsorptionRenderer":
+            raise NotImplementedError("plug-in type not built")
+        self.resol, self.volume_extent, self.feature_size, self.num_passes = resol, volume_extent, feature_size, num_passes
+        self.render_image_width, self.render_image_height = render_image_width, render_image_height
+        self.net_3d_enabled, self.diffusion_enabled = net_3d_enabled, diffusion_enabled
+        self.net_3d = None
+        if net_3d_enabled:
+            a = dict(net_3d_SimpleUnet3D_args or {})
+            a.update(in_channels=feature_size, out_channels=feature_size, image_size=resol)
+            self.net_3d = SimpleUnet3D(**a)
+        self.diffusion = ImplicitronGaussianDiffusion(**(diffusion_args or {})) if diffusion_enabled else None
+        rs = dict(raysampler_AdaptiveRaySampler_args or {})
+        self.raysampler = AdaptiveRaySampler(image_width=render_image_width, image_height=render_image_height, **rs)
+        self.renderer = HoloMultiPassEmissionAbsorptionRenderer(**(renderer_HoloMultiPassEmissionAbsorptionRenderer_args or {}))
+        ia = dict(implicit_function_HoloVoxelGridImplicitFunction_args or {})
+        ia.update(resol=resol, volume_extent=volume_extent, n_hidden=feature_size, feature_dim=0)
+        wrapper = ImplicitFunctionWrapper(HoloVoxelGridImplicitFunction(**ia))
+        self._implicit_functions = nn.ModuleList([wrapper for _ in range(num_passes)])
+        self._range_stats: Optional[torch.Tensor] = None
+        self._t0: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ sampling
+    def sample_random_voxel_features_progressive(self):
+        assert self.net_3d_enabled and self.diffusion_enabled
+        for sample in self.diffusion.p_sample_loop_progressive(
+                model=self.net_3d, shape=(1, self.feature_size, self.resol, self.resol, self.resol), clip_denoised=True,
+                progress=False):
+            yield torch.clip(sample["sample"], -1.0, 1.0)
+
+    def sample_random_voxel_features(self) -> torch.Tensor:
+        assert self.net_3d_enabled and self.diffusion_enabled
+        return self.diffusion.p_sample_loop(model=self.net_3d,
+                                            shape=(1, self.feature_size, self.resol, self.resol, self.resol),
+                                            clip_denoised=True, progress=False)
+
+    # ------------------------------------------------------------------ range asserts without a sync per assert
+    def _check_range(self, where: str):
+        mn, mx, nan = ops.decode_range(self._range_stats.cpu().tolist())
+        assert nan == 0 and mn >= -1.0 and mx <= 1.0, f"voxel features out of [-1, 1] ({where}): min {mn} max {mx} nan {nan}"
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, *, image_rgb: Optional[torch.Tensor] = None, camera: PerspectiveCameras,
+                fg_probability=None, mask_crop=None, depth_map=None, sequence_name=None, frame_timestamp=None,
+                evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, voxel_features: Optional[torch.Tensor] = None,
+                **kwargs) -> Dict[str, Any]:
+        if image_rgb is not None:
+            raise NotImplementedError("view-pooling encoder path (images -> voxel grid) is a 'next' row (SURVEY 8f)")
+        if evaluation_mode != EvaluationMode.EVALUATION:
+            raise NotImplementedError("training branch is a 'next' row (SURVEY 8f)")
+        target_cameras = camera[[0]]  # n_targets = 1 (holo_diffusion_model.py:263-273,315)
+        dev = target_cameras.device
+        if voxel_features is None:
+            voxel_features = self.sample_random_voxel_features()
+        assert voxel_features.shape[0] == 1, "only one single voxel grid is supported per GPU"
+        assert voxel_features.shape[1] == self.feature_size, "Wrong voxel feature size!"
+        C, R = self.feature_size, self.resol
+        V = R ** 3
+        if self._range_stats is None or self._range_stats.device != dev:
+            self._range_stats = torch.empty(4, dtype=torch.int32, device=dev)
+            self._t0 = torch.zeros(1, dtype=torch.int64, device=dev)
+        x = voxel_features.contiguous().float()
+        x_cl = ops.transpose2d(x.reshape(-1), C, V).view(V, C)
+        ops.range_init(self._range_stats)
+        if self.net_3d_enabled:
+            # voxel_features = tanh(net_3d(voxel_features, t=0)); the input-range assert (:381) and the two
+            # output-range asserts (:426,:428) are evaluated from one fused min/max pass each, checked once below
+            ops.act_range(x_cl, V, C, 0, None, None, self._range_stats)
+            y_cl = self.net_3d._exec.forward_cl(x_cl, (R, R, R), self._t0)
+            grid_cl = torch.empty(V, C, device=dev)
+            grid_cf = torch.empty(C * V, device=dev)
+            ops.act_range(y_cl, V, C, 1, grid_cl, grid_cf, self._range_stats)
+            voxel_features = grid_cf.view(1, C, R, R, R)
+        else:
+            grid_cl = torch.empty(V, C, device=dev)
+            ops.act_range(x_cl, V, C, 0, grid_cl, None, self._range_stats)
+        for func in self._implicit_functions:
+            func.bind_args(voxel_grid_features=voxel_features, voxel_grid_features_channels_last=grid_cl.view(R, R, R, C))
+        ray_bundle = self.raysampler(target_cameras, evaluation_mode)
+        rendered = self.renderer(ray_bundle, list(self._implicit_functions), evaluation_mode)
+        for func in self._implicit_functions:
+            func.unbind_args()
+        self._check_range("input / tanh(net_3d) output")  # single D2H of 16 bytes, after all work is queued
+        preds: Dict[str, Any] = {"rendered": rendered, "ray_bundle": ray_bundle, "voxel_features": voxel_features}
+        preds["images_render"] = rendered.features.permute(0, 3, 1, 2)
+        preds["depths_render"] = rendered.depths.permute(0, 3, 1, 2)
+        preds["masks_render"] = rendered.masks.permute(0, 3, 1, 2)
+        preds["implicitron_render"] = ImplicitronRender(image_render=preds["images_render"],
+                                                        depth_render=preds["depths_render"],
+                                                        mask_render=preds["masks_render"])
+        preds["objective"] = None
+        return preds

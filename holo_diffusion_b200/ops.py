@@ -154,8 +154,22 @@ def attention_simt(qkv, T, heads, ch, out):
     lib().call("holo_attention_simt", _ptr(qkv), T, heads, ch, _ptr(out), _stream())
 
 
+_FREQS = {}
+
+
+def timestep_freqs(dim: int, device) -> torch.Tensor:
+    """th.exp(-math.log(10000) * th.arange(half) / half) on the CPU, then moved -- nn.py:119-121."""
+    import math
+    key = (dim, str(device))
+    if key not in _FREQS:
+        half = dim // 2
+        _FREQS[key] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device)
+    return _FREQS[key]
+
+
 def timestep_embedding(t, dim, out):
-    lib().call("holo_timestep_embedding", _ptr(t, torch.int64), t.numel(), dim, _ptr(out), _stream())
+    lib().call("holo_timestep_embedding", _ptr(t, torch.int64), t.numel(), dim, _ptr(timestep_freqs(dim, t.device)),
+               _ptr(out), _stream())
 
 
 def linear_rows(x, W, b, M, in_dim, out_dim, silu_in, silu_out, out):

@@ -1,0 +1,408 @@
+"""B200-native 3-D UNet denoiser behind the reference's ``Unet3DBase`` plug-in surface.
+
+Mirrors (names, constructor arguments, state-dict keys, forward signature):
+  * ``SimpleUnet3D``  -- /root/reference/holo_diffusion/utils/diffusion_utils.py:41-86
+  * the wrapped ``UNetModel`` -- /root/reference/holo_diffusion/guided_diffusion/unet.py:566-837
+so that reference checkpoints (``net_3d._net.*`` keys) load unchanged.  The torch modules below only *hold
+parameters*; ``forward`` never calls a torch compute op: it walks the block list and launches the CUDA kernels
+of ``libholo_b200.so`` (channels-last activations, GroupNorm folded into a per-channel affine, FiLM folded into
+that affine, skip-concat consumed in place, nearest-upsample folded into the following convolution).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+GN_GROUPS = 32
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parameter containers (same attribute paths as the reference modules => same state-dict keys)
+# ----------------------------------------------------------------------------------------------------------
+class _ResParams(nn.Module):
+    def __init__(self, cin: int, cout: int, emb_dim: int):
+        super().__init__()
+        self.cin, self.cout = cin, cout
+        self.in_layers = nn.Sequential(nn.GroupNorm(GN_GROUPS, cin), nn.SiLU(), nn.Conv3d(cin, cout, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_dim, 2 * cout))
+        self.out_layers = nn.Sequential(nn.GroupNorm(GN_GROUPS, cout), nn.SiLU(), nn.Dropout(0.0),
+                                        nn.Conv3d(cout, cout, 3, padding=1))
+        self.skip_connection = nn.Identity() if cin == cout else nn.Conv3d(cin, cout, 1)
+
+
+class _AttnParams(nn.Module):
+    def __init__(self, ch: int, heads: int):
+        super().__init__()
+        self.ch, self.heads = ch, heads
+        self.norm = nn.GroupNorm(GN_GROUPS, ch)
+        self.qkv = nn.Conv1d(ch, 3 * ch, 1)
+        self.proj_out = nn.Conv1d(ch, ch, 1)
+        with torch.no_grad():  # zero_module(proj_out), unet.py:392
+            self.proj_out.weight.zero_()
+            self.proj_out.bias.zero_()
+
+
+class _DownParams(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.op = nn.Conv3d(ch, ch, 3, stride=2, padding=1)
+
+
+class _UpParams(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv3d(ch, ch, 3, padding=1)
+
+
+class UNetParams(nn.Module):
+    """Parameter tree of guided_diffusion ``UNetModel(dims=3, use_scale_shift_norm=True, resblock_updown=False,
+    conv_resample=True, homogeneous_resample=True, num_head_channels=-1)``."""
+
+    def __init__(self, in_channels: int, model_channels: int, out_channels: int, num_res_blocks: int,
+                 attention_resolutions: Sequence[int], channel_mult: Sequence[int], num_heads: int):
+        super().__init__()
+        self.in_channels, self.out_channels, self.model_channels = in_channels, out_channels, model_channels
+        self.num_heads = num_heads
+        emb = 4 * model_channels
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, emb), nn.SiLU(), nn.Linear(emb, emb))
+        width = int(channel_mult[0] * model_channels)
+        blocks: List[nn.Module] = [nn.Sequential(nn.Conv3d(in_channels, width, 3, padding=1))]
+        skip_widths = [width]
+        ds = 1
+        n_levels = len(channel_mult)
+        for level, mult in enumerate(channel_mult):
+            target = int(mult * model_channels)
+            for _ in range(num_res_blocks):
+                layers: List[nn.Module] = [_ResParams(width, target, emb)]
+                width = target
+                if ds in attention_resolutions:
+                    layers.append(_AttnParams(width, num_heads))
+                blocks.append(nn.Sequential(*layers))
+                skip_widths.append(width)
+            if level + 1 < n_levels:
+                blocks.append(nn.Sequential(_DownParams(width)))
+                skip_widths.append(width)
+                ds *= 2
+        self.input_blocks = nn.ModuleList(blocks)
+        self.middle_block = nn.Sequential(_ResParams(width, width, emb), _AttnParams(width, num_heads),
+                                          _ResParams(width, width, emb))
+        ups: List[nn.Module] = []
+        for level in reversed(range(n_levels)):
+            target = int(channel_mult[level] * model_channels)
+            for i in range(num_res_blocks + 1):
+                layers = [_ResParams(width + skip_widths.pop(), target, emb)]
+                width = target
+                if ds in attention_resolutions:
+                    layers.append(_AttnParams(width, num_heads))
+                if level > 0 and i == num_res_blocks:
+                    layers.append(_UpParams(width))
+                    ds //= 2
+                ups.append(nn.Sequential(*layers))
+        self.output_blocks = nn.ModuleList(ups)
+        self.out = nn.Sequential(nn.GroupNorm(GN_GROUPS, width), nn.SiLU(),
+                                 nn.Conv3d(int(channel_mult[0] * model_channels), out_channels, 3, padding=1))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# executor
+# ----------------------------------------------------------------------------------------------------------
+class _Act:
+    """A channels-last activation made of one or two sources (the un-materialised skip concat)."""
+
+    __slots__ = ("x1", "c1", "x2", "c2", "dims")
+
+    def __init__(self, x1, c1, dims, x2=None, c2=0):
+        self.x1, self.c1, self.x2, self.c2, self.dims = x1, c1, x2, c2, dims
+
+    @property
+    def C(self):
+        return self.c1 + self.c2
+
+    @property
+    def V(self):
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+
+class _PackedConv:
+    """Weights of one convolution in the kernel layouts, re-packed when the parameter changes."""
+
+    def __init__(self, mod: nn.Module):
+        self.mod = mod
+        self.version = None
+        self.w_simt = self.bias = self.w_hi = self.w_lo = None
+
+    def refresh(self):
+        w = self.mod.weight
+        ver = (w._version, w.data_ptr(), self.mod.bias._version, w.device)
+        if ver == self.version:
+            return
+        self.version = ver
+        wd = w.detach()
+        cout, cin = wd.shape[0], wd.shape[1]
+        taps = wd.numel() // (cout * cin)
+        wt = wd.reshape(cout, cin, taps)
+        self.cout, self.cin, self.taps = cout, cin, taps
+        self.w_simt = wt.permute(2, 1, 0).contiguous().float()        # [tap][Cin][Cout]
+        wk = wt.permute(0, 2, 1).contiguous().float()                  # [Cout][tap][Cin]  (K-major for TMA/UMMA)
+        self.w_hi = wk.to(torch.bfloat16)
+        self.w_lo = (wk - self.w_hi.float()).to(torch.bfloat16)
+        self.bias = self.mod.bias.detach().float().contiguous()
+
+
+class UNetExecutor:
+    """Runs ``UNetParams`` on the CUDA kernels for one sample of shape (C, D, H, W)."""
+
+    def __init__(self, params: UNetParams, use_tensor_cores: bool = True):
+        self.p = params
+        self.use_tc = use_tensor_cores
+        self._convs: Dict[int, _PackedConv] = {}
+        self._film_version = None
+        self._film_w = self._film_b = None
+        self._film_slices: Dict[int, Tuple[int, int]] = {}
+        self.tc_calls = 0
+        self.simt_calls = 0
+
+    # -- weights -------------------------------------------------------------------------------------------
+    def _pc(self, mod) -> _PackedConv:
+        pc = self._convs.get(id(mod))
+        if pc is None:
+            pc = self._convs[id(mod)] = _PackedConv(mod)
+        pc.refresh()
+        return pc
+
+    def _res_blocks(self):
+        return [m for m in self.p.modules() if isinstance(m, _ResParams)]
+
+    def _film(self):
+        blocks = self._res_blocks()
+        ver = tuple((b.emb_layers[1].weight._version, b.emb_layers[1].weight.data_ptr()) for b in blocks)
+        if ver != self._film_version:
+            self._film_version = ver
+            self._film_w = torch.cat([b.emb_layers[1].weight.detach() for b in blocks], 0).float().contiguous()
+            self._film_b = torch.cat([b.emb_layers[1].bias.detach() for b in blocks], 0).float().contiguous()
+            off = 0
+            for b in blocks:
+                n = b.emb_layers[1].weight.shape[0]
+                self._film_slices[id(b)] = (off, n)
+                off += n
+        return self._film_w, self._film_b
+
+    # -- primitive ops -------------------------------------------------------------------------------------
+    def _gn(self, act: _Act, norm: nn.GroupNorm, film, silu: bool, want_split: bool):
+        dev = act.x1.device
+        C, V = act.C, act.V
+        acc = self._acc
+        ops.gn_stats(act.x1, act.c1, act.x2, act.c2, V, acc)
+        a = torch.empty(C, device=dev)
+        b = torch.empty(C, device=dev)
+        ops.gn_finalize(acc, norm.weight.detach(), norm.bias.detach(), film, C, V, a, b, norm.eps)
+        y = y_hi = y_lo = None
+        if want_split:
+            y_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+            y_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+        else:
+            y = torch.empty(V, C, device=dev)
+        ops.gn_apply(act.x1, act.c1, act.x2, act.c2, V, a, b, silu, y, y_hi, y_lo)
+        return y, y_hi, y_lo
+
+    def _tc_ok(self, pc: _PackedConv, dims, stride: int, ups: bool) -> bool:
+        if not self.use_tc or stride != 1 or ups:
+            return False
+        if pc.cin % 64 or pc.cout % 16 or pc.cout > 256:
+            return False
+        D, H, W = dims
+        # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels
+        return W % 8 == 0 and H % 4 == 0 and D % 4 == 0
+
+    def _conv(self, mod, act: _Act, stride=1, ups=False, residual=None, pre=None) -> _Act:
+        """pre: optional (y, y_hi, y_lo) already-normalised single-source operand replacing `act`."""
+        pc = self._pc(mod)
+        dev = act.x1.device
+        k = 3 if pc.taps == 27 else 1
+        D, H, W = act.dims
+        if ups:
+            od = (2 * D, 2 * H, 2 * W)
+        elif stride == 2:
+            od = ((D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1)
+        else:
+            od = (D, H, W)
+        Vo = od[0] * od[1] * od[2]
+        out = torch.empty(Vo, pc.cout, device=dev)
+        if pre is not None and pre[1] is not None:
+            rc = ops.conv3d_tc(pre[1], pre[2], pc.cin, act.dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out)
+            if rc != 0:
+                raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted")
+            self.tc_calls += 1
+            return _Act(out, pc.cout, od)
+        if pre is not None:
+            x1, c1, x2, c2 = pre[0], pc.cin, None, 0
+        else:
+            x1, c1, x2, c2 = act.x1, act.c1, act.x2, act.c2
+        ops.conv3d_simt(x1, c1, x2, c2, act.dims, k, stride, ups, pc.w_simt, pc.bias, residual, pc.cout, out)
+        self.simt_calls += 1
+        return _Act(out, pc.cout, od)
+
+    def _conv_raw_tc(self, mod, act: _Act, residual=None) -> Optional[_Act]:
+        """Tensor-core path for a convolution whose operand is a raw (un-normalised) activation."""
+        pc = self._pc(mod)
+        if not self._tc_ok(pc, act.dims, 1, False):
+            return None
+        dev = act.x1.device
+        V = act.V
+        if act.x2 is not None:
+            return None
+        hi = torch.empty(V, pc.cin, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty(V, pc.cin, device=dev, dtype=torch.bfloat16)
+        ops.split_bf16(act.x1, hi, lo)
+        return self._conv(mod, act, residual=residual, pre=(None, hi, lo))
+
+    # -- blocks --------------------------------------------------------------------------------------------
+    def _res(self, blk: _ResParams, act: _Act, film_all) -> _Act:
+        conv1, conv2 = blk.in_layers[2], blk.out_layers[3]
+        pc1, pc2 = self._pc(conv1), self._pc(conv2)
+        pre = self._gn(act, blk.in_layers[0], None, True, self._tc_ok(pc1, act.dims, 1, False))
+        h = self._conv(conv1, act, pre=pre)
+        off, n = self._film_slices[id(blk)]
+        film = film_all[off:off + n]
+        pre2 = self._gn(h, blk.out_layers[0], film, True, self._tc_ok(pc2, h.dims, 1, False))
+        if isinstance(blk.skip_connection, nn.Identity):
+            assert act.x2 is None
+            skip = act.x1
+        else:
+            s = self._conv_raw_tc(blk.skip_connection, act)
+            if s is None:
+                s = self._conv(blk.skip_connection, act)
+            skip = s.x1
+        return self._conv(conv2, h, residual=skip, pre=pre2)
+
+    def _attn(self, blk: _AttnParams, act: _Act) -> _Act:
+        assert act.x2 is None
+        dev = act.x1.device
+        T, C = act.V, act.C
+        pcq = self._pc(blk.qkv)
+        flat = _Act(act.x1, C, (1, 1, T))
+        tcq = self._tc_ok(pcq, (T // 32 if T % 32 == 0 else 1, 4, 8), 1, False) and T % 128 == 0
+        dims = (T // 32, 4, 8) if tcq else (1, 1, T)
+        flat = _Act(act.x1, C, dims)
+        pre = self._gn(flat, blk.norm, None, False, tcq)
+        qkv = self._conv(blk.qkv, flat, pre=pre)
+        a = torch.empty(T, C, device=dev)
+        ops.attention_simt(qkv.x1, T, blk.heads, C // blk.heads, a)
+        a_act = _Act(a, C, dims)
+        out = self._conv_raw_tc(blk.proj_out, a_act, residual=act.x1) if tcq else None
+        if out is None:
+            out = self._conv(blk.proj_out, a_act, residual=act.x1)
+        return _Act(out.x1, C, act.dims)
+
+    def _run(self, seq: nn.Sequential, act: _Act, film_all) -> _Act:
+        for layer in seq:
+            if isinstance(layer, _ResParams):
+                act = self._res(layer, act, film_all)
+            elif isinstance(layer, _AttnParams):
+                act = self._attn(layer, act)
+            elif isinstance(layer, _DownParams):
+                act = self._conv(layer.op, act, stride=2)
+            elif isinstance(layer, _UpParams):
+                act = self._conv(layer.conv, act, ups=True)
+            elif isinstance(layer, nn.Conv3d):
+                r = self._conv_raw_tc(layer, act)
+                act = r if r is not None else self._conv(layer, act)
+            else:
+                raise TypeError(type(layer))
+        return act
+
+    # -- forward -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_cl(self, x_cl: torch.Tensor, dims: Tuple[int, int, int], t: torch.Tensor) -> torch.Tensor:
+        """x_cl (V, Cin) channels-last fp32, t (1,) int64 on the device -> (V, Cout) channels-last."""
+        p = self.p
+        dev = x_cl.device
+        self._acc = getattr(self, "_acc", None)
+        if self._acc is None or self._acc.device != dev:
+            self._acc = torch.zeros(64, dtype=torch.float64, device=dev)
+        mc = p.model_channels
+        e0 = torch.empty(1, mc, device=dev)
+        ops.timestep_embedding(t, mc, e0)
+        l0, l2 = p.time_embed[0], p.time_embed[2]
+        e1 = torch.empty(1, l0.out_features, device=dev)
+        ops.linear_rows(e0, l0.weight.detach(), l0.bias.detach(), 1, l0.in_features, l0.out_features, False, True, e1)
+        emb = torch.empty(1, l2.out_features, device=dev)
+        ops.linear_rows(e1, l2.weight.detach(), l2.bias.detach(), 1, l2.in_features, l2.out_features, False, False, emb)
+        fw, fb = self._film()
+        film_all = torch.empty(fw.shape[0], device=dev)
+        ops.linear_rows(emb, fw, fb, 1, fw.shape[1], fw.shape[0], True, False, film_all)
+
+        act = _Act(x_cl, p.in_channels, dims)
+        skips: List[_Act] = []
+        for blk in p.input_blocks:
+            act = self._run(blk, act, film_all)
+            skips.append(act)
+        act = self._run(p.middle_block, act, film_all)
+        for blk in p.output_blocks:
+            s = skips.pop()
+            act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1), film_all)
+        conv = p.out[2]
+        pre = self._gn(act, p.out[0], None, True, self._tc_ok(self._pc(conv), act.dims, 1, False))
+        return self._conv(conv, act, pre=pre).x1
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """x (N, C, D, H, W), t (N,) -> (N, Cout, D, H, W); samples are independent (looped)."""
+        N, C, D, H, W = x.shape
+        V = D * H * W
+        outs = []
+        x = x.contiguous().float()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        for n in range(N):
+            x_cl = ops.transpose2d(x[n].reshape(-1), C, V).view(V, C)
+            y_cl = self.forward_cl(x_cl, (D, H, W), t[n:n + 1])
+            y = ops.transpose2d(y_cl.reshape(-1), V, self.p.out_channels)
+            outs.append(y.view(1, self.p.out_channels, D, H, W))
+        return outs[0] if N == 1 else torch.cat(outs, 0)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# plug-in surface
+# ----------------------------------------------------------------------------------------------------------
+class Unet3DBase(nn.Module):
+    """diffusion_utils.py:30-38."""
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, cond_features: Optional[torch.Tensor] = None,
+                **kwargs) -> torch.Tensor:
+        raise NotImplementedError()
+
+
+class SimpleUnet3D(Unet3DBase):
+    """Drop-in for the reference ``SimpleUnet3D`` (same constructor fields, same ``_net.*`` parameter names,
+    Xavier-uniform Conv3d/Linear weights with zero biases -- diffusion_utils.py:43-80)."""
+
+    def __init__(self, image_size: int = 64, in_channels: int = 128, out_channels: int = 128,
+                 model_channels: int = 128, num_res_blocks: int = 2, channel_mult: Sequence[int] = (1, 2, 4, 8),
+                 attention_resolutions: Sequence[int] = (8, 16), num_heads: int = 2, dropout: float = 0.0,
+                 homogeneous_resample: bool = True, use_tensor_cores: bool = True):
+        super().__init__()
+        if dropout != 0.0:
+            raise NotImplementedError("inference path: dropout must be 0 (reference default)")
+        if not homogeneous_resample:
+            raise NotImplementedError("only homogeneous (x2 in D,H,W) resampling is built")
+        self.image_size = image_size
+        self._net = UNetParams(in_channels, model_channels, out_channels, num_res_blocks,
+                               tuple(attention_resolutions), tuple(channel_mult), num_heads)
+        for m in self._net.modules():
+            if isinstance(m, (nn.Conv3d, nn.Linear)):
+                nn.init.xavier_uniform_(m.weight)
+                with torch.no_grad():
+                    m.bias.zero_()
+        self._exec = UNetExecutor(self._net, use_tensor_cores)
+
+    def forward(self, x, timesteps, cond_features=None):
+        if cond_features is not None:
+            x = torch.cat([x, cond_features], dim=1)
+        if not x.is_cuda:
+            raise ops.HoloError("SimpleUnet3D: CUDA tensors only (no CPU fallback)")
+        return self._exec.forward(x, timesteps)

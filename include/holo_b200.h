@@ -109,8 +109,9 @@ int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, in
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);
 
 /* timestep_embedding -- nn.py:109-127 -- and the small Linear layers (time_embed unet.py:646-650, emb_layers :199-205):
- * out[m][o] = act_out(b[o] + sum_i W[o][i] * act_in(x[m][i])) with act = SiLU when the flag is set. */
-int holo_timestep_embedding(const long long* t_i64, int n, int dim, float* out, void* stream);
+ * out[m][o] = act_out(b[o] + sum_i W[o][i] * act_in(x[m][i])) with act = SiLU when the flag is set.
+ * freqs (dim/2): exp(-ln(1e4) * i / (dim/2)), built by the caller on the host as the reference does (nn.py:119-121). */
+int holo_timestep_embedding(const long long* t_i64, int n, int dim, const float* freqs, float* out, void* stream);
 int holo_linear_rows(const float* x, const float* W, const float* b, int M, int in_dim, int out_dim, int silu_in,
                      int silu_out, float* out, void* stream);
 

@@ -1,0 +1,188 @@
+"""GPU parity of the denoiser kernels and the whole UNet against the CPU oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cl(x):  # (1,C,D,H,W) -> (V,C) cuda
+    C = x.shape[1]
+    return x[0].reshape(C, -1).t().contiguous().cuda()
+
+
+def _from_cl(y, C, dims):
+    return y.t().reshape(1, C, *dims).cpu()
+
+
+@pytest.mark.parametrize("C1,C2,Cout,R,k,stride,ups", [
+    (16, 0, 64, 8, 3, 1, False),
+    (64, 64, 64, 8, 3, 1, False),     # two-source (skip concat)
+    (32, 0, 32, 9, 3, 2, False),      # Downsample, odd size
+    (32, 0, 32, 4, 3, 1, True),       # Upsample: nearest x2 folded into the conv
+    (64, 32, 128, 6, 1, 1, False),    # 1x1 skip conv on the concat
+    (8, 0, 12, 5, 3, 1, False),       # ragged tiles
+])
+def test_conv_simt(C1, C2, Cout, R, k, stride, ups):
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, C1 + C2, R, R, R, generator=g)
+    w = torch.randn(Cout, C1 + C2, k, k, k, generator=g) / math.sqrt((C1 + C2) * k ** 3)
+    b = torch.randn(Cout, generator=g)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    ref = F.conv3d(xin, w, b, stride=stride, padding=k // 2)
+    res = torch.randn_like(ref)
+    ref = ref + res
+    od = ref.shape[2:]
+    x1 = _cl(x[:, :C1])
+    x2 = _cl(x[:, C1:]) if C2 else None
+    wp = w.reshape(Cout, C1 + C2, -1).permute(2, 1, 0).contiguous().cuda()
+    out = torch.empty(od.numel(), Cout, device="cuda")
+    ops.conv3d_simt(x1, C1, x2, C2, (R, R, R), k, stride, ups, wp, b.cuda(), _cl(res), Cout, out)
+    assert rel_err(_from_cl(out, Cout, od), ref) < 1e-5
+
+
+@pytest.mark.parametrize("C1,C2,R,film,silu", [(64, 0, 8, False, True), (64, 128, 6, True, True), (32, 0, 4, False, False)])
+def test_groupnorm(C1, C2, R, film, silu):
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    C = C1 + C2
+    x = torch.randn(1, C, R, R, R, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.group_norm(x, 32, gamma, beta, 1e-5)
+    fl = None
+    if film:
+        fl = torch.randn(2 * C, generator=g) * 0.3
+        ref = ref * (1 + fl[:C].view(1, C, 1, 1, 1)) + fl[C:].view(1, C, 1, 1, 1)
+    if silu:
+        ref = F.silu(ref)
+    V = R ** 3
+    acc = torch.zeros(64, dtype=torch.float64, device="cuda")
+    x1, x2 = _cl(x[:, :C1]), (_cl(x[:, C1:]) if C2 else None)
+    ops.gn_stats(x1, C1, x2, C2, V, acc)
+    a, b = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.gn_finalize(acc, gamma.cuda(), beta.cuda(), fl.cuda() if film else None, C, V, a, b)
+    y = torch.empty(V, C, device="cuda")
+    hi = torch.empty(V, C, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty(V, C, device="cuda", dtype=torch.bfloat16)
+    ops.gn_apply(x1, C1, x2, C2, V, a, b, silu, y, hi, lo)
+    assert float(acc.abs().max()) == 0.0  # finalize re-zeroes the accumulator
+    assert rel_err(_from_cl(y, C, (R, R, R)), ref) < 1e-5
+    # hi + lo reproduces y to ~2^-17 relative
+    assert rel_err(hi.float() + lo.float(), y) < 2e-5
+
+
+@pytest.mark.parametrize("T,heads,ch", [(64, 2, 256), (512, 2, 128), (200, 1, 32), (4096, 2, 64)])
+def test_attention(T, heads, ch):
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    qkv = torch.randn(1, heads * 3 * ch, T, generator=g)
+    q, k, v = qkv.reshape(heads, 3 * ch, T).split(ch, 1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), -1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(1, -1, T)
+    out = torch.empty(T, heads * ch, device="cuda")
+    ops.attention_simt(qkv[0].t().contiguous().cuda(), T, heads, ch, out)
+    assert rel_err(out.t().cpu()[None], ref) < 1e-5
+
+
+def test_embedding_and_linear():
+    from holo_diffusion_b200 import ops
+    t = torch.tensor([0, 1, 500, 999])
+    ref = uo.timestep_embedding(t, 64)
+    out = torch.empty(4, 64, device="cuda")
+    ops.timestep_embedding(t.cuda(), 64, out)
+    assert rel_err(out, ref) < 1e-5
+    g = torch.Generator().manual_seed(3)
+    W, b, x = torch.randn(300, 64, generator=g), torch.randn(300, generator=g), torch.randn(4, 64, generator=g)
+    y = torch.empty(4, 300, device="cuda")
+    ops.linear_rows(x.cuda(), W.cuda(), b.cuda(), 4, 64, 300, True, True, y)
+    assert rel_err(y, F.silu(F.linear(F.silu(x), W, b))) < 1e-5
+
+
+def _build(in_ch, R, tc, **kw):
+    from holo_diffusion_b200.unet import SimpleUnet3D
+    net = SimpleUnet3D(image_size=R, in_channels=in_ch, out_channels=in_ch, use_tensor_cores=tc, **kw)
+    return net
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("t", [0, 500])
+def test_unet_base_args_16(tc, t):
+    """Base UNet args (configs/base.yaml:93-98) on a 16^3 x 16ch grid, randomised proj_out / GN affine / biases."""
+    kw = dict(model_channels=64, num_res_blocks=2, channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(4, 8), num_heads=2)
+    sd = uo.make_unet_state_dict(16, 16, seed=2)
+    net = _build(16, 16, tc, **kw)
+    net._net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = torch.tanh(torch.randn(1, 16, 16, 16, 16, generator=torch.Generator().manual_seed(0)))
+    tt = torch.full((1,), t, dtype=torch.long)
+    ref = uo.unet_forward(sd, x, tt)
+    out = net(x.cuda(), tt.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < TOL
+    if tc:
+        assert net._exec.tc_calls > 0, "tensor-core path was not taken"
+
+
+def test_unet_small_arch_batch2():
+    kw = dict(model_channels=32, num_res_blocks=1, channel_mult=(1, 2), attention_resolutions=(2,), num_heads=1)
+    sd = uo.make_unet_state_dict(8, 8, model_ch=32, num_res_blocks=1, channel_mult=(1, 2), attention_resolutions=(2,), seed=5)
+    net = _build(8, 8, False, **kw)
+    net._net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = torch.randn(2, 8, 8, 8, 8, generator=torch.Generator().manual_seed(1))
+    tt = torch.tensor([3, 700])
+    ref = uo.unet_forward(sd, x, tt, n_heads=1)
+    out = net(x.cuda(), tt.cuda())
+    assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("Cin,Cout,dims,k", [
+    (64, 64, (8, 8, 8), 3),        # one M tile deep in each direction, halo on all faces
+    (128, 64, (8, 12, 16), 3),     # non-cubic volume, 2 K slabs
+    (64, 128, (4, 4, 8), 1),       # 1x1 (skip connection / qkv)
+    (192, 256, (8, 8, 8), 3),      # concat width, two N blocks
+    (64, 32, (8, 8, 16), 3),       # final conv: narrow N
+    (64, 16, (4, 8, 8), 3),        # cfg #1 output width
+    (128, 384, (16, 4, 8), 1),     # qkv as a GEMM over 512 tokens
+])
+def test_conv_tc(Cin, Cout, dims, k):
+    """tcgen05 3xBF16 convolution against fp32 F.conv3d; also checks the fused hi/lo split of the result."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    D, H, W = dims
+    x = torch.randn(1, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, k, generator=g) / math.sqrt(Cin * k ** 3)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(1, Cout, D, H, W, generator=g)
+    ref = F.conv3d(x, w, b, padding=k // 2) + res
+    V = D * H * W
+    x_cl = _cl(x)
+    hi = torch.empty(V, Cin, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(x_cl, hi, lo)
+    wk = w.reshape(Cout, Cin, -1).permute(0, 2, 1).contiguous().cuda()
+    w_hi = wk.to(torch.bfloat16)
+    w_lo = (wk - w_hi.float()).to(torch.bfloat16)
+    out = torch.empty(V, Cout, device="cuda")
+    o_hi = torch.empty(V, Cout, device="cuda", dtype=torch.bfloat16)
+    o_lo = torch.empty_like(o_hi)
+    rc = ops.conv3d_tc(hi, lo, Cin, dims, k, w_hi, w_lo, b.cuda(), _cl(res), Cout, out, o_hi, o_lo)
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert rel_err(_from_cl(out, Cout, dims), ref) < 2e-5
+    assert rel_err(o_hi.float() + o_lo.float(), out) < 2e-5
+
+
+def test_conv_tc_rejects_unsupported():
+    from holo_diffusion_b200 import ops
+    z = torch.zeros(64, 32, device="cuda", dtype=torch.bfloat16)
+    o = torch.zeros(64, 32, device="cuda")
+    assert ops.conv3d_tc(z, z, 32, (4, 4, 4), 3, z, z, None, None, 32, o) == -3  # Cin not a multiple of 64
