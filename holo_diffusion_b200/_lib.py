@@ -2,7 +2,7 @@
 
 The prototypes are read from ``include/holo_b200.h`` so that the header is the single source of truth for the
 C-ABI.  There is NO fallback: if the library is missing the import fails loudly (build it with
-``python -m holo_diffusion_b200.build`` or ``__graft_entry__.build()``).
+``python holo_diffusion_b200/build.py`` or ``__graft_entry__.build()``).
 """
 from __future__ import annotations
 
@@ -51,7 +51,7 @@ class _Lib:
     def __init__(self):
         if not os.path.exists(LIB_PATH):
             raise ImportError(
-                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m holo_diffusion_b200.build` "
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python holo_diffusion_b200/build.py` "
                 "(there is no CPU fallback).")
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()

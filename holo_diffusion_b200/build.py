@@ -1,6 +1,6 @@
-"""In-tree build of libholo_b200.so (sm_100a only) and of the C oracle helpers.
+"""In-tree build of libholo_b200.so (sm_100a only).
 
-`python -m holo_diffusion_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
+`python holo_diffusion_b200/build.py` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
@@ -25,11 +25,25 @@ def _newer(src: str, dst: str, deps) -> bool:
     return any(os.path.getmtime(p) > t for p in [src, *deps])
 
 
+def _source_hash(paths) -> str:
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(HERE, "..", "include", "holo_b200.h"))
+    # content stamp: a snapshot copied to another box loses mtimes; never recompile an up-to-date library there
+    stamp_path = LIB + ".stamp"
+    digest = _source_hash([os.path.join(CSRC, f) for f in srcs] + hdrs)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_path) and open(stamp_path).read().strip() == digest:
+        return LIB
     jobs = []
     for s in srcs:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
@@ -54,6 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    open(stamp_path, "w").write(digest)
     return LIB
 
 

@@ -122,6 +122,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 struct TcParams {
     int Cin, D, H, W, ksize, Cout;
+    long long out_pitch;  // elements between consecutive output rows (= Cout for dense tensors)
     const float* bias;
     const float* residual;
     float* out;
@@ -246,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
             if (P.residual) {
-                const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.Cout + n);
+                const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     float4 b = __ldg(rp + j4);
@@ -254,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
             if (P.out) {
-                float4* op = reinterpret_cast<float4*>(P.out + v * P.Cout + n);
+                float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4)
                     op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
@@ -269,8 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
                     lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
                 }
-                uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.Cout + n);
-                uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.Cout + n);
+                uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
+                uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
                 hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                 lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
@@ -302,11 +303,11 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int make_act_map(CUtensorMap* m, const void* base, int C, int D, int H, int W) {
+int make_act_map(CUtensorMap* m, const void* base, int C, long long pitch, int D, int H, int W) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[4] = {SLAB, TILE_W, TILE_H, TILE_D};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
@@ -315,11 +316,11 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int D, int H, int W) {
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-int make_w_map(CUtensorMap* m, const void* base, int Ktot, int Cout, int block_n) {
+int make_w_map(CUtensorMap* m, const void* base, int Ktot, long long pitch, int Cout, int block_n) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
     cuuint32_t box[2] = {SLAB, (cuuint32_t)block_n};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
@@ -341,13 +342,21 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
 
 }  // namespace
 
-extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize,
-                              const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
-                              float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
-    HOLO_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16), "holo_conv3d_tc: null arg");
-    HOLO_CHECK_ARG((out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr), "holo_conv3d_tc: hi/lo outputs come together");
-    if (!(ksize == 1 || ksize == 3) || Cin % SLAB || Cout % 16 || W % TILE_W || H % TILE_H || D % TILE_D) {
-        holo_set_error("holo_conv3d_tc: unsupported shape Cin=%d Cout=%d dims=%dx%dx%d k=%d", Cin, Cout, D, H, W, ksize);
+static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int D, int H,
+                        int W, int ksize, const void* w_hi, const void* w_lo, long long w_pitch, const float* bias,
+                        const float* residual, int Cout, long long out_pitch, float* out, void* out_hi_bf16,
+                        void* out_lo_bf16, void* stream) {
+    if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
+        holo_set_error("%s: null arg", who);
+        return HOLO_ERR_ARG;
+    }
+    if ((out_hi_bf16 == nullptr) != (out_lo_bf16 == nullptr)) {
+        holo_set_error("%s: hi/lo outputs come together", who);
+        return HOLO_ERR_ARG;
+    }
+    if (!(ksize == 1 || ksize == 3) || Cin % SLAB || Cout % 16 || W % TILE_W || H % TILE_H || D % TILE_D ||
+        x_pitch % 8 || w_pitch % 8 || out_pitch % 4) {
+        holo_set_error("%s: unsupported shape Cin=%d Cout=%d dims=%dx%dx%d k=%d", who, Cin, Cout, D, H, W, ksize);
         return HOLO_ERR_UNSUPPORTED;
     }
     int block_n;
@@ -360,16 +369,16 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     if (block_n == 128 && tiles * (Cout / 128) < 148) block_n = 64;
     const int taps = ksize * ksize * ksize;
     CUtensorMap ah, al, bh, bl;
-    int e = make_act_map(&ah, x_hi, Cin, D, H, W);
-    if (!e) e = make_act_map(&al, x_lo, Cin, D, H, W);
-    if (!e) e = make_w_map(&bh, w_hi, taps * Cin, Cout, block_n);
-    if (!e) e = make_w_map(&bl, w_lo, taps * Cin, Cout, block_n);
+    int e = make_act_map(&ah, x_hi, Cin, x_pitch, D, H, W);
+    if (!e) e = make_act_map(&al, x_lo, Cin, x_pitch, D, H, W);
+    if (!e) e = make_w_map(&bh, w_hi, taps * Cin, w_pitch, Cout, block_n);
+    if (!e) e = make_w_map(&bl, w_lo, taps * Cin, w_pitch, Cout, block_n);
     if (e) {
-        holo_set_error("holo_conv3d_tc: cuTensorMapEncodeTiled failed (%d)", e);
+        holo_set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, e);
         return HOLO_ERR_CUDA;
     }
     TcParams P;
-    P.Cin = Cin, P.D = D, P.H = H, P.W = W, P.ksize = ksize, P.Cout = Cout;
+    P.Cin = Cin, P.D = D, P.H = H, P.W = W, P.ksize = ksize, P.Cout = Cout, P.out_pitch = out_pitch;
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     cudaStream_t st = (cudaStream_t)stream;
@@ -379,4 +388,25 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
         case 32: return launch<32>(ah, al, bh, bl, P, tiles, st);
         default: return launch<16>(ah, al, bh, bl, P, tiles, st);
     }
+}
+
+extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize,
+                              const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
+                              float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
+    const int taps = ksize * ksize * ksize;
+    return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, w_hi, w_lo, (long long)taps * Cin, bias,
+                        residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream);
+}
+
+// Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,
+// bf16 hi/lo pairs, arbitrary row pitches).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
+extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
+                            const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
+                            long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
+    if (M % BLOCK_M) {
+        holo_set_error("holo_gemm_tc: M=%d must be a multiple of 128", M);
+        return HOLO_ERR_UNSUPPORTED;
+    }
+    return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, b_hi, b_lo, b_pitch, bias,
+                        residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream);
 }

@@ -198,12 +198,25 @@ extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, l
     return HOLO_OK;
 }
 
-// fp32 -> bf16 hi/lo split of a plain tensor (operands that do not come out of a GroupNorm)
-__global__ void split_bf16_kernel(const float* __restrict__ x, long long n4, uint16_t* __restrict__ hi,
-                                  uint16_t* __restrict__ lo) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+// fp32 -> bf16 hi/lo split of a plain channels-last tensor (operands that do not come out of a GroupNorm).
+// Options: zero-pad the channel count up to Cpad (the tensor-core conv walks K in 64-channel slabs), and fold a
+// nearest x2 upsample of the (D,H,W) volume (Upsample.forward, unet.py:94-97) so the upsampled fp32 tensor is
+// never written.
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long Vout, int C, int Cpad, int ups, int Din,
+                                  int Hin, int Win, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const int q = Cpad / 4;
+    const long long total = Vout * q;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        float4 r = reinterpret_cast<const float4*>(x)[i];
+        long long v = i / q;
+        int c = (int)(i % q) * 4;
+        long long vs = v;
+        if (ups) {
+            int Wo = Win * 2, Ho = Hin * 2;
+            int ow = (int)(v % Wo), oh = (int)((v / Wo) % Ho), od = (int)(v / ((long long)Wo * Ho));
+            vs = ((long long)(od >> 1) * Hin + (oh >> 1)) * Win + (ow >> 1);
+        }
+        float4 r = (c < C) ? *reinterpret_cast<const float4*>(x + vs * C + c) : make_float4(0, 0, 0, 0);
         float rr[4] = {r.x, r.y, r.z, r.w};
         uint16_t h4[4], l4[4];
 #pragma unroll
@@ -213,18 +226,26 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n4, uin
             h4[k] = *reinterpret_cast<uint16_t*>(&h);
             l4[k] = *reinterpret_cast<uint16_t*>(&l);
         }
-        reinterpret_cast<uint2*>(hi)[i] =
+        *reinterpret_cast<uint2*>(hi + v * Cpad + c) =
             make_uint2((uint32_t)h4[0] | ((uint32_t)h4[1] << 16), (uint32_t)h4[2] | ((uint32_t)h4[3] << 16));
-        reinterpret_cast<uint2*>(lo)[i] =
+        *reinterpret_cast<uint2*>(lo + v * Cpad + c) =
             make_uint2((uint32_t)l4[0] | ((uint32_t)l4[1] << 16), (uint32_t)l4[2] | ((uint32_t)l4[3] << 16));
     }
 }
 
-extern "C" int holo_split_bf16(const float* x, long long n, void* hi_bf16, void* lo_bf16, void* stream) {
-    HOLO_CHECK_ARG(x && hi_bf16 && lo_bf16 && n > 0 && n % 4 == 0, "holo_split_bf16: n must be a positive multiple of 4");
-    int blocks = holo_cdiv(n / 4, 256 * 4);
+extern "C" int holo_split_bf16(const float* x, long long V, int C, int Cpad, int upsample2x, int Din, int Hin, int Win,
+                               void* hi_bf16, void* lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(x && hi_bf16 && lo_bf16 && V > 0 && C > 0 && C % 4 == 0 && Cpad % 4 == 0 && Cpad >= C,
+                   "holo_split_bf16: C and Cpad must be multiples of 4, Cpad >= C");
+    long long Vout = V;
+    if (upsample2x) {
+        HOLO_CHECK_ARG((long long)Din * Hin * Win == V, "holo_split_bf16: dims do not match V");
+        Vout = V * 8;
+    }
+    int blocks = holo_cdiv(Vout * (Cpad / 4), 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n / 4, (uint16_t*)hi_bf16, (uint16_t*)lo_bf16);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, Vout, C, Cpad, upsample2x, Din, Hin, Win,
+                                                                (uint16_t*)hi_bf16, (uint16_t*)lo_bf16);
     HOLO_CHECK_LAUNCH("holo_split_bf16");
     return HOLO_OK;
 }

@@ -130,8 +130,41 @@ def gn_apply(x1, C1, x2, C2, V, a, b, silu: bool, y=None, y_hi=None, y_lo=None):
                _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16), _stream())
 
 
-def split_bf16(x, hi, lo):
-    lib().call("holo_split_bf16", _ptr(x), x.numel(), _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
+def split_bf16(x, V, C, Cpad, hi, lo, ups_dims=None):
+    """x (V,C) fp32 -> hi/lo (Vout,Cpad) bf16; ups_dims=(D,H,W) folds a nearest x2 upsample (Vout = 8V)."""
+    d = ups_dims or (0, 0, 0)
+    lib().call("holo_split_bf16", _ptr(x), V, C, Cpad, 1 if ups_dims else 0, d[0], d[1], d[2],
+               _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
+
+
+def _ptr_off(t, off_elems: int, dtype):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr() + off_elems * t.element_size())
+
+
+def gemm_tc(a_hi, a_lo, a_off, a_pitch, M, K, b_hi, b_lo, b_off, b_pitch, N, bias, residual, out_pitch, out, out_off=0,
+            out_hi=None, out_lo=None) -> int:
+    """out[m][n] (+out_off, row pitch out_pitch) = bias + residual + sum_k a[m][k] b[n][k] on tcgen05 (bf16x3)."""
+    bf = torch.bfloat16
+    rc = lib().try_call("holo_gemm_tc", _ptr_off(a_hi, a_off, bf), _ptr_off(a_lo, a_off, bf), a_pitch, M, K,
+                        _ptr_off(b_hi, b_off, bf), _ptr_off(b_lo, b_off, bf), b_pitch, N, _ptr(bias),
+                        _ptr_off(residual, out_off, torch.float32), out_pitch, _ptr_off(out, out_off, torch.float32),
+                        _ptr_off(out_hi, out_off, bf), _ptr_off(out_lo, out_off, bf), _stream())
+    if rc not in (0, -3):
+        raise HoloError(f"holo_gemm_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
+    return rc
+
+
+def softmax_split(S, n_rows, T, scale2, P_hi, P_lo):
+    lib().call("holo_softmax_split", _ptr(S), n_rows, T, float(scale2), _ptr(P_hi, torch.bfloat16),
+               _ptr(P_lo, torch.bfloat16), _stream())
+
+
+def transpose_split(src, src_off, src_pitch, rows, cols, hi, lo):
+    lib().call("holo_transpose_split_bf16", _ptr_off(src, src_off, torch.float32), src_pitch, rows, cols,
+               _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
 
 
 def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, w, bias, residual, Cout, out):

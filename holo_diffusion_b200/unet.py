@@ -147,11 +147,18 @@ class _PackedConv:
         taps = wd.numel() // (cout * cin)
         wt = wd.reshape(cout, cin, taps)
         self.cout, self.cin, self.taps = cout, cin, taps
+        self.cin_pad = (cin + 63) // 64 * 64                          # the tcgen05 kernel walks K in 64-channel slabs
         self.w_simt = wt.permute(2, 1, 0).contiguous().float()        # [tap][Cin][Cout]
-        wk = wt.permute(0, 2, 1).contiguous().float()                  # [Cout][tap][Cin]  (K-major for TMA/UMMA)
+        wk = torch.zeros(cout, taps, self.cin_pad, device=wd.device)   # [Cout][tap][Cin_pad]  (K-major for TMA/UMMA)
+        wk[:, :, :cin] = wt.permute(0, 2, 1)
         self.w_hi = wk.to(torch.bfloat16)
         self.w_lo = (wk - self.w_hi.float()).to(torch.bfloat16)
         self.bias = self.mod.bias.detach().float().contiguous()
+
+
+def _tile_ok(dims) -> bool:
+    D, H, W = dims  # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels
+    return W % 8 == 0 and H % 4 == 0 and D % 4 == 0
 
 
 class UNetExecutor:
@@ -166,6 +173,7 @@ class UNetExecutor:
         self._film_slices: Dict[int, Tuple[int, int]] = {}
         self.tc_calls = 0
         self.simt_calls = 0
+        self._acc = None
 
     # -- weights -------------------------------------------------------------------------------------------
     def _pc(self, mod) -> _PackedConv:
@@ -193,16 +201,21 @@ class UNetExecutor:
         return self._film_w, self._film_b
 
     # -- primitive ops -------------------------------------------------------------------------------------
+    def _tc_ok(self, pc: _PackedConv, out_dims) -> bool:
+        """Can this convolution (stride 1, after any upsample) run on the tcgen05 kernel?"""
+        return self.use_tc and pc.cout % 16 == 0 and pc.cout <= 4096 and _tile_ok(out_dims)
+
     def _gn(self, act: _Act, norm: nn.GroupNorm, film, silu: bool, want_split: bool):
+        """GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation.  Returns (fp32, hi, lo)."""
         dev = act.x1.device
         C, V = act.C, act.V
-        acc = self._acc
-        ops.gn_stats(act.x1, act.c1, act.x2, act.c2, V, acc)
+        ops.gn_stats(act.x1, act.c1, act.x2, act.c2, V, self._acc)
         a = torch.empty(C, device=dev)
         b = torch.empty(C, device=dev)
-        ops.gn_finalize(acc, norm.weight.detach(), norm.bias.detach(), film, C, V, a, b, norm.eps)
+        ops.gn_finalize(self._acc, norm.weight.detach(), norm.bias.detach(), film, C, V, a, b, norm.eps)
         y = y_hi = y_lo = None
         if want_split:
+            assert C % 64 == 0
             y_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
             y_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
         else:
@@ -210,18 +223,35 @@ class UNetExecutor:
         ops.gn_apply(act.x1, act.c1, act.x2, act.c2, V, a, b, silu, y, y_hi, y_lo)
         return y, y_hi, y_lo
 
-    def _tc_ok(self, pc: _PackedConv, dims, stride: int, ups: bool) -> bool:
-        if not self.use_tc or stride != 1 or ups:
-            return False
-        if pc.cin % 64 or pc.cout % 16 or pc.cout > 256:
-            return False
-        D, H, W = dims
-        # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels
-        return W % 8 == 0 and H % 4 == 0 and D % 4 == 0
+    def _split_raw(self, act: _Act, pc: _PackedConv, ups: bool = False):
+        """bf16 hi/lo pair of a raw (un-normalised) single-source activation, channel-padded, optionally upsampled."""
+        assert act.x2 is None
+        dev = act.x1.device
+        Vo = act.V * (8 if ups else 1)
+        hi = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
+        ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None)
+        return hi, lo
 
-    def _conv(self, mod, act: _Act, stride=1, ups=False, residual=None, pre=None) -> _Act:
-        """pre: optional (y, y_hi, y_lo) already-normalised single-source operand replacing `act`."""
-        pc = self._pc(mod)
+    def _conv_tc(self, pc: _PackedConv, hi, lo, out_dims, residual=None, want_split_out=False) -> _Act:
+        dev = hi.device
+        k = 3 if pc.taps == 27 else 1
+        Vo = out_dims[0] * out_dims[1] * out_dims[2]
+        out = torch.empty(Vo, pc.cout, device=dev)
+        o_hi = o_lo = None
+        if want_split_out:
+            o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
+            o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
+        rc = ops.conv3d_tc(hi, lo, pc.cin_pad, out_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo)
+        if rc != 0:
+            raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
+                                + ops.lib().cdll.holo_last_error().decode())
+        self.tc_calls += 1
+        r = _Act(out, pc.cout, out_dims)
+        r_split = (o_hi, o_lo)
+        return r if not want_split_out else (r, r_split)
+
+    def _conv_simt(self, pc: _PackedConv, act: _Act, stride=1, ups=False, residual=None, pre=None) -> _Act:
         dev = act.x1.device
         k = 3 if pc.taps == 27 else 1
         D, H, W = act.dims
@@ -231,72 +261,81 @@ class UNetExecutor:
             od = ((D - 1) // 2 + 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1)
         else:
             od = (D, H, W)
-        Vo = od[0] * od[1] * od[2]
-        out = torch.empty(Vo, pc.cout, device=dev)
-        if pre is not None and pre[1] is not None:
-            rc = ops.conv3d_tc(pre[1], pre[2], pc.cin, act.dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out)
-            if rc != 0:
-                raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted")
-            self.tc_calls += 1
-            return _Act(out, pc.cout, od)
+        out = torch.empty(od[0] * od[1] * od[2], pc.cout, device=dev)
         if pre is not None:
-            x1, c1, x2, c2 = pre[0], pc.cin, None, 0
+            x1, c1, x2, c2 = pre, pc.cin, None, 0
         else:
             x1, c1, x2, c2 = act.x1, act.c1, act.x2, act.c2
         ops.conv3d_simt(x1, c1, x2, c2, act.dims, k, stride, ups, pc.w_simt, pc.bias, residual, pc.cout, out)
         self.simt_calls += 1
         return _Act(out, pc.cout, od)
 
-    def _conv_raw_tc(self, mod, act: _Act, residual=None) -> Optional[_Act]:
-        """Tensor-core path for a convolution whose operand is a raw (un-normalised) activation."""
+    def _conv_norm(self, mod, act: _Act, norm, film, residual=None) -> _Act:
+        """conv(SiLU(GN(act)))  -- the in_layers / out_layers / out pattern."""
         pc = self._pc(mod)
-        if not self._tc_ok(pc, act.dims, 1, False):
-            return None
-        dev = act.x1.device
-        V = act.V
-        if act.x2 is not None:
-            return None
-        hi = torch.empty(V, pc.cin, device=dev, dtype=torch.bfloat16)
-        lo = torch.empty(V, pc.cin, device=dev, dtype=torch.bfloat16)
-        ops.split_bf16(act.x1, hi, lo)
-        return self._conv(mod, act, residual=residual, pre=(None, hi, lo))
+        tc = self._tc_ok(pc, act.dims) and pc.cin % 64 == 0
+        y, y_hi, y_lo = self._gn(act, norm, film, True, tc)
+        if tc:
+            return self._conv_tc(pc, y_hi, y_lo, act.dims, residual)
+        return self._conv_simt(pc, act, residual=residual, pre=y)
+
+    def _conv_raw(self, mod, act: _Act, stride=1, ups=False, residual=None) -> _Act:
+        """conv on a raw activation (first conv, skip 1x1, Upsample/Downsample convs)."""
+        pc = self._pc(mod)
+        D, H, W = act.dims
+        od = (2 * D, 2 * H, 2 * W) if ups else (D, H, W)
+        if stride == 1 and act.x2 is None and self._tc_ok(pc, od):
+            hi, lo = self._split_raw(act, pc, ups)
+            return self._conv_tc(pc, hi, lo, od, residual)
+        return self._conv_simt(pc, act, stride=stride, ups=ups, residual=residual)
 
     # -- blocks --------------------------------------------------------------------------------------------
     def _res(self, blk: _ResParams, act: _Act, film_all) -> _Act:
-        conv1, conv2 = blk.in_layers[2], blk.out_layers[3]
-        pc1, pc2 = self._pc(conv1), self._pc(conv2)
-        pre = self._gn(act, blk.in_layers[0], None, True, self._tc_ok(pc1, act.dims, 1, False))
-        h = self._conv(conv1, act, pre=pre)
+        h = self._conv_norm(blk.in_layers[2], act, blk.in_layers[0], None)
         off, n = self._film_slices[id(blk)]
-        film = film_all[off:off + n]
-        pre2 = self._gn(h, blk.out_layers[0], film, True, self._tc_ok(pc2, h.dims, 1, False))
         if isinstance(blk.skip_connection, nn.Identity):
             assert act.x2 is None
             skip = act.x1
         else:
-            s = self._conv_raw_tc(blk.skip_connection, act)
-            if s is None:
-                s = self._conv(blk.skip_connection, act)
-            skip = s.x1
-        return self._conv(conv2, h, residual=skip, pre=pre2)
+            skip = self._conv_raw(blk.skip_connection, act).x1
+        return self._conv_norm(blk.out_layers[3], h, blk.out_layers[0], film_all[off:off + n], residual=skip)
 
     def _attn(self, blk: _AttnParams, act: _Act) -> _Act:
         assert act.x2 is None
         dev = act.x1.device
         T, C = act.V, act.C
-        pcq = self._pc(blk.qkv)
+        heads = blk.heads
+        ch = C // heads
+        pcq, pcp = self._pc(blk.qkv), self._pc(blk.proj_out)
+        tc = self.use_tc and T % 128 == 0 and ch % 64 == 0 and C % 64 == 0
         flat = _Act(act.x1, C, (1, 1, T))
-        tcq = self._tc_ok(pcq, (T // 32 if T % 32 == 0 else 1, 4, 8), 1, False) and T % 128 == 0
-        dims = (T // 32, 4, 8) if tcq else (1, 1, T)
-        flat = _Act(act.x1, C, dims)
-        pre = self._gn(flat, blk.norm, None, False, tcq)
-        qkv = self._conv(blk.qkv, flat, pre=pre)
-        a = torch.empty(T, C, device=dev)
-        ops.attention_simt(qkv.x1, T, blk.heads, C // blk.heads, a)
-        a_act = _Act(a, C, dims)
-        out = self._conv_raw_tc(blk.proj_out, a_act, residual=act.x1) if tcq else None
-        if out is None:
-            out = self._conv(blk.proj_out, a_act, residual=act.x1)
+        if not tc:
+            y, _, _ = self._gn(flat, blk.norm, None, False, False)
+            qkv = self._conv_simt(pcq, flat, pre=y)
+            a = torch.empty(T, C, device=dev)
+            ops.attention_simt(qkv.x1, T, heads, ch, a)
+            out = self._conv_simt(pcp, _Act(a, C, (1, 1, T)), residual=act.x1)
+            return _Act(out.x1, C, act.dims)
+        gdims = (T // 32, 4, 8)  # GEMM view of the token axis for the TMA box
+        _, y_hi, y_lo = self._gn(flat, blk.norm, None, False, True)
+        qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True)
+        S = torch.empty(T, T, device=dev)
+        P_hi = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
+        P_lo = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
+        vt_hi = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
+        vt_lo = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
+        a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        for h in range(heads):
+            base = h * 3 * ch
+            rc = ops.gemm_tc(q_hi, q_lo, base, 3 * C, T, ch, q_hi, q_lo, base + ch, 3 * C, T, None, None, T, S)
+            assert rc == 0
+            ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)   # (q s)(k s) = s^2 q k, s = ch^-1/4
+            ops.transpose_split(qkv.x1, base + 2 * ch, 3 * C, T, ch, vt_hi, vt_lo)
+            rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, None, h * ch, a_hi, a_lo)
+            assert rc == 0
+            self.tc_calls += 2
+        out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
         return _Act(out.x1, C, act.dims)
 
     def _run(self, seq: nn.Sequential, act: _Act, film_all) -> _Act:
@@ -306,12 +345,11 @@ class UNetExecutor:
             elif isinstance(layer, _AttnParams):
                 act = self._attn(layer, act)
             elif isinstance(layer, _DownParams):
-                act = self._conv(layer.op, act, stride=2)
+                act = self._conv_raw(layer.op, act, stride=2)
             elif isinstance(layer, _UpParams):
-                act = self._conv(layer.conv, act, ups=True)
+                act = self._conv_raw(layer.conv, act, ups=True)
             elif isinstance(layer, nn.Conv3d):
-                r = self._conv_raw_tc(layer, act)
-                act = r if r is not None else self._conv(layer, act)
+                act = self._conv_raw(layer, act)
             else:
                 raise TypeError(type(layer))
         return act
@@ -322,7 +360,6 @@ class UNetExecutor:
         """x_cl (V, Cin) channels-last fp32, t (1,) int64 on the device -> (V, Cout) channels-last."""
         p = self.p
         dev = x_cl.device
-        self._acc = getattr(self, "_acc", None)
         if self._acc is None or self._acc.device != dev:
             self._acc = torch.zeros(64, dtype=torch.float64, device=dev)
         mc = p.model_channels
@@ -346,9 +383,7 @@ class UNetExecutor:
         for blk in p.output_blocks:
             s = skips.pop()
             act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1), film_all)
-        conv = p.out[2]
-        pre = self._gn(act, p.out[0], None, True, self._tc_ok(self._pc(conv), act.dims, 1, False))
-        return self._conv(conv, act, pre=pre).x1
+        return self._conv_norm(p.out[2], act, p.out[0], None).x1
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:

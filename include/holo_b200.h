@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 100
+#define HOLO_B200_VERSION 101
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -88,7 +88,10 @@ int holo_gn_finalize(double* acc64, const float* gamma, const float* beta, const
                      long long V, float eps, float* a, float* b, void* stream);
 int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a, const float* b,
                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
-int holo_split_bf16(const float* x, long long n, void* hi_bf16, void* lo_bf16, void* stream);
+/* fp32 (V,C) -> bf16 hi/lo (Vout,Cpad): zero-pads channels to Cpad; upsample2x folds F.interpolate(nearest, x2)
+ * of the (Din,Hin,Win) volume (Upsample.forward, unet.py:94-97), Vout = 8 V. */
+int holo_split_bf16(const float* x, long long V, int C, int Cpad, int upsample2x, int Din, int Hin, int Win,
+                    void* hi_bf16, void* lo_bf16, void* stream);
 
 /* Exact-fp32 implicit-GEMM convolution (nn.Conv3d 3^3/1^3, stride 1|2, padding k/2; nn.Conv1d k=1):
  * unet.py:185,211,222,657,792 / Downsample :129-131 / Upsample :89-97 (upsample2x folds F.interpolate nearest x2)
@@ -104,6 +107,18 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, const void* w_hi,
                    const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
                    void* out_hi_bf16, void* out_lo_bf16, void* stream);
+
+/* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
+ * hi/lo pairs, K-major with arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
+ * With holo_softmax_split / holo_transpose_split_bf16 it carries QKVAttentionLegacy (unet.py:438-455) on tensor
+ * cores: S = Q K^T, P = softmax(scale2 * S) (fp32, one key row per CTA, emitted as bf16 hi/lo), O = P V. */
+int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
+                 const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
+                 long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream);
+int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_hi_bf16, void* P_lo_bf16,
+                       void* stream);
+int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, int cols, void* hi_bf16,
+                              void* lo_bf16, void* stream);
 
 /* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);

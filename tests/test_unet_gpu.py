@@ -167,7 +167,7 @@ def test_conv_tc(Cin, Cout, dims, k):
     x_cl = _cl(x)
     hi = torch.empty(V, Cin, device="cuda", dtype=torch.bfloat16)
     lo = torch.empty_like(hi)
-    ops.split_bf16(x_cl, hi, lo)
+    ops.split_bf16(x_cl, V, Cin, Cin, hi, lo)
     wk = w.reshape(Cout, Cin, -1).permute(0, 2, 1).contiguous().cuda()
     w_hi = wk.to(torch.bfloat16)
     w_lo = (wk - w_hi.float()).to(torch.bfloat16)
@@ -179,6 +179,55 @@ def test_conv_tc(Cin, Cout, dims, k):
     assert rc == 0
     assert rel_err(_from_cl(out, Cout, dims), ref) < 2e-5
     assert rel_err(o_hi.float() + o_lo.float(), out) < 2e-5
+
+
+def test_split_pad_and_upsample():
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    C, R = 32, 4
+    x = torch.randn(1, C, R, R, R, generator=g)
+    V = R ** 3
+    hi = torch.empty(8 * V, 64, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(_cl(x), V, C, 64, hi, lo, (R, R, R))
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    got = (hi.float() + lo.float())
+    assert float(got[:, C:].abs().max()) == 0.0
+    assert rel_err(_from_cl(got[:, :C], C, (2 * R,) * 3), up) < 2e-5
+
+
+@pytest.mark.parametrize("T,heads,ch", [(512, 2, 128), (4096, 2, 64), (256, 1, 64)])
+def test_attention_tensor_core_pipeline(T, heads, ch):
+    """S = QK^T (holo_gemm_tc) -> fp32 softmax (holo_softmax_split) -> PV (holo_gemm_tc) against the fp32 einsum."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    C = heads * ch
+    qkv = torch.randn(1, heads * 3 * ch, T, generator=g)
+    q, k, v = qkv.reshape(heads, 3 * ch, T).split(ch, 1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), -1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(1, -1, T)
+    x = qkv[0].t().contiguous().cuda()          # (T, 3C)
+    hi = torch.empty(T, 3 * C, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(x, T, 3 * C, 3 * C, hi, lo)
+    S = torch.empty(T, T, device="cuda")
+    P_hi = torch.empty(T, T, device="cuda", dtype=torch.bfloat16)
+    P_lo = torch.empty_like(P_hi)
+    vt_hi = torch.empty(ch, T, device="cuda", dtype=torch.bfloat16)
+    vt_lo = torch.empty_like(vt_hi)
+    out = torch.empty(T, C, device="cuda")
+    for h in range(heads):
+        b = h * 3 * ch
+        assert ops.gemm_tc(hi, lo, b, 3 * C, T, ch, hi, lo, b + ch, 3 * C, T, None, None, T, S) == 0
+        if h == 0:
+            torch.cuda.synchronize()
+            assert rel_err(S, (q[0].t() @ k[0])) < 2e-5
+        ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)
+        ops.transpose_split(x, b + 2 * ch, 3 * C, T, ch, vt_hi, vt_lo)
+        assert ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, out, h * ch) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out.t().cpu()[None], ref) < 5e-5
 
 
 def test_conv_tc_rejects_unsupported():
