@@ -202,8 +202,10 @@ extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, l
 // Options: zero-pad the channel count up to Cpad (the tensor-core conv walks K in 64-channel slabs), and fold a
 // nearest x2 upsample of the (D,H,W) volume (Upsample.forward, unet.py:94-97) so the upsampled fp32 tensor is
 // never written.
-__global__ void split_bf16_kernel(const float* __restrict__ x, long long Vout, int C, int Cpad, int ups, int Din,
-                                  int Hin, int Win, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+__global__ void split_bf16_kernel(const float* __restrict__ x, int C1, const float* __restrict__ x2, int C2,
+                                  long long Vout, int Cpad, int ups, int Din, int Hin, int Win,
+                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const int C = C1 + C2;
     const int q = Cpad / 4;
     const long long total = Vout * q;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -216,7 +218,9 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long Vout, i
             int ow = (int)(v % Wo), oh = (int)((v / Wo) % Ho), od = (int)(v / ((long long)Wo * Ho));
             vs = ((long long)(od >> 1) * Hin + (oh >> 1)) * Win + (ow >> 1);
         }
-        float4 r = (c < C) ? *reinterpret_cast<const float4*>(x + vs * C + c) : make_float4(0, 0, 0, 0);
+        float4 r = make_float4(0, 0, 0, 0);
+        if (c < C1) r = *reinterpret_cast<const float4*>(x + vs * C1 + c);
+        else if (c < C) r = *reinterpret_cast<const float4*>(x2 + vs * C2 + (c - C1));
         float rr[4] = {r.x, r.y, r.z, r.w};
         uint16_t h4[4], l4[4];
 #pragma unroll
@@ -233,10 +237,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long Vout, i
     }
 }
 
-extern "C" int holo_split_bf16(const float* x, long long V, int C, int Cpad, int upsample2x, int Din, int Hin, int Win,
-                               void* hi_bf16, void* lo_bf16, void* stream) {
-    HOLO_CHECK_ARG(x && hi_bf16 && lo_bf16 && V > 0 && C > 0 && C % 4 == 0 && Cpad % 4 == 0 && Cpad >= C,
-                   "holo_split_bf16: C and Cpad must be multiples of 4, Cpad >= C");
+extern "C" int holo_split_bf16(const float* x1, int C1, const float* x2, int C2, long long V, int Cpad, int upsample2x,
+                               int Din, int Hin, int Win, void* hi_bf16, void* lo_bf16, void* stream) {
+    const int C = C1 + C2;
+    HOLO_CHECK_ARG(x1 && hi_bf16 && lo_bf16 && V > 0 && C1 > 0 && C1 % 4 == 0 && C2 % 4 == 0 && Cpad % 4 == 0 && Cpad >= C,
+                   "holo_split_bf16: channel counts must be multiples of 4, Cpad >= C1 + C2");
+    HOLO_CHECK_ARG(C2 == 0 || x2, "holo_split_bf16: second source missing");
     long long Vout = V;
     if (upsample2x) {
         HOLO_CHECK_ARG((long long)Din * Hin * Win == V, "holo_split_bf16: dims do not match V");
@@ -244,7 +250,7 @@ extern "C" int holo_split_bf16(const float* x, long long V, int C, int Cpad, int
     }
     int blocks = holo_cdiv(Vout * (Cpad / 4), 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, Vout, C, Cpad, upsample2x, Din, Hin, Win,
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, C1, x2, C2, Vout, Cpad, upsample2x, Din, Hin, Win,
                                                                 (uint16_t*)hi_bf16, (uint16_t*)lo_bf16);
     HOLO_CHECK_LAUNCH("holo_split_bf16");
     return HOLO_OK;

@@ -42,7 +42,8 @@ class HoloDiffusionModel(nn.Module):
                  renderer_class_type: str = "HoloMultiPassEmissionAbsorptionRenderer",
                  renderer_HoloMultiPassEmissionAbsorptionRenderer_args: Optional[dict] = None,
                  implicit_function_class_type: str = "HoloVoxelGridImplicitFunction",
-                 implicit_function_HoloVoxelGridImplicitFunction_args: Optional[dict] = None, **unused):
+                 implicit_function_HoloVoxelGridImplicitFunction_args: Optional[dict] = None,
+                 use_cuda_graph: bool = True, **unused):
         super().__init__()
         if implicit_function_class_type != "HoloVoxelGridImplicitFunction":
             raise ValueError(f"{type(self)} supports only HoloVoxelGridImplicitFunction!")
@@ -67,6 +68,11 @@ class HoloDiffusionModel(nn.Module):
         self._implicit_functions = nn.ModuleList([wrapper for _ in range(num_passes)])
         self._range_stats: Optional[torch.Tensor] = None
         self._t0: Optional[torch.Tensor] = None
+        # one CUDA graph per (device, grid shape, weights version): outputs live in static buffers that the next
+        # forward() overwrites -- clone what must outlive it
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._graph_key = None
 
     # ------------------------------------------------------------------ sampling
     def sample_random_voxel_features_progressive(self):
@@ -87,33 +93,17 @@ class HoloDiffusionModel(nn.Module):
         mn, mx, nan = ops.decode_range(self._range_stats.cpu().tolist())
         assert nan == 0 and mn >= -1.0 and mx <= 1.0, f"voxel features out of [-1, 1] ({where}): min {mn} max {mx} nan {nan}"
 
-    # ------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def forward(self, *, image_rgb: Optional[torch.Tensor] = None, camera: PerspectiveCameras,
-                fg_probability=None, mask_crop=None, depth_map=None, sequence_name=None, frame_timestamp=None,
-                evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, voxel_features: Optional[torch.Tensor] = None,
-                **kwargs) -> Dict[str, Any]:
-        if image_rgb is not None:
-            raise NotImplementedError("view-pooling encoder path (images -> voxel grid) is a 'next' row (SURVEY 8f)")
-        if evaluation_mode != EvaluationMode.EVALUATION:
-            raise NotImplementedError("training branch is a 'next' row (SURVEY 8f)")
-        target_cameras = camera[[0]]  # n_targets = 1 (holo_diffusion_model.py:263-273,315)
-        dev = target_cameras.device
-        if voxel_features is None:
-            voxel_features = self.sample_random_voxel_features()
-        assert voxel_features.shape[0] == 1, "only one single voxel grid is supported per GPU"
-        assert voxel_features.shape[1] == self.feature_size, "Wrong voxel feature size!"
+    # ------------------------------------------------------------------ device work of one view (no host sync)
+    def _device_forward(self, cam: PerspectiveCameras, voxel_features: torch.Tensor):
+        dev = voxel_features.device
         C, R = self.feature_size, self.resol
         V = R ** 3
-        if self._range_stats is None or self._range_stats.device != dev:
-            self._range_stats = torch.empty(4, dtype=torch.int32, device=dev)
-            self._t0 = torch.zeros(1, dtype=torch.int64, device=dev)
-        x = voxel_features.contiguous().float()
-        x_cl = ops.transpose2d(x.reshape(-1), C, V).view(V, C)
+        x_cl = ops.transpose2d(voxel_features.reshape(-1), C, V).view(V, C)
         ops.range_init(self._range_stats)
         if self.net_3d_enabled:
-            # voxel_features = tanh(net_3d(voxel_features, t=0)); the input-range assert (:381) and the two
-            # output-range asserts (:426,:428) are evaluated from one fused min/max pass each, checked once below
+            # voxel_features = tanh(net_3d(voxel_features, t=0)) (:420-425); the input-range assert (:381) and the
+            # output-range asserts (:426,:428) come from fused min/max passes and are checked once, after the
+            # whole view has been queued
             ops.act_range(x_cl, V, C, 0, None, None, self._range_stats)
             y_cl = self.net_3d._exec.forward_cl(x_cl, (R, R, R), self._t0)
             grid_cl = torch.empty(V, C, device=dev)
@@ -125,11 +115,71 @@ class HoloDiffusionModel(nn.Module):
             ops.act_range(x_cl, V, C, 0, grid_cl, None, self._range_stats)
         for func in self._implicit_functions:
             func.bind_args(voxel_grid_features=voxel_features, voxel_grid_features_channels_last=grid_cl.view(R, R, R, C))
-        ray_bundle = self.raysampler(target_cameras, evaluation_mode)
-        rendered = self.renderer(ray_bundle, list(self._implicit_functions), evaluation_mode)
+        ray_bundle = self.raysampler(cam, EvaluationMode.EVALUATION)
+        rendered = self.renderer(ray_bundle, list(self._implicit_functions), EvaluationMode.EVALUATION)
         for func in self._implicit_functions:
             func.unbind_args()
-        self._check_range("input / tanh(net_3d) output")  # single D2H of 16 bytes, after all work is queued
+        return rendered, ray_bundle, voxel_features
+
+    def _weights_signature(self):
+        return sum(p._version for p in self.parameters()), next(self.parameters()).data_ptr()
+
+    def _graph_forward(self, cam: PerspectiveCameras, voxel_features: torch.Tensor):
+        """Replay the whole view (UNet + tanh + rays + render, ~600 launches) as one CUDA graph with static I/O."""
+        dev = voxel_features.device
+        key = (str(dev), tuple(voxel_features.shape), self._weights_signature())
+        if self._graph is None or self._graph_key != key:
+            self._g_vox = torch.empty_like(voxel_features)
+            self._g_cam = PerspectiveCameras(torch.ones(1, 2), torch.zeros(1, 2), torch.eye(3)[None], torch.zeros(1, 3)).to(dev)
+            self._copy_inputs(cam, voxel_features)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._device_forward(self._g_cam, self._g_vox)  # warm-up: packs weights, sets kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._g_out = self._device_forward(self._g_cam, self._g_vox)
+            self._graph, self._graph_key = g, key
+        self._copy_inputs(cam, voxel_features)
+        self._graph.replay()
+        return self._g_out
+
+    def _copy_inputs(self, cam, voxel_features):
+        self._g_vox.copy_(voxel_features, non_blocking=True)
+        self._g_cam.R.copy_(cam.R, non_blocking=True)
+        self._g_cam.T.copy_(cam.T, non_blocking=True)
+        self._g_cam.focal_length.copy_(cam.focal_length, non_blocking=True)
+        self._g_cam.principal_point.copy_(cam.principal_point, non_blocking=True)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, *, image_rgb: Optional[torch.Tensor] = None, camera: PerspectiveCameras,
+                fg_probability=None, mask_crop=None, depth_map=None, sequence_name=None, frame_timestamp=None,
+                evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, voxel_features: Optional[torch.Tensor] = None,
+                **kwargs) -> Dict[str, Any]:
+        if image_rgb is not None:
+            raise NotImplementedError("view-pooling encoder path (images -> voxel grid) is a 'next' row (SURVEY 8f)")
+        if evaluation_mode != EvaluationMode.EVALUATION:
+            raise NotImplementedError("training branch is a 'next' row (SURVEY 8f)")
+        target_cameras = camera[[0]]  # n_targets = 1 (holo_diffusion_model.py:263-273,315)
+        if voxel_features is None:
+            voxel_features = self.sample_random_voxel_features()
+        dev = voxel_features.device
+        if dev.type != "cuda":
+            raise ops.HoloError("HoloDiffusionModel: CUDA tensors only (no CPU fallback)")
+        assert voxel_features.shape[0] == 1, "only one single voxel grid is supported per GPU"
+        assert voxel_features.shape[1] == self.feature_size, "Wrong voxel feature size!"
+        if self._range_stats is None or self._range_stats.device != dev:
+            self._range_stats = torch.empty(4, dtype=torch.int32, device=dev)
+            self._t0 = torch.zeros(1, dtype=torch.int64, device=dev)
+        voxel_features = voxel_features.contiguous().float()
+        if self.use_cuda_graph:
+            rendered, ray_bundle, voxel_features = self._graph_forward(target_cameras, voxel_features)
+        else:
+            rendered, ray_bundle, voxel_features = self._device_forward(target_cameras.to(dev), voxel_features)
+        self._check_range("input / tanh(net_3d) output")  # the only host sync: 16 bytes, after all work is queued
         preds: Dict[str, Any] = {"rendered": rendered, "ray_bundle": ray_bundle, "voxel_features": voxel_features}
         preds["images_render"] = rendered.features.permute(0, 3, 1, 2)
         preds["depths_render"] = rendered.depths.permute(0, 3, 1, 2)

@@ -130,10 +130,10 @@ def gn_apply(x1, C1, x2, C2, V, a, b, silu: bool, y=None, y_hi=None, y_lo=None):
                _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16), _stream())
 
 
-def split_bf16(x, V, C, Cpad, hi, lo, ups_dims=None):
-    """x (V,C) fp32 -> hi/lo (Vout,Cpad) bf16; ups_dims=(D,H,W) folds a nearest x2 upsample (Vout = 8V)."""
+def split_bf16(x, V, C, Cpad, hi, lo, ups_dims=None, x2=None, C2=0):
+    """cat(x (V,C), x2 (V,C2)) fp32 -> hi/lo (Vout,Cpad) bf16; ups_dims=(D,H,W) folds a nearest x2 upsample."""
     d = ups_dims or (0, 0, 0)
-    lib().call("holo_split_bf16", _ptr(x), V, C, Cpad, 1 if ups_dims else 0, d[0], d[1], d[2],
+    lib().call("holo_split_bf16", _ptr(x), C, _ptr(x2), C2, V, Cpad, 1 if ups_dims else 0, d[0], d[1], d[2],
                _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
 
 

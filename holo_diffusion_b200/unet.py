@@ -224,13 +224,13 @@ class UNetExecutor:
         return y, y_hi, y_lo
 
     def _split_raw(self, act: _Act, pc: _PackedConv, ups: bool = False):
-        """bf16 hi/lo pair of a raw (un-normalised) single-source activation, channel-padded, optionally upsampled."""
-        assert act.x2 is None
+        """bf16 hi/lo pair of a raw (un-normalised) activation (skip concat consumed in place), channel-padded,
+        optionally upsampled."""
         dev = act.x1.device
         Vo = act.V * (8 if ups else 1)
         hi = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
         lo = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
-        ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None)
+        ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None, act.x2, act.c2)
         return hi, lo
 
     def _conv_tc(self, pc: _PackedConv, hi, lo, out_dims, residual=None, want_split_out=False) -> _Act:
@@ -284,7 +284,7 @@ class UNetExecutor:
         pc = self._pc(mod)
         D, H, W = act.dims
         od = (2 * D, 2 * H, 2 * W) if ups else (D, H, W)
-        if stride == 1 and act.x2 is None and self._tc_ok(pc, od):
+        if stride == 1 and self._tc_ok(pc, od):
             hi, lo = self._split_raw(act, pc, ups)
             return self._conv_tc(pc, hi, lo, od, residual)
         return self._conv_simt(pc, act, stride=stride, ups=ups, residual=residual)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 101
+#define HOLO_B200_VERSION 102
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -88,10 +88,11 @@ int holo_gn_finalize(double* acc64, const float* gamma, const float* beta, const
                      long long V, float eps, float* a, float* b, void* stream);
 int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a, const float* b,
                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
-/* fp32 (V,C) -> bf16 hi/lo (Vout,Cpad): zero-pads channels to Cpad; upsample2x folds F.interpolate(nearest, x2)
- * of the (Din,Hin,Win) volume (Upsample.forward, unet.py:94-97), Vout = 8 V. */
-int holo_split_bf16(const float* x, long long V, int C, int Cpad, int upsample2x, int Din, int Hin, int Win,
-                    void* hi_bf16, void* lo_bf16, void* stream);
+/* fp32 cat(x1 (V,C1), x2 (V,C2)) -> bf16 hi/lo (Vout,Cpad): consumes the skip concat in place, zero-pads channels
+ * to Cpad; upsample2x folds F.interpolate(nearest, x2) of the (Din,Hin,Win) volume (Upsample.forward,
+ * unet.py:94-97), Vout = 8 V. */
+int holo_split_bf16(const float* x1, int C1, const float* x2, int C2, long long V, int Cpad, int upsample2x, int Din,
+                    int Hin, int Win, void* hi_bf16, void* lo_bf16, void* stream);
 
 /* Exact-fp32 implicit-GEMM convolution (nn.Conv3d 3^3/1^3, stride 1|2, padding k/2; nn.Conv1d k=1):
  * unet.py:185,211,222,657,792 / Downsample :129-131 / Upsample :89-97 (upsample2x folds F.interpolate nearest x2)

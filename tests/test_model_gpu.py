@@ -1,0 +1,89 @@
+"""End-to-end parity of HoloDiffusionModel.forward (the generate_samples.py call pattern) and of the DDPM sampler."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from fixtures import make_grid, make_mlp
+from oracle import diffusion_oracle as do
+from oracle import render_oracle as ro
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+UNET = dict(model_channels=64, num_res_blocks=2, num_heads=2, channel_mult=[1, 1, 2, 4, 8], attention_resolutions=[4, 8])
+
+
+def _model(C, R, HW, S, passes, graph):
+    import holo_diffusion_b200 as hd
+    m = hd.HoloDiffusionModel(
+        resol=R, feature_size=C, num_passes=passes, render_image_width=HW, render_image_height=HW,
+        net_3d_SimpleUnet3D_args=UNET, raysampler_AdaptiveRaySampler_args=dict(n_pts_per_ray_evaluation=S),
+        renderer_HoloMultiPassEmissionAbsorptionRenderer_args=dict(
+            n_pts_per_ray_fine_evaluation=8, raymarcher_EmissionAbsorptionRaymarcher_args=dict(bg_color=(1.0, 1.0, 1.0))),
+        use_cuda_graph=graph)
+    sd = uo.make_unet_state_dict(C, C, seed=2)
+    mlp = make_mlp(C)
+    m.net_3d._net.load_state_dict(sd, strict=True)
+    m._implicit_functions[0]._fn.render_mlp.load_state_dict(mlp, strict=True)
+    return m.cuda(), sd, mlp
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_model_forward_matches_oracle(graph):
+    import holo_diffusion_b200 as hd
+    C, R, HW, S = 16, 16, 24, 16
+    m, sd, mlp = _model(C, R, HW, S, 1, graph)
+    cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, ro.CANONICAL_CO3D_UP_AXIS, 3.2)
+    ocams = ro.simple_360_cameras(8)
+    for pose, seed in ((1, 0), (5, 3)):  # second call replays the captured graph with new inputs
+        grid = make_grid(C, R, seed)
+        preds = m(camera=cams[[pose]].to("cuda"), voxel_features=grid.cuda())
+        g = torch.tanh(uo.unet_forward(sd, grid, torch.zeros(1, dtype=torch.long)))
+        ref = ro.render_chunked(mlp, g, ro.sample_rays(ocams[pose], HW, HW, S), R, 8.0, 1, 0, chunk_size_grid=0)
+        assert rel_err(preds["voxel_features"], g) < 1e-4
+        assert rel_err(preds["images_render"], ref.features.permute(0, 3, 1, 2)) < 1e-4
+        assert rel_err(preds["depths_render"], ref.depths.permute(0, 3, 1, 2)) < 1e-4
+        assert preds["images_render"].shape == (1, 3, HW, HW)
+        # ray bookkeeping is bit exact: pixel grid / ray order
+        assert torch.equal(preds["ray_bundle"].xys.cpu()[0], ro.ndc_xy_grid(HW, HW))
+
+
+def test_model_range_assert_fires():
+    import holo_diffusion_b200 as hd
+    m, _, _ = _model(16, 16, 8, 4, 1, False)
+    cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, ro.CANONICAL_CO3D_UP_AXIS, 3.2)
+    with pytest.raises(AssertionError):
+        m(camera=cams[[0]].to("cuda"), voxel_features=torch.full((1, 16, 16, 16, 16), 1.5).cuda())
+
+
+def test_ddpm_steps_match_reference_vectors():
+    """p_sample / q_sample against the vectors produced by the unmodified reference GaussianDiffusion."""
+    import os
+    import holo_diffusion_b200 as hd
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "diffusion_ref.npz"))
+    d = hd.ImplicitronGaussianDiffusion()
+    x, noise, t = (torch.from_numpy(g[k]).cuda() for k in ("x", "noise", "t"))
+    out = d.p_sample(lambda z, tt: torch.tanh(1.7 * z) * 1.3, x, t, noise_sampler=lambda *_: noise)
+    assert rel_err(out["sample"], torch.from_numpy(g["p_sample"])) < 1e-6
+    assert rel_err(out["pred_xstart"], torch.from_numpy(g["pred_xstart"])) < 1e-6
+    assert rel_err(d.q_sample(x, t, noise), torch.from_numpy(g["q_sample"])) < 1e-6
+
+
+def test_short_sampling_chain_matches_oracle():
+    """4 ancestral steps t = 999, 666, 333, 0 with injected noise: CUDA UNet + fused step vs oracle UNet + oracle step."""
+    import holo_diffusion_b200 as hd
+    C, R = 16, 16
+    m, sd, _ = _model(C, R, 8, 4, 1, False)
+    d = hd.ImplicitronGaussianDiffusion()
+    tab = do.schedule_tables()
+    gen = torch.Generator().manual_seed(11)
+    noises = {i: torch.randn(1, C, R, R, R, generator=gen) for i in (1000, 999, 666, 333, 0)}
+    dev_sampler = lambda i, shape, dev: noises[i].to(dev)  # noqa: E731
+    got = d.p_sample_loop(m.net_3d, (1, C, R, R, R), noise_sampler=dev_sampler, device="cuda", max_iter=4)
+    x = noises[1000]
+    for i in (999, 666, 333, 0):
+        t = torch.full((1,), i, dtype=torch.long)
+        x = do.p_sample(tab, lambda z, tt: uo.unet_forward(sd, z, tt), x, t, noises[i])["sample"]
+    assert rel_err(got, x) < 2e-4  # 4 chained UNet evaluations
