@@ -291,12 +291,12 @@ def run_ours(a):
         rec = []
         orig_tc, orig_simt = ops.conv3d_tc, ops.conv3d_simt
 
-        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None):
+        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None, stride=1):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo)
+            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo, stride)
             e.record()
-            rec.append(("tc", 2.0 * dims[0] * dims[1] * dims[2] * Cout * Cin * k ** 3, s, e))
+            rec.append(("tc", 2.0 * (dims[0] // stride) * (dims[1] // stride) * (dims[2] // stride) * Cout * Cin * k ** 3, s, e))
             return rc
 
         def simt(x1, C1, x2, C2, dims, k, stride, ups, w, bias, res, Cout, out):

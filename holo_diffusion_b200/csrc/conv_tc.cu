@@ -121,7 +121,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 struct TcParams {
-    int Cin, D, H, W, ksize, Cout;
+    int Cin, D, H, W, ksize, Cout;   // D, H, W = OUTPUT volume
+    int tw, th, td;                  // voxel box of one M tile: 8x4x4 (128 rows) or 4x4x4 (64 rows, upper half idle)
+    int stride;                      // 1 | 2 (input coordinate = out * stride + tap - pad)
+    int iters_per_split;             // split-K: gridDim.z slices of the (tap, slab) loop; atomics into a zeroed out
     long long out_pitch;  // elements between consecutive output rows (= Cout for dense tensors)
     const float* bias;
     const float* residual;
@@ -144,16 +147,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     // tile coordinates
-    const int tiles_w = P.W / TILE_W, tiles_h = P.H / TILE_H;
+    const int tiles_w = P.W / P.tw, tiles_h = P.H / P.th;
     int tile = blockIdx.x;
-    const int w0 = (tile % tiles_w) * TILE_W;
-    const int h0 = ((tile / tiles_w) % tiles_h) * TILE_H;
-    const int d0 = (tile / (tiles_w * tiles_h)) * TILE_D;
+    const int w0 = (tile % tiles_w) * P.tw;
+    const int h0 = ((tile / tiles_w) % tiles_h) * P.th;
+    const int d0 = (tile / (tiles_w * tiles_h)) * P.td;
+    const int rows = P.tw * P.th * P.td;
     const int n0 = blockIdx.y * BLOCK_N;
     const int taps = P.ksize * P.ksize * P.ksize;
     const int pad = P.ksize / 2;
     const int slabs = P.Cin / SLAB;
-    const int k_iters = taps * slabs;
+    const int k_total = taps * slabs;
+    const int it_begin = blockIdx.z * P.iters_per_split;
+    const int it_end = min(k_total, it_begin + P.iters_per_split);
+    const bool split = gridDim.z > 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -179,16 +186,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < k_iters; ++it) {
+            const uint32_t tx_bytes = 2u * (uint32_t)rows * 128u + 2u * (uint32_t)C::B_TILE_BYTES;
+            for (int it = it_begin; it < it_end; ++it) {
                 const int tap = it / slabs, slab = it % slabs;
                 const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + stage * C::STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                mbar_expect_tx(&full_bar[stage], tx_bytes);
                 const int c0 = slab * SLAB;
-                tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, w0 + kw - pad, h0 + kh - pad, d0 + kd - pad);
-                tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, w0 + kw - pad, h0 + kh - pad,
-                            d0 + kd - pad);
+                const int xw = w0 * P.stride + kw - pad, xh = h0 * P.stride + kh - pad, xd = d0 * P.stride + kd - pad;
+                tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, xw, xh, xd);
+                tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, xw, xh, xd);
                 const int kk = tap * P.Cin + c0;
                 tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kk, n0);
                 tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &map_b_lo, &full_bar[stage], kk, n0);
@@ -200,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         constexpr uint32_t idesc = make_idesc_bf16(BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it_begin; it < it_end; ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (lane == 0) {
@@ -213,12 +221,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
                     const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
                     const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko), dbl = make_kmajor_sw128_desc(b_lo + ko);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (it | k) != 0);  // small terms first
+                    umma_bf16(tmem_base, dal, dbh, idesc, (it > it_begin) || (k != 0));  // small terms first
                     umma_bf16(tmem_base, dah, dbl, idesc, 1);
                     umma_bf16(tmem_base, dah, dbh, idesc, 1);
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                if (it == k_iters - 1) umma_commit(tmem_full_bar);
+                if (it == it_end - 1) umma_commit(tmem_full_bar);
             }
             __syncwarp();
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
@@ -227,26 +235,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ================= epilogue =================
         const int q = warp % 4;  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
-        const int w = w0 + (r % TILE_W), h = h0 + ((r / TILE_W) % TILE_H), d = d0 + r / (TILE_W * TILE_H);
+        const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
         const size_t v = ((size_t)d * P.H + h) * P.W + w;
+        const bool row_ok = r < rows;
+        const bool lead = blockIdx.z == 0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
             uint32_t acc[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+            if (!row_ok) continue;
             const int n = n0 + c0;
             float vals[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]);
-            if (P.bias) {
+            if (P.bias && lead) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + j4);
                     vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
                 }
             }
-            if (P.residual) {
+            if (P.residual && lead) {
                 const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -254,7 +265,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
                 }
             }
-            if (P.out) {
+            if (P.out && split) {
+                float* op = P.out + v * P.out_pitch + n;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
+            } else if (P.out) {
                 float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4)
@@ -303,13 +318,15 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int make_act_map(CUtensorMap* m, const void* base, int C, long long pitch, int D, int H, int W) {
+int make_act_map(CUtensorMap* m, const void* base, int C, long long pitch, int D, int H, int W, int tw, int th, int td,
+                 int stride) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D};
     cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-    cuuint32_t box[4] = {SLAB, TILE_W, TILE_H, TILE_D};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // with an element stride s the box spans s*t input elements and the TMA keeps every s-th one (t of them)
+    cuuint32_t box[4] = {SLAB, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)(td * stride)};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -331,21 +348,21 @@ int make_w_map(CUtensorMap* m, const void* base, int Ktot, long long pitch, int 
 
 template <int BLOCK_N>
 int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-           const TcParams& P, int tiles, cudaStream_t st) {
+           const TcParams& P, int tiles, int nsplit, cudaStream_t st) {
     auto k = conv_tc_kernel<BLOCK_N>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
               "holo_conv3d_tc");
-    k<<<dim3(tiles, P.Cout / BLOCK_N), NUM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(ah, al, bh, bl, P);
+    k<<<dim3(tiles, P.Cout / BLOCK_N, nsplit), NUM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(ah, al, bh, bl, P);
     HOLO_CHECK_LAUNCH("holo_conv3d_tc");
     return HOLO_OK;
 }
 
 }  // namespace
 
-static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int D, int H,
-                        int W, int ksize, const void* w_hi, const void* w_lo, long long w_pitch, const float* bias,
-                        const float* residual, int Cout, long long out_pitch, float* out, void* out_hi_bf16,
-                        void* out_lo_bf16, void* stream) {
+static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int Din, int Hin,
+                        int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
+                        const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
+                        void* out_hi_bf16, void* out_lo_bf16, void* stream) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -354,9 +371,16 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         holo_set_error("%s: hi/lo outputs come together", who);
         return HOLO_ERR_ARG;
     }
-    if (!(ksize == 1 || ksize == 3) || Cin % SLAB || Cout % 16 || W % TILE_W || H % TILE_H || D % TILE_D ||
-        x_pitch % 8 || w_pitch % 8 || out_pitch % 4) {
-        holo_set_error("%s: unsupported shape Cin=%d Cout=%d dims=%dx%dx%d k=%d", who, Cin, Cout, D, H, W, ksize);
+    const int D = Din / stride, H = Hin / stride, W = Win / stride;  // output volume
+    int tw, th, td;
+    if (W % 8 == 0 && H % 4 == 0 && D % 4 == 0) tw = 8, th = 4, td = 4;
+    else if (W % 4 == 0 && H % 4 == 0 && D % 4 == 0) tw = 4, th = 4, td = 4;
+    else tw = 0, th = 0, td = 0;
+    const bool stride_ok = stride == 1 || (stride == 2 && ksize == 3 && Din % 2 == 0 && Hin % 2 == 0 && Win % 2 == 0);
+    if (!(ksize == 1 || ksize == 3) || !stride_ok || tw == 0 || Cin % SLAB || Cout % 16 || x_pitch % 8 || w_pitch % 8 ||
+        out_pitch % 4) {
+        holo_set_error("%s: unsupported shape Cin=%d Cout=%d dims=%dx%dx%d k=%d stride=%d", who, Cin, Cout, Din, Hin, Win,
+                       ksize, stride);
         return HOLO_ERR_UNSUPPORTED;
     }
     int block_n;
@@ -365,12 +389,25 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     else if (Cout % 32 == 0) block_n = 32;
     else block_n = 16;
     // small volumes: prefer more CTAs over wider tiles
-    const int tiles = (D / TILE_D) * (H / TILE_H) * (W / TILE_W);
+    const int tiles = (D / td) * (H / th) * (W / tw);
     if (block_n == 128 && tiles * (Cout / 128) < 148) block_n = 64;
     const int taps = ksize * ksize * ksize;
+    const int k_total = taps * (Cin / SLAB);
+    // split-K: when the M x N grid cannot fill the 148 SMs and K is long, slice the (tap, slab) loop across
+    // gridDim.z and accumulate with fp32 atomics into a zeroed output (>= 4 iterations per slice)
+    int nsplit = 1, per = k_total;
+    const int base = tiles * (Cout / block_n);
+    if (base < 120 && k_total >= 8 && out && !out_hi_bf16) {
+        int want = (296 + base - 1) / base;
+        int maxs = k_total / 4;
+        nsplit = want < maxs ? want : maxs;
+        if (nsplit < 1) nsplit = 1;
+        per = (k_total + nsplit - 1) / nsplit;
+        nsplit = (k_total + per - 1) / per;
+    }
     CUtensorMap ah, al, bh, bl;
-    int e = make_act_map(&ah, x_hi, Cin, x_pitch, D, H, W);
-    if (!e) e = make_act_map(&al, x_lo, Cin, x_pitch, D, H, W);
+    int e = make_act_map(&ah, x_hi, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
+    if (!e) e = make_act_map(&al, x_lo, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
     if (!e) e = make_w_map(&bh, w_hi, taps * Cin, w_pitch, Cout, block_n);
     if (!e) e = make_w_map(&bl, w_lo, taps * Cin, w_pitch, Cout, block_n);
     if (e) {
@@ -379,23 +416,31 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     }
     TcParams P;
     P.Cin = Cin, P.D = D, P.H = H, P.W = W, P.ksize = ksize, P.Cout = Cout, P.out_pitch = out_pitch;
+    P.tw = tw, P.th = th, P.td = td, P.stride = stride, P.iters_per_split = per;
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     cudaStream_t st = (cudaStream_t)stream;
+    if (nsplit > 1) {
+        if (out_pitch != Cout) {
+            holo_set_error("%s: split-K needs a dense output", who);
+            return HOLO_ERR_UNSUPPORTED;
+        }
+        HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
+    }
     switch (block_n) {
-        case 128: return launch<128>(ah, al, bh, bl, P, tiles, st);
-        case 64: return launch<64>(ah, al, bh, bl, P, tiles, st);
-        case 32: return launch<32>(ah, al, bh, bl, P, tiles, st);
-        default: return launch<16>(ah, al, bh, bl, P, tiles, st);
+        case 128: return launch<128>(ah, al, bh, bl, P, tiles, nsplit, st);
+        case 64: return launch<64>(ah, al, bh, bl, P, tiles, nsplit, st);
+        case 32: return launch<32>(ah, al, bh, bl, P, tiles, nsplit, st);
+        default: return launch<16>(ah, al, bh, bl, P, tiles, nsplit, st);
     }
 }
 
-extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize,
+extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
     const int taps = ksize * ksize * ksize;
-    return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, w_hi, w_lo, (long long)taps * Cin, bias,
-                        residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream);
+    return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
+                        (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,
@@ -407,6 +452,6 @@ extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitc
         holo_set_error("holo_gemm_tc: M=%d must be a multiple of 128", M);
         return HOLO_ERR_UNSUPPORTED;
     }
-    return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, b_hi, b_lo, b_pitch, bias,
+    return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
                         residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream);
 }

@@ -1,0 +1,566 @@
+// Fused volumetric renderer, tensor-core version (sm_100a): the 256-wide hidden layer of the collapsed RenderMLP
+// runs on tcgen05 (M = 128 rays of one depth step, N = 256 hidden units, K = 32 features as a 3xBF16 split),
+// everything else of a ray -- trilinear gather, density, emission-absorption compositing, importance
+// re-sampling, second pass -- stays in registers of the thread that owns the ray.
+//
+// Same contract and reference citations as render.cu (holo_render_fwd); this kernel is selected for C in {16, 32}
+// with the shipped 256-wide density net.  Per depth step and group of 128 rays:
+//   ray threads : sample x (fp32) -> sigma (fp32 CUDA cores) -> write [x_hi | x_lo] as one 128-byte swizzled row
+//   MMA warp    : D[128 x 256] = [x_hi|x_lo].[W_hi|W_hi]^T + x_hi.W_lo^T + 1.[b_hi + b_lo]^T      (7 UMMAs, TMEM)
+//   ray threads : tcgen05.ld the row, rgb_pre = lin(x) + sum_j 0.4 wr_j |t_j|   (leaky(t) = 0.6 t + 0.4 |t|, the
+//                 linear part 0.6 wr.(W x + b) is a 3 x C map folded at pack time), sigmoid, compositing.
+// Two groups per CTA ping-pong so one group's MMA hides behind the other's CUDA-core work.  The refiner is
+// streamed: the coarse weights go to a [S][n_rays] scratch, the inverse-cdf samples are generated in increasing
+// order and merged with the coarse depths on the fly (both runs are sorted), so no per-ray arrays are needed.
+#include "common.cuh"
+#include "../../include/holo_b200.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int HID = 256;
+constexpr int GROUP = 128;            // rays per group (= UMMA M)
+constexpr int RAY_THREADS = 2 * GROUP;
+constexpr int THREADS = RAY_THREADS + 64;  // + one MMA warp per group
+
+// shared-memory image (byte offsets; every UMMA tile 1024-aligned)
+constexpr int OFF_A0 = 0;                 // [128][128B]  group 0 operand rows
+constexpr int OFF_A1 = 16 * 1024;         // group 1
+constexpr int OFF_B1 = 32 * 1024;         // [256][128B]  [W_hi | W_hi]
+constexpr int OFF_B2 = 64 * 1024;         // [256][128B]  [W_lo | 0]
+constexpr int OFF_ONES = 96 * 1024;       // [128][128B]  [1, 1, 0, ...]
+constexpr int OFF_BB = 112 * 1024;        // [256][128B]  [b_hi, b_lo, 0, ...]
+constexpr int OFF_F32 = 144 * 1024;       // fp32 parameter block (see pack kernel)
+constexpr int F32_WSIG = 0;               // [32] density row of W_eff
+constexpr int F32_LIN = 32;               // [3][32]  0.6 * wr . W_eff[:256]
+constexpr int F32_MISC = 128;             // b_sigma, lin_const[3]
+constexpr int F32_EP = 132;               // [256][3] 0.4 * wr[i][j] stored j-major
+constexpr int F32_DIR = 132 + 768;        // [3][E] + br[3]   (E <= 27)
+constexpr int F32_COUNT = F32_DIR + 3 * 27 + 3;
+constexpr int IMG_BYTES = OFF_F32 + ((F32_COUNT * 4 + 15) / 16) * 16;
+constexpr int OFF_BAR = IMG_BYTES;        // mbarriers + tmem slot
+constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
+           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+__device__ __forceinline__ float linspace01(int i, int n) {
+    if (n == 1) return 0.0f;
+    float step = 1.0f / (float)(n - 1);
+    return (i < n / 2) ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
+}
+
+struct RenderTcParams {
+    const float* grid;
+    int D, Hh, Ww, C;
+    float inv_x, inv_y, inv_z;
+    const uint8_t* image;  // packed smem image (IMG_BYTES)
+    int n_harm;
+    const float* origins;
+    const float* dirs;
+    const float* lengths;
+    int n_rays, S, n_fine, add_input, n_passes;
+    float bg[3];
+    float bg_opacity;
+    float* features;
+    float* depths;
+    float* masks;
+    float* weights;
+    float* lengths_out;
+    float* p_features;
+    float* p_depths;
+    float* p_masks;
+    float* p_weights;
+    float* scratch_w;  // [S][n_rays] coarse weights (two passes only)
+};
+
+// trilinear gather of C channels (C = 16 or 32) into x[32] (upper half zero for C = 16)
+template <int C>
+__device__ __forceinline__ void sample_point(const float* __restrict__ grid, int D, int H, int W, float lx, float ly,
+                                             float lz, float (&f)[32]) {
+    float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
+    float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
+    float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
+    float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+    int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)W + 1.f);
+    int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)H + 1.f);
+    int z0 = (int)fminf(fmaxf(fz0, -2.f), (float)D + 1.f);
+    float wx1 = ix - fx0, wy1 = iy - fy0, wz1 = iz - fz0;
+    float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy, wz0 = (fz0 + 1.f) - iz;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) f[c] = 0.f;
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+        int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
+        int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
+        if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) {
+            const float4* p = reinterpret_cast<const float4*>(grid + (((size_t)zz * H + yy) * W + xx) * C);
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+                float4 v = __ldg(p + c4);
+                f[c4 * 4 + 0] += v.x * w;
+                f[c4 * 4 + 1] += v.y * w;
+                f[c4 * 4 + 2] += v.z * w;
+                f[c4 * 4 + 3] += v.w * w;
+            }
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);      // [2]
+    uint64_t* mma_done = a_full + 2;                                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+    const float* sF = reinterpret_cast<const float*>(smem + OFF_F32);
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    // stage the weight image
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(P.image) + (OFF_B1 / 16);
+        uint4* dst = reinterpret_cast<uint4*>(smem + OFF_B1);
+        for (int i = tid; i < (IMG_BYTES - OFF_B1) / 16; i += THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        mbar_init(&a_full[0], GROUP), mbar_init(&a_full[1], GROUP);
+        mbar_init(&mma_done[0], 1), mbar_init(&mma_done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == RAY_THREADS / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged B tiles are read by the async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int S1 = P.S;
+    const int S2 = P.add_input ? P.S + P.n_fine : P.n_fine;
+    const int total_steps = S1 + (P.n_passes > 1 ? S2 : 0);
+
+    if (warp >= RAY_THREADS / 32) {
+        // ============================ MMA issuer of group g ============================
+        const int g = warp - RAY_THREADS / 32;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(GROUP >> 4) << 24);
+        const uint32_t a = smem_u32(smem + (g ? OFF_A1 : OFF_A0));
+        const uint32_t b1 = smem_u32(smem + OFF_B1), b2 = smem_u32(smem + OFF_B2);
+        const uint32_t on = smem_u32(smem + OFF_ONES), bb = smem_u32(smem + OFF_BB);
+        const uint32_t d = tmem_base + (uint32_t)(g * HID);
+        for (int step = 0; step < total_steps; ++step) {
+            mbar_wait(&a_full[g], step & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                umma(d, sw128_desc(on), sw128_desc(bb), idesc, 0);                       // bias (starts the tile)
+                umma(d, sw128_desc(a), sw128_desc(b2), idesc, 1);                        // x_hi . W_lo, K 0..15
+                umma(d, sw128_desc(a + 32), sw128_desc(b2 + 32), idesc, 1);              //              K 16..31
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                                              // [x_hi|x_lo] . [W_hi|W_hi]
+                    umma(d, sw128_desc(a + 32 * k), sw128_desc(b1 + 32 * k), idesc, 1);
+                umma_commit(&mma_done[g]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================ ray threads ============================
+        const int g = warp / 4;
+        const int row = tid - g * GROUP;                 // row of the group's M tile = TMEM lane
+        const long long ray_raw = (long long)blockIdx.x * RAY_THREADS + tid;
+        const bool valid = ray_raw < P.n_rays;
+        const size_t ray = valid ? (size_t)ray_raw : (size_t)(P.n_rays - 1);  // idle lanes shadow the last ray
+        uint8_t* a_row = smem + (g ? OFF_A1 : OFF_A0) + (row / 8) * 1024 + (row % 8) * 128;
+        const int sw = row % 8;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp % 4) * 32) << 16) + (uint32_t)(g * HID);
+        const float* wsig = sF + F32_WSIG;
+        const float* lin = sF + F32_LIN;
+        const float b_sigma = sF[F32_MISC];
+
+        float o[3], d[3], dn[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) o[i] = P.origins[ray * 3 + i], d[i] = P.dirs[ray * 3 + i];
+        {
+            float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dn[i] = d[i] / nrm;
+        }
+        // per-ray constant of the radiance pre-activation: br + Wr[:, H:] . PE(dn) + 0.6 * wr . b_eff
+        float rd[3];
+        {
+            const int nh = P.n_harm, E = 3 * (2 * nh + 1);
+            const float* sDir = sF + F32_DIR;
+            const float* br = sDir + 3 * E;
+            rd[0] = br[0] + sF[F32_MISC + 1], rd[1] = br[1] + sF[F32_MISC + 2], rd[2] = br[2] + sF[F32_MISC + 3];
+            for (int c = 0; c < 3; ++c) {
+                float freq = 1.f;
+                for (int k = 0; k < nh; ++k) {
+                    float e = dn[c] * freq;
+                    float sn = sinf(e), cs = cosf(e);
+                    int ms = c * nh + k, mc = 3 * nh + c * nh + k;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + ms] * sn + sDir[i * E + mc] * cs;
+                    freq *= 2.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + 6 * nh + c] * dn[c];
+            }
+        }
+        const float* zin = P.lengths + ray * S1;
+        uint32_t phase_a = 0;  // completed MMA count parity for this group
+        const float eps = 1e-5f;
+        float w_tot = 0.f;     // sum_{i=1}^{S1-2} (w_i + eps), accumulated during the coarse pass
+
+        // sample the point at depth z: density (fp32), linear radiance part, operand row; then hand it to the MMA warp
+        float sig_n, lin_n[3];
+        auto produce = [&](float z) {
+            float x[32];
+            sample_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z * d[0]) * P.inv_x, (o[1] + z * d[1]) * P.inv_y,
+                            (o[2] + z * d[2]) * P.inv_z, x);
+            float s0 = b_sigma, s1 = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c += 2) {
+                s0 = fmaf(wsig[c], x[c], s0), s1 = fmaf(wsig[c + 1], x[c + 1], s1);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                l0 = fmaf(lin[c], x[c], l0), l1 = fmaf(lin[32 + c], x[c], l1), l2 = fmaf(lin[64 + c], x[c], l2);
+            }
+            sig_n = holo_leaky(s0 + s1);
+            lin_n[0] = l0, lin_n[1] = l1, lin_n[2] = l2;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float a0 = x[2 * c], a1 = x[2 * c + 1];
+                float h0 = __bfloat162float(__float2bfloat16_rn(a0)), h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                hi[c] = pack_bf16x2(a0, a1);
+                lo[c] = pack_bf16x2(a0 - h0, a1 - h1);
+            }
+            // row = [x_hi (4 chunks) | x_lo (4 chunks)], 16-byte chunk c lands at chunk (c ^ (row % 8))  (SWIZZLE_128B)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(a_row + ((c ^ sw) * 16)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4*>(a_row + (((c + 4) ^ sw) * 16)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&a_full[g]);
+        };
+
+        for (int pass = 0; pass < P.n_passes; ++pass) {
+            const int S = pass == 0 ? S1 : S2;
+            const bool last = pass == P.n_passes - 1;
+            // ---- depth stream: coarse depths, or the on-the-fly merge of coarse depths and inverse-cdf samples
+            int ic = 0, jf = 0, inds = 0;
+            float c_prev = 0.f, c_cur = 0.f, f_next = INFINITY;
+            const int ncdf = S1 - 1;
+            const float* wsc = P.scratch_w + ray;  // column of coarse weights, stride n_rays
+            auto gen_fine = [&]() {               // next inverse-cdf sample (sample_pdf, deterministic u)
+                if (jf >= P.n_fine) {
+                    f_next = INFINITY;
+                    return;
+                }
+                float u = linspace01(jf, P.n_fine);
+                while (inds < ncdf && c_cur <= u) {  // searchsorted(cdf, u, right=True)
+                    c_prev = c_cur;
+                    ++inds;
+                    if (inds < ncdf) c_cur = c_prev + (wsc[(size_t)inds * P.n_rays] + eps) / w_tot;
+                }
+                int below = max(inds - 1, 0), above = min(inds, ncdf - 1);
+                float c0 = c_prev, c1 = (inds < ncdf) ? c_cur : c_prev;
+                float b0 = 0.5f * (zin[below + 1] + zin[below]);
+                float b1 = 0.5f * (zin[above + 1] + zin[above]);
+                float den = c1 - c0;
+                if (den < eps) den = 1.f;
+                float t = (u - c0) / den;
+                f_next = b0 + t * (b1 - b0);
+            };
+            float z_last = -INFINITY;
+            auto next_z = [&]() -> float {
+                float z;
+                if (pass == 0) {
+                    z = zin[min(ic, S1 - 1)];
+                    ++ic;
+                } else {
+                    float zc = (P.add_input && ic < S1) ? zin[ic] : INFINITY;
+                    if (zc <= f_next) {
+                        z = zc;
+                        ++ic;
+                    } else {
+                        z = f_next;
+                        ++jf;
+                        gen_fine();
+                    }
+                    z = fmaxf(z, z_last);  // the two runs are sorted up to 1-ulp ties (torch.sort in the refiner)
+                }
+                z_last = z;
+                return z;
+            };
+            if (pass == 1) gen_fine();
+
+            float cum = 0.f, opac_prev = 0.f, af[3] = {0.f, 0.f, 0.f}, ad = 0.f;
+            float* wout = last ? P.weights : P.p_weights;
+            float* lout = (pass == 1) ? P.lengths_out : nullptr;
+            float z_cur = next_z();
+            float z_nxt = (S > 1) ? next_z() : z_cur;
+            produce(z_cur);
+            for (int s = 0; s < S; ++s) {
+                const float sig = sig_n;
+                float r0 = rd[0] + lin_n[0], r1 = rd[1] + lin_n[1], r2 = rd[2] + lin_n[2];
+                mbar_wait(&mma_done[g], phase_a);
+                phase_a ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int j0 = 0; j0 < HID; j0 += 32) {
+                    uint32_t t[32];
+                    tmem_ld32(taddr + (uint32_t)j0, t);
+                    const float4* ep = reinterpret_cast<const float4*>(sF + F32_EP + j0 * 3);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {  // 4 hidden units = 12 coefficients = 3 float4
+                        float4 e0 = ep[q * 3 + 0], e1 = ep[q * 3 + 1], e2 = ep[q * 3 + 2];
+                        float t0 = fabsf(__uint_as_float(t[q * 4 + 0])), t1 = fabsf(__uint_as_float(t[q * 4 + 1]));
+                        float t2 = fabsf(__uint_as_float(t[q * 4 + 2])), t3 = fabsf(__uint_as_float(t[q * 4 + 3]));
+                        r0 = fmaf(e0.x, t0, r0), r1 = fmaf(e0.y, t0, r1), r2 = fmaf(e0.z, t0, r2);
+                        r0 = fmaf(e0.w, t1, r0), r1 = fmaf(e1.x, t1, r1), r2 = fmaf(e1.y, t1, r2);
+                        r0 = fmaf(e1.z, t2, r0), r1 = fmaf(e1.w, t2, r1), r2 = fmaf(e2.x, t2, r2);
+                        r0 = fmaf(e2.y, t3, r0), r1 = fmaf(e2.z, t3, r1), r2 = fmaf(e2.w, t3, r2);
+                    }
+                }
+                // the accumulator and the operand row are free again: start the next depth step's MMA now
+                const float z_s = z_cur, z_n = z_nxt;
+                if (s + 1 < S) {
+                    z_cur = z_nxt;
+                    z_nxt = (s + 2 < S) ? next_z() : z_cur;
+                    produce(z_cur);
+                }
+                float rgb0 = 1.f / (1.f + expf(-holo_leaky(r0)));
+                float rgb1 = 1.f / (1.f + expf(-holo_leaky(r1)));
+                float rgb2 = 1.f / (1.f + expf(-holo_leaky(r2)));
+                float delta = (s + 1 < S) ? (z_n - z_s) : P.bg_opacity;
+                float wd = delta * fmaxf(sig, 0.f);
+                float capped = 1.f - expf(-wd);
+                cum += wd;
+                float opac = 1.f - expf(-cum);
+                float absorb = (s == 0) ? 1.f : (1.f - opac_prev);
+                float w = capped * absorb;
+                af[0] += w * rgb0, af[1] += w * rgb1, af[2] += w * rgb2;
+                ad += w * z_s;
+                opac_prev = opac;
+                if (valid) {
+                    if (wout) wout[ray * S + s] = w;
+                    if (lout) lout[ray * S + s] = z_s;
+                    if (!last) {
+                        P.scratch_w[(size_t)s * P.n_rays + ray] = w;
+                    }
+                }
+                if (!last && s >= 1 && s <= S1 - 2) w_tot += w + eps;
+            }
+            if (valid) {
+                float mask = opac_prev;
+                float* F = last ? P.features : P.p_features;
+                float* Dp = last ? P.depths : P.p_depths;
+                float* M = last ? P.masks : P.p_masks;
+                if (F) {
+                    F[ray * 3 + 0] = af[0] + (1.f - mask) * P.bg[0];
+                    F[ray * 3 + 1] = af[1] + (1.f - mask) * P.bg[1];
+                    F[ray * 3 + 2] = af[2] + (1.f - mask) * P.bg[2];
+                }
+                if (Dp) Dp[ray] = ad;
+                if (M) M[ray] = mask;
+            }
+            __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == RAY_THREADS / 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pack: collapsed density net (fp64) + radiance layer -> the shared-memory image above
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t sw128_off(int row, int byte_in_row) {
+    int chunk = byte_in_row / 16, within = byte_in_row % 16;
+    return (size_t)(row / 8) * 1024 + (row % 8) * 128 + ((chunk ^ (row % 8)) * 16) + within;
+}
+
+__global__ void pack_render_tc_fill_kernel(const double* __restrict__ A, const double* __restrict__ c,
+                                           const float* __restrict__ Wr, const float* __restrict__ br, int C, int E,
+                                           uint8_t* __restrict__ img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    __nv_bfloat16* b1 = reinterpret_cast<__nv_bfloat16*>(img + OFF_B1);
+    __nv_bfloat16* b2 = reinterpret_cast<__nv_bfloat16*>(img + OFF_B2);
+    __nv_bfloat16* on = reinterpret_cast<__nv_bfloat16*>(img + OFF_ONES);
+    __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(img + OFF_BB);
+    float* f32 = reinterpret_cast<float*>(img + OFF_F32);
+    for (int i = tid; i < HID * 32; i += nth) {
+        int j = i / 32, k = i % 32;
+        float w = (k < C) ? (float)A[(size_t)j * C + k] : 0.f;
+        __nv_bfloat16 h = __float2bfloat16_rn(w);
+        __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        b1[sw128_off(j, k * 2) / 2] = h;
+        b1[sw128_off(j, (32 + k) * 2) / 2] = h;
+        b2[sw128_off(j, k * 2) / 2] = l;
+    }
+    for (int j = tid; j < HID; j += nth) {
+        float b = (float)c[j];
+        __nv_bfloat16 h = __float2bfloat16_rn(b);
+        bb[sw128_off(j, 0) / 2] = h;
+        bb[sw128_off(j, 2) / 2] = __float2bfloat16_rn(b - __bfloat162float(h));
+        // 0.4 * wr[i][j], j-major triples
+        f32[F32_EP + j * 3 + 0] = 0.4f * Wr[0 * (HID + E) + j];
+        f32[F32_EP + j * 3 + 1] = 0.4f * Wr[1 * (HID + E) + j];
+        f32[F32_EP + j * 3 + 2] = 0.4f * Wr[2 * (HID + E) + j];
+    }
+    for (int r = tid; r < GROUP; r += nth) {
+        on[sw128_off(r, 0) / 2] = __float2bfloat16_rn(1.f);
+        on[sw128_off(r, 2) / 2] = __float2bfloat16_rn(1.f);
+    }
+    for (int k = tid; k < 32; k += nth) f32[F32_WSIG + k] = (k < C) ? (float)A[(size_t)HID * C + k] : 0.f;
+    for (int i = tid; i < 3 * 32; i += nth) {
+        int ch = i / 32, k = i % 32;
+        double acc = 0.0;
+        if (k < C)
+            for (int j = 0; j < HID; ++j) acc += (double)Wr[ch * (HID + E) + j] * A[(size_t)j * C + k];
+        f32[F32_LIN + i] = (float)(0.6 * acc);
+    }
+    if (tid < 3) {
+        double acc = 0.0;
+        for (int j = 0; j < HID; ++j) acc += (double)Wr[tid * (HID + E) + j] * c[j];
+        f32[F32_MISC + 1 + tid] = (float)(0.6 * acc);
+        f32[F32_DIR + 3 * E + tid] = br[tid];
+    }
+    if (tid == 0) f32[F32_MISC] = (float)c[HID];
+    for (int i = tid; i < 3 * E; i += nth) f32[F32_DIR + i] = Wr[(i / E) * (HID + E) + HID + (i % E)];
+}
+
+}  // namespace
+
+extern "C" long long holo_render_tc_image_bytes(void) { return IMG_BYTES; }
+
+extern "C" int holo_pack_render_mlp_tc(const double* A_eff, const double* c_eff, const float* Wr, const float* br, int H,
+                                       int C, int E, void* image, void* stream) {
+    HOLO_CHECK_ARG(A_eff && c_eff && Wr && br && image, "holo_pack_render_mlp_tc: null arg");
+    if (H != HID || !(C == 16 || C == 32) || E > 27 || E < 3) {
+        holo_set_error("holo_pack_render_mlp_tc: needs hidden=256, C in {16,32}, E<=27 (got %d, %d, %d)", H, C, E);
+        return HOLO_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    HOLO_CUDA(cudaMemsetAsync(image, 0, IMG_BYTES, st), "holo_pack_render_mlp_tc");
+    pack_render_tc_fill_kernel<<<32, 256, 0, st>>>(A_eff, c_eff, Wr, br, C, E, (uint8_t*)image);
+    HOLO_CHECK_LAUNCH("holo_pack_render_mlp_tc");
+    return HOLO_OK;
+}
+
+extern "C" int holo_render_fwd_tc(const float* grid_dhwc, int D, int H, int W, int C, float volume_extent,
+                                  const void* tc_image, int n_harmonic, const float* origins, const float* dirs,
+                                  const float* lengths, int n_rays, int S, int n_passes, int n_fine,
+                                  int add_input_samples, const float* bg3_host, float background_opacity,
+                                  float* features, float* depths, float* masks, float* weights, float* lengths_out,
+                                  float* prev_features, float* prev_depths, float* prev_masks, float* prev_weights,
+                                  float* scratch_weights, void* stream) {
+    if (n_rays == 0) return HOLO_OK;
+    HOLO_CHECK_ARG(grid_dhwc && tc_image && origins && dirs && lengths, "holo_render_fwd_tc: null input");
+    HOLO_CHECK_ARG(features && depths && masks, "holo_render_fwd_tc: null output");
+    HOLO_CHECK_ARG(n_passes == 1 || n_passes == 2, "holo_render_fwd_tc: n_passes must be 1 or 2");
+    HOLO_CHECK_ARG(S >= 2 && (n_passes == 1 || (n_fine >= 1 && S >= 3 && scratch_weights)),
+                   "holo_render_fwd_tc: bad S/n_fine or missing scratch (S*n_rays floats)");
+    HOLO_CHECK_ARG(D > 1 && H > 1 && W > 1, "holo_render_fwd_tc: grid must be at least 2^3");
+    if (!(C == 16 || C == 32)) {
+        holo_set_error("holo_render_fwd_tc: C=%d unsupported (16, 32)", C);
+        return HOLO_ERR_UNSUPPORTED;
+    }
+    RenderTcParams P;
+    P.grid = grid_dhwc, P.D = D, P.Hh = H, P.Ww = W, P.C = C;
+    P.inv_x = 1.0f / ((float)(W - 1) * (volume_extent / (float)W) * 0.5f);
+    P.inv_y = 1.0f / ((float)(H - 1) * (volume_extent / (float)H) * 0.5f);
+    P.inv_z = 1.0f / ((float)(D - 1) * (volume_extent / (float)D) * 0.5f);
+    P.image = (const uint8_t*)tc_image;
+    P.n_harm = n_harmonic;
+    P.origins = origins, P.dirs = dirs, P.lengths = lengths;
+    P.n_rays = n_rays, P.S = S, P.n_fine = n_passes > 1 ? n_fine : 0, P.add_input = add_input_samples ? 1 : 0;
+    P.n_passes = n_passes;
+    P.bg[0] = bg3_host ? bg3_host[0] : 1.f, P.bg[1] = bg3_host ? bg3_host[1] : 1.f, P.bg[2] = bg3_host ? bg3_host[2] : 1.f;
+    P.bg_opacity = background_opacity;
+    P.features = features, P.depths = depths, P.masks = masks, P.weights = weights, P.lengths_out = lengths_out;
+    P.p_features = prev_features, P.p_depths = prev_depths, P.p_masks = prev_masks, P.p_weights = prev_weights;
+    P.scratch_w = scratch_weights;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = holo_cdiv(n_rays, RAY_THREADS);
+    if (C == 32) {
+        HOLO_CUDA(cudaFuncSetAttribute(render_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+                  "holo_render_fwd_tc");
+        render_tc_kernel<32><<<blocks, THREADS, SMEM_BYTES, st>>>(P);
+    } else {
+        HOLO_CUDA(cudaFuncSetAttribute(render_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
+                  "holo_render_fwd_tc");
+        render_tc_kernel<16><<<blocks, THREADS, SMEM_BYTES, st>>>(P);
+    }
+    HOLO_CHECK_LAUNCH("holo_render_fwd_tc");
+    return HOLO_OK;
+}

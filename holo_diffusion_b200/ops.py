@@ -71,12 +71,18 @@ def collapse_and_pack_render_mlp(density_layers, skips, radiance_w, radiance_b, 
     packed = torch.empty(n, device=dev)
     lib().call("holo_pack_render_mlp", _ptr(A, torch.float64), _ptr(c, torch.float64), _ptr(radiance_w),
                _ptr(radiance_b), H, C, E, _ptr(packed), _stream())
-    return packed, H, E
+    tc_image = None
+    if H == 256 and C in (16, 32) and E <= 27:
+        tc_image = torch.empty(lib().cdll.holo_render_tc_image_bytes(), dtype=torch.uint8, device=dev)
+        lib().call("holo_pack_render_mlp_tc", _ptr(A, torch.float64), _ptr(c, torch.float64), _ptr(radiance_w),
+                   _ptr(radiance_b), H, C, E, _ptr(tc_image, torch.uint8), _stream())
+    return packed, H, E, tc_image
 
 
 def render_fwd(grid_dhwc, volume_extent: float, packed_mlp, hidden: int, n_harmonic: int, origins, dirs, lengths,
                n_passes: int = 1, n_fine: int = 0, add_input_samples: bool = True, bg=(1.0, 1.0, 1.0),
-               background_opacity: float = 1e10, return_weights: bool = False, return_prev: bool = True):
+               background_opacity: float = 1e10, return_weights: bool = False, return_prev: bool = True, tc_image=None):
+    """tc_image given -> the tcgen05 kernel (holo_render_fwd_tc), else the fp32 CUDA-core kernel (holo_render_fwd)."""
     D, H, W, C = grid_dhwc.shape
     n_rays, S = lengths.shape
     dev = grid_dhwc.device
@@ -97,13 +103,21 @@ def render_fwd(grid_dhwc, volume_extent: float, packed_mlp, hidden: int, n_harmo
             "weights": torch.empty(n_rays, S, device=dev) if return_weights else None,
             "lengths": lengths,
         }
-    lib().call("holo_render_fwd", _ptr(grid_dhwc), D, H, W, C, float(volume_extent), _ptr(packed_mlp), hidden,
-               n_harmonic, _ptr(origins), _ptr(dirs), _ptr(lengths), n_rays, S, n_passes, n_fine,
-               1 if add_input_samples else 0, ctypes.cast(_host3(bg), ctypes.c_void_p), float(background_opacity),
-               _ptr(out["features"]), _ptr(out["depths"]), _ptr(out["masks"]), _ptr(out["weights"]),
-               _ptr(out["lengths"]) if n_passes > 1 else None,
-               _ptr(prev["features"]) if prev else None, _ptr(prev["depths"]) if prev else None,
-               _ptr(prev["masks"]) if prev else None, _ptr(prev["weights"]) if prev else None, _stream())
+    tail = (_ptr(out["features"]), _ptr(out["depths"]), _ptr(out["masks"]), _ptr(out["weights"]),
+            _ptr(out["lengths"]) if n_passes > 1 else None,
+            _ptr(prev["features"]) if prev else None, _ptr(prev["depths"]) if prev else None,
+            _ptr(prev["masks"]) if prev else None, _ptr(prev["weights"]) if prev else None)
+    if tc_image is not None:
+        scratch = torch.empty(S * n_rays, device=dev) if n_passes > 1 else None
+        lib().call("holo_render_fwd_tc", _ptr(grid_dhwc), D, H, W, C, float(volume_extent), _ptr(tc_image, torch.uint8),
+                   n_harmonic, _ptr(origins), _ptr(dirs), _ptr(lengths), n_rays, S, n_passes, n_fine,
+                   1 if add_input_samples else 0, ctypes.cast(_host3(bg), ctypes.c_void_p), float(background_opacity),
+                   *tail, _ptr(scratch), _stream())
+    else:
+        lib().call("holo_render_fwd", _ptr(grid_dhwc), D, H, W, C, float(volume_extent), _ptr(packed_mlp), hidden,
+                   n_harmonic, _ptr(origins), _ptr(dirs), _ptr(lengths), n_rays, S, n_passes, n_fine,
+                   1 if add_input_samples else 0, ctypes.cast(_host3(bg), ctypes.c_void_p), float(background_opacity),
+                   *tail, _stream())
     out["prev"] = prev
     return out
 
@@ -172,10 +186,11 @@ def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, 
                1 if ups else 0, _ptr(w), _ptr(bias), _ptr(residual), Cout, _ptr(out), _stream())
 
 
-def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None) -> int:
-    """Returns the library status (0 ok, -3 unsupported shape); other errors raise."""
+def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None,
+              stride: int = 1) -> int:
+    """dims = INPUT volume.  Returns the library status (0 ok, -3 unsupported shape); other errors raise."""
     rc = lib().try_call("holo_conv3d_tc", _ptr(x_hi, torch.bfloat16), _ptr(x_lo, torch.bfloat16), Cin, dims[0],
-                        dims[1], dims[2], ksize, _ptr(w_hi, torch.bfloat16), _ptr(w_lo, torch.bfloat16), _ptr(bias),
+                        dims[1], dims[2], ksize, stride, _ptr(w_hi, torch.bfloat16), _ptr(w_lo, torch.bfloat16), _ptr(bias),
                         _ptr(residual), Cout, _ptr(out), _ptr(out_hi, torch.bfloat16), _ptr(out_lo, torch.bfloat16),
                         _stream())
     if rc not in (0, -3):

@@ -142,8 +142,9 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
                  stratified_sampling_coarse_training: bool = True, stratified_sampling_coarse_evaluation: bool = False,
                  append_coarse_samples_to_fine: bool = True, density_noise_std_train: float = 1.0,
                  return_weights: bool = False, raymarcher_class_type: str = "EmissionAbsorptionRaymarcher",
-                 raymarcher_EmissionAbsorptionRaymarcher_args: Optional[dict] = None):
+                 raymarcher_EmissionAbsorptionRaymarcher_args: Optional[dict] = None, use_tensor_cores: bool = True):
         super().__init__()
+        self.use_tensor_cores = use_tensor_cores
         if raymarcher_class_type != "EmissionAbsorptionRaymarcher":
             raise NotImplementedError("only EmissionAbsorptionRaymarcher is fused")
         rm = dict(surface_thickness=1, bg_color=(0.0,), replicate_last_interval=False, background_opacity=1e10,
@@ -182,7 +183,7 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
             assert grid is not None, "voxel_grid_features must be provided!"
             assert grid.shape[0] == 1, "only one voxel grid per process (holo_diffusion_model.py:326)"
             grid_cl = grid_to_channels_last(grid)
-        packed, hidden, E = fn.render_mlp.packed()
+        packed, hidden, E, tc_image = fn.render_mlp.packed()
         spatial = ray_bundle.lengths.shape[:-1]
         S = ray_bundle.lengths.shape[-1]
         n = int(torch.Size(spatial).numel())
@@ -191,7 +192,7 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
                              ray_bundle.lengths.reshape(n, S).contiguous(), n_passes=n_passes,
                              n_fine=self.n_pts_per_ray_fine_evaluation, add_input_samples=self.append_coarse_samples_to_fine,
                              bg=self.bg_color, background_opacity=self.background_opacity,
-                             return_weights=self.return_weights)
+                             return_weights=self.return_weights, tc_image=tc_image if self.use_tensor_cores else None)
 
         def wrap(o, prev):
             return RendererOutput(features=o["features"].view(*spatial, 3), depths=o["depths"].view(*spatial, 1),

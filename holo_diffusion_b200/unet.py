@@ -157,8 +157,8 @@ class _PackedConv:
 
 
 def _tile_ok(dims) -> bool:
-    D, H, W = dims  # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels
-    return W % 8 == 0 and H % 4 == 0 and D % 4 == 0
+    D, H, W = dims  # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels, or 4 x 4 x 4 for the coarsest levels
+    return W % 4 == 0 and H % 4 == 0 and D % 4 == 0
 
 
 class UNetExecutor:
@@ -233,16 +233,18 @@ class UNetExecutor:
         ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None, act.x2, act.c2)
         return hi, lo
 
-    def _conv_tc(self, pc: _PackedConv, hi, lo, out_dims, residual=None, want_split_out=False) -> _Act:
+    def _conv_tc(self, pc: _PackedConv, hi, lo, in_dims, residual=None, want_split_out=False, stride=1) -> _Act:
         dev = hi.device
         k = 3 if pc.taps == 27 else 1
+        out_dims = tuple(d // stride for d in in_dims)
         Vo = out_dims[0] * out_dims[1] * out_dims[2]
         out = torch.empty(Vo, pc.cout, device=dev)
         o_hi = o_lo = None
         if want_split_out:
             o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
             o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
-        rc = ops.conv3d_tc(hi, lo, pc.cin_pad, out_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo)
+        rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
+                           stride)
         if rc != 0:
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
@@ -283,10 +285,11 @@ class UNetExecutor:
         """conv on a raw activation (first conv, skip 1x1, Upsample/Downsample convs)."""
         pc = self._pc(mod)
         D, H, W = act.dims
-        od = (2 * D, 2 * H, 2 * W) if ups else (D, H, W)
-        if stride == 1 and self._tc_ok(pc, od):
+        ind = (2 * D, 2 * H, 2 * W) if ups else (D, H, W)   # volume the convolution reads
+        even = all(d % 2 == 0 for d in ind)
+        if (stride == 1 or even) and self._tc_ok(pc, tuple(d // stride for d in ind)):
             hi, lo = self._split_raw(act, pc, ups)
-            return self._conv_tc(pc, hi, lo, od, residual)
+            return self._conv_tc(pc, hi, lo, ind, residual, stride=stride)
         return self._conv_simt(pc, act, stride=stride, ups=ups, residual=residual)
 
     # -- blocks --------------------------------------------------------------------------------------------

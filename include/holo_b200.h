@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 102
+#define HOLO_B200_VERSION 104
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -71,6 +71,20 @@ int holo_render_fwd(const float* grid_dhwc, int D, int H, int W, int C, float vo
                     float* weights, float* lengths_out, float* prev_features, float* prev_depths, float* prev_masks,
                     float* prev_weights, void* stream);
 
+/* Tensor-core version of the fused renderer (same contract and outputs as holo_render_fwd): the 256-wide hidden
+ * layer runs on tcgen05 as a 3xBF16 split (M = 128 rays of one depth step), density / compositing / re-sampling stay
+ * in fp32 registers.  C in {16, 32}, hidden = 256.  tc_image: holo_render_tc_image_bytes() bytes written by
+ * holo_pack_render_mlp_tc from the collapsed net; scratch_weights: S * n_rays floats (two passes only). */
+long long holo_render_tc_image_bytes(void);
+int holo_pack_render_mlp_tc(const double* A_eff, const double* c_eff, const float* Wr, const float* br, int H, int C,
+                            int E, void* image, void* stream);
+int holo_render_fwd_tc(const float* grid_dhwc, int D, int H, int W, int C, float volume_extent, const void* tc_image,
+                       int n_harmonic, const float* origins, const float* dirs, const float* lengths, int n_rays,
+                       int S, int n_passes, int n_fine, int add_input_samples, const float* bg3_host,
+                       float background_opacity, float* features, float* depths, float* masks, float* weights,
+                       float* lengths_out, float* prev_features, float* prev_depths, float* prev_masks,
+                       float* prev_weights, float* scratch_weights, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Denoiser (guided_diffusion UNetModel, unet.py:566-837) building blocks
  * ------------------------------------------------------------------------------------------------------- */
@@ -102,11 +116,13 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
                      const float* residual, int Cout, float* out, void* stream);
 
 /* tcgen05 (5th-gen tensor core) implicit-GEMM convolution, 3xBF16 split operands, fp32 TMEM accumulation.
- * Same contract as holo_conv3d_simt for ksize 1|3, stride 1, no upsample, one source; operands are bf16 hi/lo
- * pairs: x_hi/x_lo (V,Cin) channels-last, w_hi/w_lo [Cout][tap][Cin] (K-major).  Cin % 64 == 0, Cout % 16 == 0,
- * Cout <= 256 per call.  Returns HOLO_ERR_UNSUPPORTED (-3) for shapes it does not take. */
-int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, const void* w_hi,
-                   const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
+ * Same contract as holo_conv3d_simt for ksize 1|3, stride 1|2 (Downsample.op, unet.py:129-131), one source; operands
+ * are bf16 hi/lo pairs: x_hi/x_lo (V,Cin) channels-last over the INPUT volume (D,H,W), w_hi/w_lo [Cout][tap][Cin]
+ * (K-major).  Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with
+ * fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
+ * shapes it does not take. */
+int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
+                   const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
                    void* out_hi_bf16, void* out_lo_bf16, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16

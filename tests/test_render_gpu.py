@@ -17,35 +17,42 @@ def _pack(p, C, dev):
                                             p["_radiance_net.mlp.0.0.bias"].to(dev), C)
 
 
-def _cuda_render(grid, p, bundle, extent, n_passes, n_fine, weights=True):
+def _cuda_render(grid, p, bundle, extent, n_passes, n_fine, weights=True, tc=False):
     from holo_diffusion_b200 import ops
     dev = "cuda"
     C = grid.shape[1]
-    packed, H, E = _pack(p, C, dev)
+    packed, H, E, tc_image = _pack(p, C, dev)
+    if tc:
+        assert tc_image is not None
     g = grid[0].permute(1, 2, 3, 0).contiguous().to(dev)
     n = bundle.origins[0].reshape(-1, 3).shape[0]
     S = bundle.lengths.shape[-1]
     out = ops.render_fwd(g, extent, packed, H, (E // 3 - 1) // 2, bundle.origins[0].reshape(n, 3).contiguous().to(dev),
                          bundle.directions[0].reshape(n, 3).contiguous().to(dev),
                          bundle.lengths[0].reshape(n, S).contiguous().to(dev), n_passes=n_passes, n_fine=n_fine,
-                         return_weights=weights)
+                         return_weights=weights, tc_image=tc_image if tc else None)
     torch.cuda.synchronize()
     return out
 
 
-@pytest.mark.parametrize("C,R,HW,S,n_passes,n_fine", [
-    (16, 32, 64, 16, 1, 0),    # BASELINE cfg #1, single pass
-    (16, 32, 64, 16, 2, 16),   # cfg #1, reference-faithful two-pass
-    (32, 16, 24, 64, 2, 16),   # base.yaml sampling (64 + 16) on a small grid
-    (8, 8, 9, 5, 2, 3),        # odd sizes: ragged tile, odd S, tiny n_fine
-    (64, 16, 16, 32, 2, 64),   # shipped configs: 64 channels, teddybear.yaml n_fine 64
+@pytest.mark.parametrize("C,R,HW,S,n_passes,n_fine,tc", [
+    (16, 32, 64, 16, 1, 0, False),    # BASELINE cfg #1, single pass
+    (16, 32, 64, 16, 2, 16, False),   # cfg #1, reference-faithful two-pass
+    (32, 16, 24, 64, 2, 16, False),   # base.yaml sampling (64 + 16) on a small grid
+    (8, 8, 9, 5, 2, 3, False),        # odd sizes: ragged tile, odd S, tiny n_fine
+    (64, 16, 16, 32, 2, 64, False),   # shipped configs: 64 channels, teddybear.yaml n_fine 64
+    (16, 32, 64, 16, 1, 0, True),     # the same through the tcgen05 kernel
+    (16, 32, 64, 16, 2, 16, True),
+    (32, 16, 24, 64, 2, 16, True),
+    (32, 8, 9, 5, 2, 3, True),        # ragged: 81 rays in one 256-ray CTA, odd S
+    (32, 16, 40, 8, 2, 64, True),     # several CTAs, more fine than coarse samples
 ])
-def test_render_matches_oracle(C, R, HW, S, n_passes, n_fine):
+def test_render_matches_oracle(C, R, HW, S, n_passes, n_fine, tc):
     grid, p = make_grid(C, R), make_mlp(C)
     cams = ro.simple_360_cameras(8)
     b = ro.sample_rays(cams[1], HW, HW, S)
     ref = ro.render_chunked(p, grid, b, R, 8.0, n_passes, n_fine, chunk_size_grid=0)
-    out = _cuda_render(grid, p, b, 8.0, n_passes, n_fine)
+    out = _cuda_render(grid, p, b, 8.0, n_passes, n_fine, tc=tc)
     n = HW * HW
     assert ref.masks.min() < 0.9 and ref.masks.max() > 0.9, "fixture must exercise compositing"
     if n_passes == 1:
@@ -100,7 +107,7 @@ def test_render_empty_and_outside():
     from holo_diffusion_b200 import ops
     C, R = 16, 8
     grid, p = make_grid(C, R), make_mlp(C)
-    packed, H, E = _pack(p, C, "cuda")
+    packed, H, E, _ = _pack(p, C, "cuda")
     g = grid[0].permute(1, 2, 3, 0).contiguous().cuda()
     o = torch.tensor([[100.0, 100.0, 100.0]] * 4).cuda()
     d = torch.tensor([[0.0, 0.0, 1.0]] * 4).cuda()

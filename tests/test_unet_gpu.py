@@ -152,6 +152,9 @@ def test_unet_small_arch_batch2():
     (64, 32, (8, 8, 16), 3),       # final conv: narrow N
     (64, 16, (4, 8, 8), 3),        # cfg #1 output width
     (128, 384, (16, 4, 8), 1),     # qkv as a GEMM over 512 tokens
+    (512, 512, (4, 4, 4), 3),      # coarsest level: 64-row tile + split-K over 216 (tap, slab) iterations
+    (256, 256, (8, 8, 8), 3),      # 8^3 level: split-K
+    (1024, 512, (4, 4, 4), 1),     # 1x1 skip at the coarsest level
 ])
 def test_conv_tc(Cin, Cout, dims, k):
     """tcgen05 3xBF16 convolution against fp32 F.conv3d; also checks the fused hi/lo split of the result."""
@@ -179,6 +182,32 @@ def test_conv_tc(Cin, Cout, dims, k):
     assert rc == 0
     assert rel_err(_from_cl(out, Cout, dims), ref) < 2e-5
     assert rel_err(o_hi.float() + o_lo.float(), out) < 2e-5
+    out2 = torch.empty_like(out)  # without the fused split output small grids take the split-K path
+    assert ops.conv3d_tc(hi, lo, Cin, dims, k, w_hi, w_lo, b.cuda(), _cl(res), Cout, out2) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out2, out) < 1e-5
+
+
+@pytest.mark.parametrize("C,R", [(64, 16), (128, 8)])
+def test_conv_tc_stride2(C, R):
+    """Downsample.op on the tensor cores: TMA element strides pick every second voxel."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, C, R, R, R, generator=g)
+    w = torch.randn(C, C, 3, 3, 3, generator=g) / math.sqrt(C * 27)
+    b = torch.randn(C, generator=g)
+    ref = F.conv3d(x, w, b, stride=2, padding=1)
+    V = R ** 3
+    hi = torch.empty(V, C, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(_cl(x), V, C, C, hi, lo)
+    wk = w.reshape(C, C, -1).permute(0, 2, 1).contiguous().cuda()
+    w_hi = wk.to(torch.bfloat16)
+    w_lo = (wk - w_hi.float()).to(torch.bfloat16)
+    out = torch.empty((R // 2) ** 3, C, device="cuda")
+    assert ops.conv3d_tc(hi, lo, C, (R, R, R), 3, w_hi, w_lo, b.cuda(), None, C, out, stride=2) == 0
+    torch.cuda.synchronize()
+    assert rel_err(_from_cl(out, C, (R // 2,) * 3), ref) < 2e-5
 
 
 def test_split_pad_and_upsample():
