@@ -44,42 +44,48 @@ extern "C" int holo_transpose2d(const float* src, float* dst, int rows, int cols
 // Every block reduces a slab of voxels; per-channel partials in fp32, combined per group and accumulated
 // into global fp64 (sum, sumsq).  acc must be zeroed (holo_gn_finalize re-zeroes it after use).
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-                                long long V, int vox_per_block, double* __restrict__ acc) {
-    extern __shared__ float sh[];  // 2 * C
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                        int C2, long long V, int vox_per_block,
+                                                        double* __restrict__ acc) {
+    extern __shared__ float sh[];  // [vstep][2C] per-thread partials, then [2C] totals
     const int C = C1 + C2;
     const int cq = C / 4;  // float4 lanes per voxel
-    float* s_sum = sh;
-    float* s_sq = sh + C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
     long long v0 = (long long)blockIdx.x * vox_per_block;
     long long v1 = v0 + vox_per_block;
     if (v1 > V) v1 = V;
     // thread t owns float4 lane (t % cq) and walks voxels with stride blockDim/cq
     const int lane = threadIdx.x % cq;
+    const int vrow = threadIdx.x / cq;
     const int vstep = blockDim.x / cq;
     const int c = lane * 4;
-    if (threadIdx.x < vstep * cq) {
-        float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-        for (long long v = v0 + threadIdx.x / cq; v < v1; v += vstep) {
-            float4 a = (c < C1) ? *reinterpret_cast<const float4*>(x1 + v * C1 + c)
-                                : *reinterpret_cast<const float4*>(x2 + v * C2 + (c - C1));
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    if (vrow < vstep) {
+        const float* base = (c < C1) ? x1 + c : x2 + (c - C1);
+        const int pitch = (c < C1) ? C1 : C2;
+#pragma unroll 4
+        for (long long v = v0 + vrow; v < v1; v += vstep) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(base + v * pitch));
             s.x += a.x, s.y += a.y, s.z += a.z, s.w += a.w;
-            q.x += a.x * a.x, q.y += a.y * a.y, q.z += a.z * a.z, q.w += a.w * a.w;
+            q.x = fmaf(a.x, a.x, q.x), q.y = fmaf(a.y, a.y, q.y), q.z = fmaf(a.z, a.z, q.z), q.w = fmaf(a.w, a.w, q.w);
         }
-        atomicAdd(&s_sum[c + 0], s.x), atomicAdd(&s_sum[c + 1], s.y);
-        atomicAdd(&s_sum[c + 2], s.z), atomicAdd(&s_sum[c + 3], s.w);
-        atomicAdd(&s_sq[c + 0], q.x), atomicAdd(&s_sq[c + 1], q.y);
-        atomicAdd(&s_sq[c + 2], q.z), atomicAdd(&s_sq[c + 3], q.w);
+        float* row = sh + (size_t)vrow * 2 * C;
+        *reinterpret_cast<float4*>(row + c) = s;
+        *reinterpret_cast<float4*>(row + C + c) = q;
+    }
+    __syncthreads();
+    // column sums over the vstep rows: thread t < 2C owns one (channel, sum|sumsq) column
+    for (int col = threadIdx.x; col < 2 * C; col += blockDim.x) {
+        float tot = 0.f;
+        for (int r = 0; r < vstep; ++r) tot += sh[(size_t)r * 2 * C + col];
+        sh[col] = tot;  // row 0 becomes the totals (each column is owned by one thread)
     }
     __syncthreads();
     const int cpg = C / 32;
-    if (threadIdx.x < 32) {
-        double s = 0, q = 0;
-        for (int k = 0; k < cpg; ++k) s += (double)s_sum[threadIdx.x * cpg + k], q += (double)s_sq[threadIdx.x * cpg + k];
-        atomicAdd(&acc[threadIdx.x * 2], s);
-        atomicAdd(&acc[threadIdx.x * 2 + 1], q);
+    if (threadIdx.x < 64) {
+        const int g = threadIdx.x % 32, which = threadIdx.x / 32;  // which: 0 sum, 1 sumsq
+        double a = 0;
+        for (int k = 0; k < cpg; ++k) a += (double)sh[which * C + g * cpg + k];
+        atomicAdd(&acc[g * 2 + which], a);
     }
 }
 
@@ -95,8 +101,9 @@ extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, l
     long long vpb = (V + 148 * 8 - 1) / (148 * 8);
     if (vpb < 64) vpb = 64;
     int blocks = holo_cdiv(V, vpb);
-    gn_stats_kernel<<<blocks, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb,
-                                                                                    acc64);
+    const int vstep = threads / (C / 4);
+    size_t smem = (size_t)(vstep > 1 ? vstep : 1) * 2 * C * sizeof(float);
+    gn_stats_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb, acc64);
     HOLO_CHECK_LAUNCH("holo_gn_stats");
     return HOLO_OK;
 }
@@ -107,12 +114,16 @@ extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, l
 __global__ void gn_finalize_kernel(double* __restrict__ acc, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ film, int C,
                                    double count, float eps, float* __restrict__ a, float* __restrict__ b) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // single block: after every thread has read the statistics they are re-zeroed for the next GroupNorm
+    __shared__ double s_acc[64];
+    if (threadIdx.x < 64) s_acc[threadIdx.x] = acc[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < 64) acc[threadIdx.x] = 0.0;
     int cpg = C / 32;
-    if (c < C) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         int g = c / cpg;
-        double mean = acc[g * 2] / count;
-        double var = acc[g * 2 + 1] / count - mean * mean;
+        double mean = s_acc[g * 2] / count;
+        double var = s_acc[g * 2 + 1] / count - mean * mean;
         if (var < 0) var = 0;
         float rstd = (float)(1.0 / sqrt(var + (double)eps));
         float aa = rstd * gamma[c];
@@ -134,9 +145,7 @@ extern "C" int holo_gn_finalize(double* acc64, const float* gamma, const float* 
                                 int C, long long V, float eps, float* a, float* b, void* stream) {
     HOLO_CHECK_ARG(acc64 && gamma && beta && a && b && C % 32 == 0, "holo_gn_finalize: bad args");
     double count = (double)V * (double)(C / 32);
-    gn_finalize_kernel<<<holo_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(acc64, gamma, beta, film_scale_shift, C,
-                                                                           count, eps, a, b);
-    zero_f64_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(acc64, 64);
+    gn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc64, gamma, beta, film_scale_shift, C, count, eps, a, b);
     HOLO_CHECK_LAUNCH("holo_gn_finalize");
     return HOLO_OK;
 }

@@ -185,7 +185,7 @@ def test_conv_tc(Cin, Cout, dims, k):
     out2 = torch.empty_like(out)  # without the fused split output small grids take the split-K path
     assert ops.conv3d_tc(hi, lo, Cin, dims, k, w_hi, w_lo, b.cuda(), _cl(res), Cout, out2) == 0
     torch.cuda.synchronize()
-    assert rel_err(out2, out) < 1e-5
+    assert rel_err(_from_cl(out2, Cout, dims), ref) < 2e-5
 
 
 @pytest.mark.parametrize("C,R", [(64, 16), (128, 8)])
