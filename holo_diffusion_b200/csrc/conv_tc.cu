@@ -20,6 +20,7 @@
 #include "../../include/holo_b200.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -397,7 +398,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     // gridDim.z and accumulate with fp32 atomics into a zeroed output (>= 4 iterations per slice)
     int nsplit = 1, per = k_total;
     const int base = tiles * (Cout / block_n);
-    if (base < 120 && k_total >= 8 && out && !out_hi_bf16) {
+    if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && out_pitch == Cout) {
         int want = (296 + base - 1) / base;
         int maxs = k_total / 4;
         nsplit = want < maxs ? want : maxs;
@@ -435,10 +436,23 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     }
 }
 
+int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, const void* w_hi,
+                        const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
+                        void* out_hi, void* out_lo, cudaStream_t st);
+
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
     const int taps = ksize * ksize * ksize;
+    // large 3^3 stride-1 layers: halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic
+    static const bool no_halo = getenv("HOLO_CONV_NO_HALO") != nullptr;
+    if (!no_halo && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
+        (out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr) && W % 8 == 0 && H % 16 == 0 && D % 2 == 0 &&
+        Cout % 64 == 0 && Cin % 64 == 0 && (long long)(W / 8) * (H / 16) * (D / 2) * (Cout / 64) >= 120) {
+        int rc = holo_conv3d_tc_halo(x_hi, x_lo, Cin, D, H, W, w_hi, w_lo, bias, residual, Cout, out, out_hi_bf16,
+                                     out_lo_bf16, (cudaStream_t)stream);
+        if (rc != HOLO_ERR_UNSUPPORTED) return rc;
+    }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream);
 }

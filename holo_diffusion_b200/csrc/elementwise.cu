@@ -42,7 +42,8 @@ extern "C" int holo_transpose2d(const float* src, float* dst, int rows, int cols
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics over a channels-last tensor made of up to two sources (the skip concat, unet.py:829).
 // Every block reduces a slab of voxels; per-channel partials in fp32, combined per group and accumulated
-// into global fp64 (sum, sumsq).  acc must be zeroed (holo_gn_finalize re-zeroes it after use).
+// into global fp64 (sum, sumsq), 8 replicas x 32 groups x 2.  acc (512 doubles) must be zeroed (holo_gn_finalize
+// re-zeroes it after use).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
                                                         int C2, long long V, int vox_per_block,
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         const int g = threadIdx.x % 32, which = threadIdx.x / 32;  // which: 0 sum, 1 sumsq
         double a = 0;
         for (int k = 0; k < cpg; ++k) a += (double)sh[which * C + g * cpg + k];
-        atomicAdd(&acc[g * 2 + which], a);
+        // 8 replicas of the accumulator spread the same-address fp64 atomics of ~1000 CTAs
+        atomicAdd(&acc[(blockIdx.x & 7) * 64 + g * 2 + which], a);
     }
 }
 
@@ -97,9 +99,9 @@ extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, l
     HOLO_CHECK_ARG(C2 == 0 || x2, "holo_gn_stats: second source missing");
     int threads = 256;
     if (C / 4 > threads) threads = C / 4;
-    // aim for >= 4 waves of 148 SMs but at least 64 voxels per block
-    long long vpb = (V + 148 * 8 - 1) / (148 * 8);
-    if (vpb < 64) vpb = 64;
+    // ~4 CTAs per SM for the big tensors; the coarse levels (V = 64 .. 4096) still get several CTAs
+    long long vpb = (V + 148 * 4 - 1) / (148 * 4);
+    if (vpb < 8) vpb = 8;
     int blocks = holo_cdiv(V, vpb);
     const int vstep = threads / (C / 4);
     size_t smem = (size_t)(vstep > 1 ? vstep : 1) * 2 * C * sizeof(float);
@@ -116,9 +118,14 @@ __global__ void gn_finalize_kernel(double* __restrict__ acc, const float* __rest
                                    double count, float eps, float* __restrict__ a, float* __restrict__ b) {
     // single block: after every thread has read the statistics they are re-zeroed for the next GroupNorm
     __shared__ double s_acc[64];
-    if (threadIdx.x < 64) s_acc[threadIdx.x] = acc[threadIdx.x];
+    if (threadIdx.x < 64) {
+        double a = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a += acc[r * 64 + threadIdx.x];
+        s_acc[threadIdx.x] = a;
+    }
     __syncthreads();
-    if (threadIdx.x < 64) acc[threadIdx.x] = 0.0;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) acc[i] = 0.0;
     int cpg = C / 32;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         int g = c / cpg;

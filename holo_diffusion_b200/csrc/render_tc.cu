@@ -100,6 +100,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld and pin the register uses behind it (zero-instruction "launder" asms)
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+        asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]),
+                          "+r"(r[i + 6]), "+r"(r[i + 7]));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
            ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
@@ -165,6 +184,24 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ grid, int
                 f[c4 * 4 + 3] += v.w * w;
             }
         }
+    }
+}
+
+// L1 prefetch of the 8 corner lines of a point (one 128-byte line per corner at C = 32)
+template <int C>
+__device__ __forceinline__ void prefetch_point(const float* __restrict__ grid, int D, int H, int W, float lx, float ly,
+                                               float lz) {
+    float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
+    float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
+    float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
+    int x0 = (int)fminf(fmaxf(floorf(ix), -2.f), (float)W + 1.f);
+    int y0 = (int)fminf(fmaxf(floorf(iy), -2.f), (float)H + 1.f);
+    int z0 = (int)fminf(fmaxf(floorf(iz), -2.f), (float)D + 1.f);
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+        int xx = x0 + (corner & 1), yy = y0 + ((corner >> 1) & 1), zz = z0 + (corner >> 2);
+        if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(grid + (((size_t)zz * H + yy) * W + xx) * C));
     }
 }
 
@@ -369,23 +406,36 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
             for (int s = 0; s < S; ++s) {
                 const float sig = sig_n;
                 float r0 = rd[0] + lin_n[0], r1 = rd[1] + lin_n[1], r2 = rd[2] + lin_n[2];
+                if (s + 1 < S)  // warm L1 with the next point's corners while this step's MMA / epilogue run
+                    prefetch_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_nxt * d[0]) * P.inv_x,
+                                      (o[1] + z_nxt * d[1]) * P.inv_y, (o[2] + z_nxt * d[2]) * P.inv_z);
                 mbar_wait(&mma_done[g], phase_a);
                 phase_a ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int j0 = 0; j0 < HID; j0 += 32) {
-                    uint32_t t[32];
-                    tmem_ld32(taddr + (uint32_t)j0, t);
-                    const float4* ep = reinterpret_cast<const float4*>(sF + F32_EP + j0 * 3);
+                {
+                    uint32_t ta[32], tb[32];
+                    auto consume = [&](const uint32_t (&t)[32], int j0) {
+                        const float4* ep = reinterpret_cast<const float4*>(sF + F32_EP + j0 * 3);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {  // 4 hidden units = 12 coefficients = 3 float4
-                        float4 e0 = ep[q * 3 + 0], e1 = ep[q * 3 + 1], e2 = ep[q * 3 + 2];
-                        float t0 = fabsf(__uint_as_float(t[q * 4 + 0])), t1 = fabsf(__uint_as_float(t[q * 4 + 1]));
-                        float t2 = fabsf(__uint_as_float(t[q * 4 + 2])), t3 = fabsf(__uint_as_float(t[q * 4 + 3]));
-                        r0 = fmaf(e0.x, t0, r0), r1 = fmaf(e0.y, t0, r1), r2 = fmaf(e0.z, t0, r2);
-                        r0 = fmaf(e0.w, t1, r0), r1 = fmaf(e1.x, t1, r1), r2 = fmaf(e1.y, t1, r2);
-                        r0 = fmaf(e1.z, t2, r0), r1 = fmaf(e1.w, t2, r1), r2 = fmaf(e2.x, t2, r2);
-                        r0 = fmaf(e2.y, t3, r0), r1 = fmaf(e2.z, t3, r1), r2 = fmaf(e2.w, t3, r2);
+                        for (int q = 0; q < 8; ++q) {  // 4 hidden units = 12 coefficients = 3 float4
+                            float4 e0 = ep[q * 3 + 0], e1 = ep[q * 3 + 1], e2 = ep[q * 3 + 2];
+                            float t0 = fabsf(__uint_as_float(t[q * 4 + 0])), t1 = fabsf(__uint_as_float(t[q * 4 + 1]));
+                            float t2 = fabsf(__uint_as_float(t[q * 4 + 2])), t3 = fabsf(__uint_as_float(t[q * 4 + 3]));
+                            r0 = fmaf(e0.x, t0, r0), r1 = fmaf(e0.y, t0, r1), r2 = fmaf(e0.z, t0, r2);
+                            r0 = fmaf(e0.w, t1, r0), r1 = fmaf(e1.x, t1, r1), r2 = fmaf(e1.y, t1, r2);
+                            r0 = fmaf(e1.z, t2, r0), r1 = fmaf(e1.w, t2, r1), r2 = fmaf(e2.x, t2, r2);
+                            r0 = fmaf(e2.y, t3, r0), r1 = fmaf(e2.z, t3, r1), r2 = fmaf(e2.w, t3, r2);
+                        }
+                    };
+                    tmem_ld32_async(taddr, ta);
+#pragma unroll 1
+                    for (int j0 = 0; j0 < HID; j0 += 64) {  // the load of the next 32 columns overlaps the FMAs
+                        tmem_ld_wait(ta);
+                        tmem_ld32_async(taddr + (uint32_t)(j0 + 32), tb);
+                        consume(ta, j0);
+                        tmem_ld_wait(tb);
+                        if (j0 + 64 < HID) tmem_ld32_async(taddr + (uint32_t)(j0 + 64), ta);
+                        consume(tb, j0 + 32);
                     }
                 }
                 // the accumulator and the operand row are free again: start the next depth step's MMA now

@@ -364,7 +364,7 @@ class UNetExecutor:
         p = self.p
         dev = x_cl.device
         if self._acc is None or self._acc.device != dev:
-            self._acc = torch.zeros(64, dtype=torch.float64, device=dev)
+            self._acc = torch.zeros(512, dtype=torch.float64, device=dev)
         mc = p.model_channels
         e0 = torch.empty(1, mc, device=dev)
         ops.timestep_embedding(t, mc, e0)

@@ -93,7 +93,7 @@ int holo_render_fwd_tc(const float* grid_dhwc, int D, int H, int W, int C, float
 int holo_transpose2d(const float* src, float* dst, int rows, int cols, void* stream);
 
 /* GroupNorm32(32, C) -- nn.py:23-25,99-106 -- over channels-last x = cat(x1 (V,C1), x2 (V,C2)) (th.cat, unet.py:829).
- * stats accumulates (sum, sumsq) per group in acc64[32][2] (must start zeroed; finalize re-zeroes it);
+ * stats accumulates (sum, sumsq) per group in acc64[8][32][2] (8 replicas; must start zeroed; finalize re-zeroes it);
  * finalize turns them into the per-channel affine y = x*a + b, folding gamma/beta and, when
  * film_scale_shift (2C: scale then shift) is given, the FiLM h*(1+scale)+shift of unet.py:248-252;
  * apply writes act(x*a+b) (act = SiLU, unet.py:184,208) as fp32 and/or as a bf16 hi/lo pair. */

@@ -63,7 +63,7 @@ def test_groupnorm(C1, C2, R, film, silu):
     if silu:
         ref = F.silu(ref)
     V = R ** 3
-    acc = torch.zeros(64, dtype=torch.float64, device="cuda")
+    acc = torch.zeros(512, dtype=torch.float64, device="cuda")
     x1, x2 = _cl(x[:, :C1]), (_cl(x[:, C1:]) if C2 else None)
     ops.gn_stats(x1, C1, x2, C2, V, acc)
     a, b = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
@@ -180,12 +180,13 @@ def test_conv_tc(Cin, Cout, dims, k):
     rc = ops.conv3d_tc(hi, lo, Cin, dims, k, w_hi, w_lo, b.cuda(), _cl(res), Cout, out, o_hi, o_lo)
     torch.cuda.synchronize()
     assert rc == 0
-    assert rel_err(_from_cl(out, Cout, dims), ref) < 2e-5
+    tol = 2e-5 if Cin * k ** 3 < 8192 else 4e-5   # 3xBF16 error grows ~sqrt(K); the bar is 1e-4
+    assert rel_err(_from_cl(out, Cout, dims), ref) < tol
     assert rel_err(o_hi.float() + o_lo.float(), out) < 2e-5
     out2 = torch.empty_like(out)  # without the fused split output small grids take the split-K path
     assert ops.conv3d_tc(hi, lo, Cin, dims, k, w_hi, w_lo, b.cuda(), _cl(res), Cout, out2) == 0
     torch.cuda.synchronize()
-    assert rel_err(_from_cl(out2, Cout, dims), ref) < 2e-5
+    assert rel_err(_from_cl(out2, Cout, dims), ref) < tol
 
 
 @pytest.mark.parametrize("C,R", [(64, 16), (128, 8)])
@@ -208,6 +209,37 @@ def test_conv_tc_stride2(C, R):
     assert ops.conv3d_tc(hi, lo, C, (R, R, R), 3, w_hi, w_lo, b.cuda(), None, C, out, stride=2) == 0
     torch.cuda.synchronize()
     assert rel_err(_from_cl(out, C, (R // 2,) * 3), ref) < 2e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,dims", [
+    (64, 64, (16, 32, 64)),    # 8 x 2 x 8 = 128 CTAs: halo-resident kernel, all faces padded
+    (128, 64, (8, 64, 64)),    # two slabs (4 half-slabs)
+    (64, 128, (64, 16, 16)),   # two N blocks
+])
+def test_conv_tc_halo(Cin, Cout, dims):
+    """The halo-resident tcgen05 kernel (conv_tc_halo.cu) takes these shapes; compare with fp32 F.conv3d."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    D, H, W = dims
+    x = torch.randn(1, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / math.sqrt(Cin * 27)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(1, Cout, D, H, W, generator=g)
+    ref = F.conv3d(x, w, b, padding=1) + res
+    V = D * H * W
+    hi = torch.empty(V, Cin, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(_cl(x), V, Cin, Cin, hi, lo)
+    wk = w.reshape(Cout, Cin, -1).permute(0, 2, 1).contiguous().cuda()
+    w_hi = wk.to(torch.bfloat16)
+    w_lo = (wk - w_hi.float()).to(torch.bfloat16)
+    out = torch.empty(V, Cout, device="cuda")
+    o_hi = torch.empty(V, Cout, device="cuda", dtype=torch.bfloat16)
+    o_lo = torch.empty_like(o_hi)
+    assert ops.conv3d_tc(hi, lo, Cin, dims, 3, w_hi, w_lo, b.cuda(), _cl(res), Cout, out, o_hi, o_lo) == 0
+    torch.cuda.synchronize()
+    assert rel_err(_from_cl(out, Cout, dims), ref) < 2e-5
+    assert rel_err(o_hi.float() + o_lo.float(), out) < 2e-5
 
 
 def test_split_pad_and_upsample():
