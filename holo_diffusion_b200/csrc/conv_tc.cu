@@ -36,12 +36,25 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 2);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // [hi*hi + lo*hi | hi*lo]
 };
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ bool elect_one() {
+    // one leader lane; unlike `lane == 0` the compiler keeps descriptors in uniform registers (no R2UR waterfall
+    // loop around every UTCHMMA / UTMALDG)
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -184,7 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = 2u * (uint32_t)rows * 128u + 2u * (uint32_t)C::B_TILE_BYTES;
@@ -206,25 +219,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_N);
+        // Two UMMAs per K step instead of three: the B tile holds [w_hi rows | w_lo rows] back to back, so
+        //   x_hi . [w_hi | w_lo]^T  (N = 2*BLOCK_N)  fills columns [0,BN) with hi*hi and [BN,2BN) with hi*lo,
+        //   x_lo . w_hi^T           (N = BLOCK_N)    adds lo*hi to columns [0,BN);
+        // the epilogue adds the two halves.  14 KB instead of 18 KB of shared-memory operand reads per K step
+        // (the kernel is bound by the SMEM read bandwidth of the SS-mode UMMA at N = 64).
+        constexpr uint32_t idesc1 = make_idesc_bf16(2 * BLOCK_N);
+        constexpr uint32_t idesc2 = make_idesc_bf16(BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
         for (int it = it_begin; it < it_end; ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
                 const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                const uint32_t b_lo = b_hi + C::B_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;  // b_lo follows at + B_TILE_BYTES
 #pragma unroll
                 for (int k = 0; k < SLAB / 16; ++k) {
                     const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
                     const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
-                    const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko), dbl = make_kmajor_sw128_desc(b_lo + ko);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (it > it_begin) || (k != 0));  // small terms first
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                    const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko);
+                    umma_bf16(tmem_base, dah, dbh, idesc1, (it > it_begin) || (k != 0));
+                    umma_bf16(tmem_base, dal, dbh, idesc2, 1);
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                 if (it == it_end - 1) umma_commit(tmem_full_bar);
@@ -244,13 +261,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-            uint32_t acc[16];
+            uint32_t acc[16], acc2[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), acc2);
             if (!row_ok) continue;
             const int n = n0 + c0;
             float vals[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]);
+            for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
             if (P.bias && lead) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {

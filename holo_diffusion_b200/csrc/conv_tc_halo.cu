@@ -33,6 +33,19 @@ constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_ENTRY + 1024 /*align*/ + 512 /*
 constexpr int NUM_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    // one leader lane; unlike `lane == 0` the compiler keeps descriptors in uniform registers (no R2UR waterfall
+    // loop around every UTCHMMA / UTMALDG)
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -147,7 +160,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -157,7 +170,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             int sb = 0;
             uint32_t pb = 0;
             for (int st = 0; st < n_stages; ++st) {
@@ -184,7 +197,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // x_hi . [w_hi | w_lo]^T (N = 128) then x_lo . w_hi^T (N = 64) into the first half: see conv_tc.cu
+        constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int sb = 0;
         uint32_t pb = 0;
         for (int st = 0; st < n_stages; ++st) {
@@ -197,21 +212,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 const int kd = t9 / 3, kh = t9 % 3;
                 mbar_wait(&b_full[sb], pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t b_hi = smem_u32(smem_b + sb * B_ENTRY), b_lo = b_hi + B_BYTES;
+                if (elect_one()) {
+                    const uint32_t b_hi = smem_u32(smem_b + sb * B_ENTRY);  // w_lo rows follow at + B_BYTES
 #pragma unroll
                     for (int dd = 0; dd < TD; ++dd) {
                         // operand view of tap (kh, kd) for depth slice dd: 16 groups of 8 rows, 512 B apart
                         const uint32_t off = 512u * (uint32_t)(kh + HH * (kd + dd));
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(dd * BLOCK_N);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(dd * 2 * BLOCK_N);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {  // 32 channels = 2 K-steps of 16
                             const uint32_t ko = k * 32;
                             const uint64_t dah = sw64_desc(a_hi + off + ko), dal = sw64_desc(a_lo + off + ko);
-                            const uint64_t dbh = sw64_desc(b_hi + ko), dbl = sw64_desc(b_lo + ko);
-                            umma_bf16(d_tmem, dal, dbh, idesc, (st | t9 | k) != 0);
-                            umma_bf16(d_tmem, dah, dbl, idesc, 1);
-                            umma_bf16(d_tmem, dah, dbh, idesc, 1);
+                            const uint64_t dbh = sw64_desc(b_hi + ko);
+                            umma_bf16(d_tmem, dah, dbh, idesc1, (st | t9 | k) != 0);
+                            umma_bf16(d_tmem, dal, dbh, idesc2, 1);
                         }
                     }
                     umma_commit(&b_empty[sb]);
@@ -234,12 +248,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             const size_t v = ((size_t)(d0 + dd) * P.H + h) * P.W + w;
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                uint32_t acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dd * BLOCK_N + c0), acc);
+                uint32_t acc[16], acc2[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dd * 2 * BLOCK_N + c0), acc);
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dd * 2 * BLOCK_N + BLOCK_N + c0), acc2);
                 const int n = n0 + c0;
                 float vals[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]);
+                for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
                 if (P.bias) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -283,7 +298,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
     }
 }
 

@@ -42,6 +42,19 @@ constexpr int OFF_BAR = IMG_BYTES;        // mbarriers + tmem slot
 constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    // one leader lane; unlike `lane == 0` the compiler keeps descriptors in uniform registers (no R2UR waterfall
+    // loop around every UTCHMMA / UTMALDG)
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
         for (int step = 0; step < total_steps; ++step) {
             mbar_wait(&a_full[g], step & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (elect_one()) {
                 umma(d, sw128_desc(on), sw128_desc(bb), idesc, 0);                       // bias (starts the tile)
                 umma(d, sw128_desc(a), sw128_desc(b2), idesc, 1);                        // x_hi . W_lo, K 0..15
                 umma(d, sw128_desc(a + 32), sw128_desc(b2 + 32), idesc, 1);              //              K 16..31

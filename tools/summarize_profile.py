@@ -1,0 +1,54 @@
+"""Turn gpurun_out/launches.csv (ncu --metrics gpu__time_duration.sum) and *.ncu-rep into small text summaries
+under profiles/ (run in the build container: ncu can read reports without a GPU)."""
+import collections, csv, re, subprocess, sys, os
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    data = rows[hi + 1:]
+    names = [r[4] for r in data]
+    t = [float(r[14]) for r in data]
+    def short(n):
+        m = re.search(r"(\w+_kernel)", n)
+        return "torch/other" if "at::" in n or not m else m.group(1)
+    sn = [short(n) for n in names]
+    rend = [i for i, n in enumerate(sn) if n.startswith("render_")]
+    a, b = rend[-2] + 1, rend[-1] + 1
+    agg, cnt = collections.OrderedDict(), collections.Counter()
+    for i in range(a, b):
+        agg[sn[i]] = agg.get(sn[i], 0) + t[i]; cnt[sn[i]] += 1
+    tot = sum(agg.values())
+    with open(out, "w") as f:
+        f.write(f"# one bench step (eager launches under ncu, cold-cache serialized): {b - a} launches, {tot/1e6:.3f} ms\n")
+        f.write("# compare SHARES, not absolutes (B200_PROFILING.md)\n")
+        for k, v in sorted(agg.items(), key=lambda x: -x[1]):
+            f.write(f"{k:30s} n={cnt[k]:4d} {v/1e6:8.3f} ms {100*v/tot:5.1f}%\n")
+        f.write("\n# conv_tc / halo launches in step order: grid, us\n")
+        f.write(" ".join(f"{data[i][8].replace(' ','')}:{t[i]/1e3:.1f}" for i in range(a, b) if "conv_tc" in names[i]) + "\n")
+
+KEYS = ["Kernel Name", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "launch__registers_per_thread",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum"]
+
+def rep(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        for r in rows[2:]:
+            for i, h in enumerate(hdr):
+                if any(h == k or h.endswith(k) for k in KEYS):
+                    f.write(f"{h} [{units[i]}] = {r[i]}\n")
+            st = [(float(r[i]), h) for i, h in enumerate(hdr) if "pcsamp_warps_issue_stalled" in h and not h.endswith("_not_issued") and r[i]]
+            tot = sum(v for v, _ in st) or 1
+            f.write("stall reasons: " + ", ".join(f"{h.split('stalled_')[1]} {100*v/tot:.1f}%" for v, h in sorted(st, reverse=True)[:6]) + "\n---\n")
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    if os.path.exists("gpurun_out/launches.csv"):
+        launches("gpurun_out/launches.csv", f"profiles/{tag}_launches.txt")
+    for p in sys.argv[2:]:
+        rep(p, f"profiles/{tag}_{os.path.basename(p).replace('.ncu-rep','')}.txt")
