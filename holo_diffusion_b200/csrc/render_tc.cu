@@ -181,21 +181,24 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ grid, int
     float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy, wz0 = (fz0 + 1.f) - iz;
 #pragma unroll
     for (int c = 0; c < 32; ++c) f[c] = 0.f;
+    // branch-free: out-of-range corners read a clamped (valid) address with weight 0, so all gathers of a
+    // point can be in flight together (zeros padding of grid_sample; 0 * finite = 0 exactly)
 #pragma unroll
     for (int corner = 0; corner < 8; ++corner) {
         int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
         int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
         float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
-        if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) {
-            const float4* p = reinterpret_cast<const float4*>(grid + (((size_t)zz * H + yy) * W + xx) * C);
+        bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
+        w = ok ? w : 0.f;
+        int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1), zc = min(max(zz, 0), D - 1);
+        const float4* p = reinterpret_cast<const float4*>(grid + (((size_t)zc * H + yc) * W + xc) * C);
 #pragma unroll
-            for (int c4 = 0; c4 < C / 4; ++c4) {
-                float4 v = __ldg(p + c4);
-                f[c4 * 4 + 0] += v.x * w;
-                f[c4 * 4 + 1] += v.y * w;
-                f[c4 * 4 + 2] += v.z * w;
-                f[c4 * 4 + 3] += v.w * w;
-            }
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            float4 v = __ldg(p + c4);
+            f[c4 * 4 + 0] = fmaf(v.x, w, f[c4 * 4 + 0]);
+            f[c4 * 4 + 1] = fmaf(v.y, w, f[c4 * 4 + 1]);
+            f[c4 * 4 + 2] = fmaf(v.z, w, f[c4 * 4 + 2]);
+            f[c4 * 4 + 3] = fmaf(v.w, w, f[c4 * 4 + 3]);
         }
     }
 }
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 mbar_wait(&mma_done[g], phase_a);
                 phase_a ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f;  // second set of accumulators: 6 independent FMA chains
                 {
                     uint32_t ta[32], tb[32];
                     auto consume = [&](const uint32_t (&t)[32], int j0) {
@@ -435,9 +439,9 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                             float t0 = fabsf(__uint_as_float(t[q * 4 + 0])), t1 = fabsf(__uint_as_float(t[q * 4 + 1]));
                             float t2 = fabsf(__uint_as_float(t[q * 4 + 2])), t3 = fabsf(__uint_as_float(t[q * 4 + 3]));
                             r0 = fmaf(e0.x, t0, r0), r1 = fmaf(e0.y, t0, r1), r2 = fmaf(e0.z, t0, r2);
-                            r0 = fmaf(e0.w, t1, r0), r1 = fmaf(e1.x, t1, r1), r2 = fmaf(e1.y, t1, r2);
+                            q0 = fmaf(e0.w, t1, q0), q1 = fmaf(e1.x, t1, q1), q2 = fmaf(e1.y, t1, q2);
                             r0 = fmaf(e1.z, t2, r0), r1 = fmaf(e1.w, t2, r1), r2 = fmaf(e2.x, t2, r2);
-                            r0 = fmaf(e2.y, t3, r0), r1 = fmaf(e2.z, t3, r1), r2 = fmaf(e2.w, t3, r2);
+                            q0 = fmaf(e2.y, t3, q0), q1 = fmaf(e2.z, t3, q1), q2 = fmaf(e2.w, t3, q2);
                         }
                     };
                     tmem_ld32_async(taddr, ta);
@@ -458,9 +462,9 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                     z_nxt = (s + 2 < S) ? next_z() : z_cur;
                     produce(z_cur);
                 }
-                float rgb0 = 1.f / (1.f + expf(-holo_leaky(r0)));
-                float rgb1 = 1.f / (1.f + expf(-holo_leaky(r1)));
-                float rgb2 = 1.f / (1.f + expf(-holo_leaky(r2)));
+                float rgb0 = 1.f / (1.f + expf(-holo_leaky(r0 + q0)));
+                float rgb1 = 1.f / (1.f + expf(-holo_leaky(r1 + q1)));
+                float rgb2 = 1.f / (1.f + expf(-holo_leaky(r2 + q2)));
                 float delta = (s + 1 < S) ? (z_n - z_s) : P.bg_opacity;
                 float wd = delta * fmaxf(sig, 0.f);
                 float capped = 1.f - expf(-wd);
