@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -139,6 +142,9 @@ struct TcParams {
     int tw, th, td;                  // voxel box of one M tile: 8x4x4 (128 rows) or 4x4x4 (64 rows, upper half idle)
     int stride;                      // 1 | 2 (input coordinate = out * stride + tap - pad)
     int iters_per_split;             // split-K: gridDim.z slices of the (tap, slab) loop; atomics into a zeroed out
+    int m_tiles, n_blocks, nsplit;   // work-item grid walked by the persistent CTAs
+    int stages;                      // pipeline depth actually used (<= Cfg::STAGES); short K loops take fewer stages
+                                     // and less shared memory so that several CTAs share an SM
     long long out_pitch;  // elements between consecutive output rows (= Cout for dense tensors)
     const float* bias;
     const float* residual;
@@ -151,43 +157,42 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcParams P) {
+    // PERSISTENT: each CTA walks work items (M tile, N block, K split) with a stride of gridDim.x.  The TMA producer
+    // runs ahead across item boundaries and the accumulator is double-buffered in TMEM, so the epilogue of item i
+    // (TMEM -> registers -> global) overlaps the main loop of item i+1 and the ~5 us of per-CTA prologue / epilogue
+    // that a one-tile-per-CTA launch pays 14x per SM is paid once.
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + C::STAGES;
-    uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const int n_stages = P.stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + n_stages * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + n_stages;
+    uint64_t* tmem_full_bar = empty_bar + n_stages;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    // tile coordinates
     const int tiles_w = P.W / P.tw, tiles_h = P.H / P.th;
-    int tile = blockIdx.x;
-    const int w0 = (tile % tiles_w) * P.tw;
-    const int h0 = ((tile / tiles_w) % tiles_h) * P.th;
-    const int d0 = (tile / (tiles_w * tiles_h)) * P.td;
     const int rows = P.tw * P.th * P.td;
-    const int n0 = blockIdx.y * BLOCK_N;
     const int taps = P.ksize * P.ksize * P.ksize;
     const int pad = P.ksize / 2;
     const int slabs = P.Cin / SLAB;
     const int k_total = taps * slabs;
-    const int it_begin = blockIdx.z * P.iters_per_split;
-    const int it_end = min(k_total, it_begin + P.iters_per_split);
-    const bool split = gridDim.z > 1;
+    const bool split = P.nsplit > 1;
+    const int n_items = P.m_tiles * P.n_blocks * P.nsplit;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
-        for (int s = 0; s < C::STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&tmem_full_bar[b], 1), mbar_init(&tmem_empty_bar[b], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(C::TMEM_COLS));
+                     "n"(2 * C::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -195,26 +200,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work item -> (M tile, N block, K slice); M tiles fastest so that concurrently running CTAs share weights in L2
+    auto decode = [&](int item, int& w0, int& h0, int& d0, int& n0, int& it_begin, int& it_end, int& z) {
+        const int mt = item % P.m_tiles;
+        const int rest = item / P.m_tiles;
+        const int nb = rest % P.n_blocks;
+        z = rest / P.n_blocks;
+        w0 = (mt % tiles_w) * P.tw;
+        h0 = ((mt / tiles_w) % tiles_h) * P.th;
+        d0 = (mt / (tiles_w * tiles_h)) * P.td;
+        n0 = nb * BLOCK_N;
+        it_begin = z * P.iters_per_split;
+        it_end = min(k_total, it_begin + P.iters_per_split);
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = 2u * (uint32_t)rows * 128u + 2u * (uint32_t)C::B_TILE_BYTES;
-            for (int it = it_begin; it < it_end; ++it) {
-                const int tap = it / slabs, slab = it % slabs;
-                const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* st = smem + stage * C::STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], tx_bytes);
-                const int c0 = slab * SLAB;
-                const int xw = w0 * P.stride + kw - pad, xh = h0 * P.stride + kh - pad, xd = d0 * P.stride + kd - pad;
-                tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, xw, xh, xd);
-                tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, xw, xh, xd);
-                const int kk = tap * P.Cin + c0;
-                tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kk, n0);
-                tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &map_b_lo, &full_bar[stage], kk, n0);
-                if (++stage == C::STAGES) stage = 0, phase ^= 1;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int w0, h0, d0, n0, it_begin, it_end, z;
+                decode(item, w0, h0, d0, n0, it_begin, it_end, z);
+                for (int it = it_begin; it < it_end; ++it) {
+                    const int tap = it / slabs, slab = it % slabs;
+                    const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    const int c0 = slab * SLAB;
+                    const int xw = w0 * P.stride + kw - pad, xh = h0 * P.stride + kh - pad, xd = d0 * P.stride + kd - pad;
+                    tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, xw, xh, xd);
+                    tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, xw, xh, xd);
+                    const int kk = tap * P.Cin + c0;
+                    tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kk, n0);
+                    tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &map_b_lo, &full_bar[stage], kk, n0);
+                    if (++stage == n_stages) stage = 0, phase ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
@@ -223,99 +246,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         //   x_hi . [w_hi | w_lo]^T  (N = 2*BLOCK_N)  fills columns [0,BN) with hi*hi and [BN,2BN) with hi*lo,
         //   x_lo . w_hi^T           (N = BLOCK_N)    adds lo*hi to columns [0,BN);
         // the epilogue adds the two halves.  14 KB instead of 18 KB of shared-memory operand reads per K step
-        // (the kernel is bound by the SMEM read bandwidth of the SS-mode UMMA at N = 64).
+        // (the kernel is bound by the SMEM operand bandwidth of the SS-mode UMMA at N = 64).
         constexpr uint32_t idesc1 = make_idesc_bf16(2 * BLOCK_N);
         constexpr uint32_t idesc2 = make_idesc_bf16(BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = it_begin; it < it_end; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+        int local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int w0, h0, d0, n0, it_begin, it_end, z;
+            decode(item, w0, h0, d0, n0, it_begin, it_end, z);
+            const int buf = local & 1;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::TMEM_COLS);
+            mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;  // b_lo follows at + B_TILE_BYTES
+            for (int it = it_begin; it < it_end; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;  // b_lo follows at + B_TILE_BYTES
 #pragma unroll
-                for (int k = 0; k < SLAB / 16; ++k) {
-                    const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                    const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
-                    const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko);
-                    umma_bf16(tmem_base, dah, dbh, idesc1, (it > it_begin) || (k != 0));
-                    umma_bf16(tmem_base, dal, dbh, idesc2, 1);
+                    for (int k = 0; k < SLAB / 16; ++k) {
+                        const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                        const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
+                        const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko);
+                        umma_bf16(d_tmem, dah, dbh, idesc1, (it > it_begin) || (k != 0));
+                        umma_bf16(d_tmem, dal, dbh, idesc2, 1);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (it == it_end - 1) umma_commit(&tmem_full_bar[buf]);
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                if (it == it_end - 1) umma_commit(tmem_full_bar);
+                __syncwarp();
+                if (++stage == n_stages) stage = 0, phase ^= 1;
             }
-            __syncwarp();
-            if (++stage == C::STAGES) stage = 0, phase ^= 1;
         }
     } else {
         // ================= epilogue =================
         const int q = warp % 4;  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
-        const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
-        const size_t v = ((size_t)d * P.H + h) * P.W + w;
         const bool row_ok = r < rows;
-        const bool lead = blockIdx.z == 0;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        int local = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+            int w0, h0, d0, n0, it_begin, it_end, z;
+            decode(item, w0, h0, d0, n0, it_begin, it_end, z);
+            const int buf = local & 1;
+            const uint32_t t_base = tmem_base + (uint32_t)(buf * C::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
+            const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
+            const size_t v = ((size_t)d * P.H + h) * P.W + w;
+            const bool lead = z == 0;
+            mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-            uint32_t acc[16], acc2[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BLOCK_N + c0), acc2);
-            if (!row_ok) continue;
-            const int n = n0 + c0;
-            float vals[16];
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                uint32_t acc[16], acc2[16];
+                tmem_ld16(t_base + (uint32_t)c0, acc);
+                tmem_ld16(t_base + (uint32_t)(BLOCK_N + c0), acc2);
+                if (!row_ok) continue;
+                const int n = n0 + c0;
+                float vals[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
-            if (P.bias && lead) {
+                for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+                if (P.bias && lead) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + j4);
-                    vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + j4);
+                        vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
+                    }
+                }
+                if (P.residual && lead) {
+                    const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 b = __ldg(rp + j4);
+                        vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
+                    }
+                }
+                if (P.out && split) {
+                    float* op = P.out + v * P.out_pitch + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
+                } else if (P.out) {
+                    float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
+                }
+                if (P.out_hi) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat16 h0b = __float2bfloat16_rn(vals[2 * j]), h1b = __float2bfloat16_rn(vals[2 * j + 1]);
+                        __nv_bfloat16 l0b = __float2bfloat16_rn(vals[2 * j] - __bfloat162float(h0b));
+                        __nv_bfloat16 l1b = __float2bfloat16_rn(vals[2 * j + 1] - __bfloat162float(h1b));
+                        hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                        lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                    }
+                    uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
+                    uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
+                    hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
             }
-            if (P.residual && lead) {
-                const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float4 b = __ldg(rp + j4);
-                    vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
-                }
-            }
-            if (P.out && split) {
-                float* op = P.out + v * P.out_pitch + n;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
-            } else if (P.out) {
-                float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4)
-                    op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
-            }
-            if (P.out_hi) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    __nv_bfloat16 h0b = __float2bfloat16_rn(vals[2 * j]), h1b = __float2bfloat16_rn(vals[2 * j + 1]);
-                    __nv_bfloat16 l0b = __float2bfloat16_rn(vals[2 * j] - __bfloat162float(h0b));
-                    __nv_bfloat16 l1b = __float2bfloat16_rn(vals[2 * j + 1] - __bfloat162float(h1b));
-                    hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-                    lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
-                }
-                uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
-                uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
-                hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * C::TMEM_COLS));
     }
 }
 
@@ -371,7 +413,27 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     auto k = conv_tc_kernel<BLOCK_N>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
               "holo_conv3d_tc");
-    k<<<dim3(tiles, P.Cout / BLOCK_N, nsplit), NUM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(ah, al, bh, bl, P);
+    TcParams Q = P;
+    Q.m_tiles = tiles, Q.n_blocks = P.Cout / BLOCK_N, Q.nsplit = nsplit;
+    Q.stages = Q.iters_per_split < Cfg<BLOCK_N>::STAGES ? Q.iters_per_split : Cfg<BLOCK_N>::STAGES;
+    const int smem = Q.stages * Cfg<BLOCK_N>::STAGE_BYTES + 1024 + 256;
+    // persistent grid: as many CTAs as fit on the chip (shared memory and the 512 TMEM columns bound the residency)
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    int occ_smem = (227 * 1024) / (smem + 1024);
+    int occ_tmem = 512 / (2 * Cfg<BLOCK_N>::TMEM_COLS);
+    int occ = occ_smem < occ_tmem ? occ_smem : occ_tmem;
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    const long long items = (long long)Q.m_tiles * Q.n_blocks * Q.nsplit;
+    long long grid = (long long)n_sm * occ;
+    if (grid > items) grid = items;
+    k<<<dim3((unsigned)grid), NUM_THREADS, smem, st>>>(ah, al, bh, bl, Q);
     HOLO_CHECK_LAUNCH("holo_conv3d_tc");
     return HOLO_OK;
 }
@@ -381,7 +443,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
 static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int Din, int Hin,
                         int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
-                        void* out_hi_bf16, void* out_lo_bf16, void* stream) {
+                        void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -416,7 +478,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     // gridDim.z and accumulate with fp32 atomics into a zeroed output (>= 4 iterations per slice)
     int nsplit = 1, per = k_total;
     const int base = tiles * (Cout / block_n);
-    if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && out_pitch == Cout) {
+    if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && (out_pitch == Cout || out_is_zeroed)) {
         int want = (296 + base - 1) / base;
         int maxs = k_total / 4;
         nsplit = want < maxs ? want : maxs;
@@ -439,13 +501,8 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     cudaStream_t st = (cudaStream_t)stream;
-    if (nsplit > 1) {
-        if (out_pitch != Cout) {
-            holo_set_error("%s: split-K needs a dense output", who);
-            return HOLO_ERR_UNSUPPORTED;
-        }
+    if (nsplit > 1 && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
-    }
     switch (block_n) {
         case 128: return launch<128>(ah, al, bh, bl, P, tiles, nsplit, st);
         case 64: return launch<64>(ah, al, bh, bl, P, tiles, nsplit, st);
@@ -479,11 +536,12 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
 // bf16 hi/lo pairs, arbitrary row pitches).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
 extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
                             const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
-                            long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
+                            long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, int out_is_zeroed,
+                            void* stream) {
     if (M % BLOCK_M) {
         holo_set_error("holo_gemm_tc: M=%d must be a multiple of 128", M);
         return HOLO_ERR_UNSUPPORTED;
     }
     return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
-                        residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream);
+                        residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream, out_is_zeroed);
 }

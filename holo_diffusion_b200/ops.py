@@ -159,13 +159,14 @@ def _ptr_off(t, off_elems: int, dtype):
 
 
 def gemm_tc(a_hi, a_lo, a_off, a_pitch, M, K, b_hi, b_lo, b_off, b_pitch, N, bias, residual, out_pitch, out, out_off=0,
-            out_hi=None, out_lo=None) -> int:
+            out_hi=None, out_lo=None, out_is_zeroed: bool = False) -> int:
     """out[m][n] (+out_off, row pitch out_pitch) = bias + residual + sum_k a[m][k] b[n][k] on tcgen05 (bf16x3)."""
     bf = torch.bfloat16
     rc = lib().try_call("holo_gemm_tc", _ptr_off(a_hi, a_off, bf), _ptr_off(a_lo, a_off, bf), a_pitch, M, K,
                         _ptr_off(b_hi, b_off, bf), _ptr_off(b_lo, b_off, bf), b_pitch, N, _ptr(bias),
                         _ptr_off(residual, out_off, torch.float32), out_pitch, _ptr_off(out, out_off, torch.float32),
-                        _ptr_off(out_hi, out_off, bf), _ptr_off(out_lo, out_off, bf), _stream())
+                        _ptr_off(out_hi, out_off, bf), _ptr_off(out_lo, out_off, bf), 1 if out_is_zeroed else 0,
+                        _stream())
     if rc not in (0, -3):
         raise HoloError(f"holo_gemm_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc

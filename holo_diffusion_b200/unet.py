@@ -327,17 +327,19 @@ class UNetExecutor:
         P_lo = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
         vt_hi = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
         vt_lo = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
-        a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
-        a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        a = torch.zeros(T, C, device=dev)   # PV GEMMs split K (the keys) across CTAs and accumulate here
         for h in range(heads):
             base = h * 3 * ch
             rc = ops.gemm_tc(q_hi, q_lo, base, 3 * C, T, ch, q_hi, q_lo, base + ch, 3 * C, T, None, None, T, S)
             assert rc == 0
             ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)   # (q s)(k s) = s^2 q k, s = ch^-1/4
             ops.transpose_split(qkv.x1, base + 2 * ch, 3 * C, T, ch, vt_hi, vt_lo)
-            rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, None, h * ch, a_hi, a_lo)
+            rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, a, h * ch, out_is_zeroed=True)
             assert rc == 0
             self.tc_calls += 2
+        a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        ops.split_bf16(a, T, C, C, a_hi, a_lo)
         out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
         return _Act(out.x1, C, act.dims)
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 104
+#define HOLO_B200_VERSION 105
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -127,11 +127,13 @@ int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, in
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
  * hi/lo pairs, K-major with arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
+ * out_is_zeroed = 1 promises a zero-filled fp32 `out`, which lets small grids split K and accumulate with atomics.
  * With holo_softmax_split / holo_transpose_split_bf16 it carries QKVAttentionLegacy (unet.py:438-455) on tensor
  * cores: S = Q K^T, P = softmax(scale2 * S) (fp32, one key row per CTA, emitted as bf16 hi/lo), O = P V. */
 int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
                  const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
-                 long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream);
+                 long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, int out_is_zeroed,
+                 void* stream);
 int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_hi_bf16, void* P_lo_bf16,
                        void* stream);
 int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, int cols, void* hi_bf16,
