@@ -519,8 +519,10 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
     const int taps = ksize * ksize * ksize;
-    // large 3^3 stride-1 layers: halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic
-    static const bool no_halo = getenv("HOLO_CONV_NO_HALO") != nullptr;
+    // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
+    // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
+    // (both are bound by the SS-mode UMMA operand fetch at N = 64, not by L2), so it is off by default.
+    static const bool no_halo = getenv("HOLO_CONV_HALO") == nullptr;
     if (!no_halo && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
         (out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr) && W % 8 == 0 && H % 16 == 0 && D % 2 == 0 &&
         Cout % 64 == 0 && Cin % 64 == 0 && (long long)(W / 8) * (H / 16) * (D / 2) * (Cout / 64) >= 120) {

@@ -20,8 +20,9 @@ namespace {
 
 constexpr int HID = 256;
 constexpr int GROUP = 128;            // rays per group (= UMMA M)
-constexpr int RAY_THREADS = 2 * GROUP;
-constexpr int THREADS = RAY_THREADS + 64;  // + one MMA warp per group
+constexpr int RAY_THREADS = 2 * GROUP;      // rays per CTA
+// warp roles: [0, 256) samplers (thread = ray), [256, 512) epilogue/compositing (thread = ray), [512, 576) MMA issuers
+constexpr int THREADS = 2 * RAY_THREADS + 64;
 
 // shared-memory image (byte offsets; every UMMA tile 1024-aligned)
 constexpr int OFF_A0 = 0;                 // [128][128B]  group 0 operand rows
@@ -38,8 +39,13 @@ constexpr int F32_EP = 132;               // [256][3] 0.4 * wr[i][j] stored j-ma
 constexpr int F32_DIR = 132 + 768;        // [3][E] + br[3]   (E <= 27)
 constexpr int F32_COUNT = F32_DIR + 3 * 27 + 3;
 constexpr int IMG_BYTES = OFF_F32 + ((F32_COUNT * 4 + 15) / 16) * 16;
-constexpr int OFF_BAR = IMG_BYTES;        // mbarriers + tmem slot
-constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+constexpr int OFF_A2 = ((IMG_BYTES + 1023) / 1024) * 1024;  // second operand buffer of group 0 / 1 (double buffering)
+constexpr int OFF_A3 = OFF_A2 + 16 * 1024;
+constexpr int OFF_PR = OFF_A3 + 16 * 1024;   // [group][buf][6][128] floats: sigma, lin0..2, z, z_next handed S -> E
+constexpr int PR_FLOATS = 6 * GROUP;
+constexpr int OFF_WTOT = OFF_PR + 2 * 2 * PR_FLOATS * 4;  // [group][128] cdf normaliser handed E -> S between passes
+constexpr int OFF_BAR = OFF_WTOT + 2 * GROUP * 4;         // mbarriers + tmem slot
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool elect_one() {
@@ -223,26 +229,42 @@ __device__ __forceinline__ void prefetch_point(const float* __restrict__ grid, i
 
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P) {
+    // Warp-specialised pipeline per group of 128 rays (two groups per CTA):
+    //   sampler warps  : depth stream (coarse / merged fine) -> trilinear gather -> sigma, linear radiance part ->
+    //                    operand row [x_hi | x_lo] into A[buf], scalars into PR[buf]          (step s + 1)
+    //   MMA warp       : 7 UMMAs into the group's TMEM accumulator                            (step s)
+    //   epilogue warps : TMEM row -> radiance -> emission-absorption compositing, outputs     (step s - 1)
+    // so the three stages of consecutive depth steps overlap and 16 ray warps (instead of 8) hide each other's
+    // gather / TMEM / barrier latencies.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);      // [2]
-    uint64_t* mma_done = a_full + 2;                                     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    // per group g: a_full[2], pr_free[2], tm_full, tm_free, pass_done
+    auto a_full = [&](int g, int b) { return bars + g * 8 + b; };
+    auto pr_free = [&](int g, int b) { return bars + g * 8 + 2 + b; };
+    auto tm_full = [&](int g) { return bars + g * 8 + 4; };
+    auto tm_free = [&](int g) { return bars + g * 8 + 5; };
+    auto pass_done = [&](int g) { return bars + g * 8 + 6; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const float* sF = reinterpret_cast<const float*>(smem + OFF_F32);
+    float* sPR = reinterpret_cast<float*>(smem + OFF_PR);
+    float* sWtot = reinterpret_cast<float*>(smem + OFF_WTOT);
 
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-    // stage the weight image
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.image) + (OFF_B1 / 16);
         uint4* dst = reinterpret_cast<uint4*>(smem + OFF_B1);
         for (int i = tid; i < (IMG_BYTES - OFF_B1) / 16; i += THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        mbar_init(&a_full[0], GROUP), mbar_init(&a_full[1], GROUP);
-        mbar_init(&mma_done[0], 1), mbar_init(&mma_done[1], 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(a_full(g, 0), GROUP), mbar_init(a_full(g, 1), GROUP);
+            mbar_init(pr_free(g, 0), GROUP), mbar_init(pr_free(g, 1), GROUP);
+            mbar_init(tm_full(g), 1), mbar_init(tm_free(g), GROUP), mbar_init(pass_done(g), GROUP);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == RAY_THREADS / 32) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -255,121 +277,62 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
     const int S1 = P.S;
     const int S2 = P.add_input ? P.S + P.n_fine : P.n_fine;
     const int total_steps = S1 + (P.n_passes > 1 ? S2 : 0);
+    const float eps = 1e-5f;
 
-    if (warp >= RAY_THREADS / 32) {
+    if (warp >= 16) {
         // ============================ MMA issuer of group g ============================
-        const int g = warp - RAY_THREADS / 32;
+        const int g = warp - 16;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(GROUP >> 4) << 24);
-        const uint32_t a = smem_u32(smem + (g ? OFF_A1 : OFF_A0));
+        const uint32_t a0 = smem_u32(smem + (g ? OFF_A1 : OFF_A0)), a1 = smem_u32(smem + (g ? OFF_A3 : OFF_A2));
         const uint32_t b1 = smem_u32(smem + OFF_B1), b2 = smem_u32(smem + OFF_B2);
         const uint32_t on = smem_u32(smem + OFF_ONES), bb = smem_u32(smem + OFF_BB);
         const uint32_t d = tmem_base + (uint32_t)(g * HID);
-        for (int step = 0; step < total_steps; ++step) {
-            mbar_wait(&a_full[g], step & 1);
+        for (int gs = 0; gs < total_steps; ++gs) {
+            const int buf = gs & 1;
+            mbar_wait(a_full(g, buf), (gs >> 1) & 1);
+            if (gs >= 1) mbar_wait(tm_free(g), (gs - 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
+                const uint32_t a = buf ? a1 : a0;
                 umma(d, sw128_desc(on), sw128_desc(bb), idesc, 0);                       // bias (starts the tile)
                 umma(d, sw128_desc(a), sw128_desc(b2), idesc, 1);                        // x_hi . W_lo, K 0..15
                 umma(d, sw128_desc(a + 32), sw128_desc(b2 + 32), idesc, 1);              //              K 16..31
 #pragma unroll
                 for (int k = 0; k < 4; ++k)                                              // [x_hi|x_lo] . [W_hi|W_hi]
                     umma(d, sw128_desc(a + 32 * k), sw128_desc(b1 + 32 * k), idesc, 1);
-                umma_commit(&mma_done[g]);
+                umma_commit(tm_full(g));
             }
             __syncwarp();
         }
-    } else {
-        // ============================ ray threads ============================
+    } else if (warp < 8) {
+        // ============================ samplers ============================
         const int g = warp / 4;
-        const int row = tid - g * GROUP;                 // row of the group's M tile = TMEM lane
+        const int row = tid - g * GROUP;
         const long long ray_raw = (long long)blockIdx.x * RAY_THREADS + tid;
-        const bool valid = ray_raw < P.n_rays;
-        const size_t ray = valid ? (size_t)ray_raw : (size_t)(P.n_rays - 1);  // idle lanes shadow the last ray
-        uint8_t* a_row = smem + (g ? OFF_A1 : OFF_A0) + (row / 8) * 1024 + (row % 8) * 128;
+        const size_t ray = ray_raw < P.n_rays ? (size_t)ray_raw : (size_t)(P.n_rays - 1);  // idle lanes shadow the last ray
         const int sw = row % 8;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp % 4) * 32) << 16) + (uint32_t)(g * HID);
+        const size_t row_off = (size_t)(row / 8) * 1024 + (row % 8) * 128;
+        uint8_t* a_row0 = smem + (g ? OFF_A1 : OFF_A0) + row_off;
+        uint8_t* a_row1 = smem + (g ? OFF_A3 : OFF_A2) + row_off;
         const float* wsig = sF + F32_WSIG;
         const float* lin = sF + F32_LIN;
         const float b_sigma = sF[F32_MISC];
-
-        float o[3], d[3], dn[3];
+        float o[3], d[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) o[i] = P.origins[ray * 3 + i], d[i] = P.dirs[ray * 3 + i];
-        {
-            float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) dn[i] = d[i] / nrm;
-        }
-        // per-ray constant of the radiance pre-activation: br + Wr[:, H:] . PE(dn) + 0.6 * wr . b_eff
-        float rd[3];
-        {
-            const int nh = P.n_harm, E = 3 * (2 * nh + 1);
-            const float* sDir = sF + F32_DIR;
-            const float* br = sDir + 3 * E;
-            rd[0] = br[0] + sF[F32_MISC + 1], rd[1] = br[1] + sF[F32_MISC + 2], rd[2] = br[2] + sF[F32_MISC + 3];
-            for (int c = 0; c < 3; ++c) {
-                float freq = 1.f;
-                for (int k = 0; k < nh; ++k) {
-                    float e = dn[c] * freq;
-                    float sn = sinf(e), cs = cosf(e);
-                    int ms = c * nh + k, mc = 3 * nh + c * nh + k;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + ms] * sn + sDir[i * E + mc] * cs;
-                    freq *= 2.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + 6 * nh + c] * dn[c];
-            }
-        }
         const float* zin = P.lengths + ray * S1;
-        uint32_t phase_a = 0;  // completed MMA count parity for this group
-        const float eps = 1e-5f;
-        float w_tot = 0.f;     // sum_{i=1}^{S1-2} (w_i + eps), accumulated during the coarse pass
-
-        // sample the point at depth z: density (fp32), linear radiance part, operand row; then hand it to the MMA warp
-        float sig_n, lin_n[3];
-        auto produce = [&](float z) {
-            float x[32];
-            sample_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z * d[0]) * P.inv_x, (o[1] + z * d[1]) * P.inv_y,
-                            (o[2] + z * d[2]) * P.inv_z, x);
-            float s0 = b_sigma, s1 = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; c += 2) {
-                s0 = fmaf(wsig[c], x[c], s0), s1 = fmaf(wsig[c + 1], x[c + 1], s1);
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                l0 = fmaf(lin[c], x[c], l0), l1 = fmaf(lin[32 + c], x[c], l1), l2 = fmaf(lin[64 + c], x[c], l2);
-            }
-            sig_n = holo_leaky(s0 + s1);
-            lin_n[0] = l0, lin_n[1] = l1, lin_n[2] = l2;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float a0 = x[2 * c], a1 = x[2 * c + 1];
-                float h0 = __bfloat162float(__float2bfloat16_rn(a0)), h1 = __bfloat162float(__float2bfloat16_rn(a1));
-                hi[c] = pack_bf16x2(a0, a1);
-                lo[c] = pack_bf16x2(a0 - h0, a1 - h1);
-            }
-            // row = [x_hi (4 chunks) | x_lo (4 chunks)], 16-byte chunk c lands at chunk (c ^ (row % 8))  (SWIZZLE_128B)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                *reinterpret_cast<uint4*>(a_row + ((c ^ sw) * 16)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                *reinterpret_cast<uint4*>(a_row + (((c + 4) ^ sw) * 16)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&a_full[g]);
-        };
-
+        int gs = 0;
         for (int pass = 0; pass < P.n_passes; ++pass) {
             const int S = pass == 0 ? S1 : S2;
-            const bool last = pass == P.n_passes - 1;
             // ---- depth stream: coarse depths, or the on-the-fly merge of coarse depths and inverse-cdf samples
             int ic = 0, jf = 0, inds = 0;
-            float c_prev = 0.f, c_cur = 0.f, f_next = INFINITY;
+            float c_prev = 0.f, c_cur = 0.f, f_next = INFINITY, w_tot = 1.f;
             const int ncdf = S1 - 1;
             const float* wsc = P.scratch_w + ray;  // column of coarse weights, stride n_rays
+            if (pass == 1) {
+                mbar_wait(pass_done(g), 0);        // the epilogue threads finished the coarse pass (weights, w_tot)
+                w_tot = sWtot[g * GROUP + row];
+            }
             auto gen_fine = [&]() {               // next inverse-cdf sample (sample_pdf, deterministic u)
                 if (jf >= P.n_fine) {
                     f_next = INFINITY;
@@ -412,21 +375,108 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 return z;
             };
             if (pass == 1) gen_fine();
-
+            float z_cur = next_z();
+            float z_nxt = (S > 1) ? next_z() : z_cur;
+            for (int s = 0; s < S; ++s, ++gs) {
+                const int buf = gs & 1;
+                if (s + 1 < S)  // warm L1 with the next point's corners
+                    prefetch_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_nxt * d[0]) * P.inv_x,
+                                      (o[1] + z_nxt * d[1]) * P.inv_y, (o[2] + z_nxt * d[2]) * P.inv_z);
+                float x[32];
+                sample_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_cur * d[0]) * P.inv_x, (o[1] + z_cur * d[1]) * P.inv_y,
+                                (o[2] + z_cur * d[2]) * P.inv_z, x);
+                float s0 = b_sigma, s1 = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < C / 4; ++c4) {
+                    const float4 ws = *reinterpret_cast<const float4*>(wsig + 4 * c4);
+                    const float4 la = *reinterpret_cast<const float4*>(lin + 4 * c4);
+                    const float4 lb = *reinterpret_cast<const float4*>(lin + 32 + 4 * c4);
+                    const float4 lc = *reinterpret_cast<const float4*>(lin + 64 + 4 * c4);
+                    const float x0 = x[4 * c4], x1 = x[4 * c4 + 1], x2 = x[4 * c4 + 2], x3 = x[4 * c4 + 3];
+                    s0 = fmaf(ws.x, x0, s0), s1 = fmaf(ws.y, x1, s1), s0 = fmaf(ws.z, x2, s0), s1 = fmaf(ws.w, x3, s1);
+                    l0 = fmaf(la.x, x0, l0), l0 = fmaf(la.y, x1, l0), l0 = fmaf(la.z, x2, l0), l0 = fmaf(la.w, x3, l0);
+                    l1 = fmaf(lb.x, x0, l1), l1 = fmaf(lb.y, x1, l1), l1 = fmaf(lb.z, x2, l1), l1 = fmaf(lb.w, x3, l1);
+                    l2 = fmaf(lc.x, x0, l2), l2 = fmaf(lc.y, x1, l2), l2 = fmaf(lc.z, x2, l2), l2 = fmaf(lc.w, x3, l2);
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float a0 = x[2 * c], a1 = x[2 * c + 1];
+                    float h0 = __bfloat162float(__float2bfloat16_rn(a0)), h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                    hi[c] = pack_bf16x2(a0, a1);
+                    lo[c] = pack_bf16x2(a0 - h0, a1 - h1);
+                }
+                // both buffers of this step's parity must have been drained by the epilogue (step gs - 2)
+                if (gs >= 2) mbar_wait(pr_free(g, buf), ((gs >> 1) - 1) & 1);
+                uint8_t* a_row = buf ? a_row1 : a_row0;
+                // row = [x_hi (4 chunks) | x_lo (4 chunks)], 16-byte chunk c lands at chunk (c ^ (row % 8))  (SWIZZLE_128B)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<uint4*>(a_row + ((c ^ sw) * 16)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(a_row + (((c + 4) ^ sw) * 16)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+                float* pr = sPR + (size_t)(g * 2 + buf) * PR_FLOATS + row;
+                pr[0 * GROUP] = holo_leaky(s0 + s1);
+                pr[1 * GROUP] = l0, pr[2 * GROUP] = l1, pr[3 * GROUP] = l2;
+                pr[4 * GROUP] = z_cur, pr[5 * GROUP] = z_nxt;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(a_full(g, buf));
+                z_cur = z_nxt;
+                z_nxt = (s + 2 < S) ? next_z() : z_cur;
+            }
+        }
+    } else {
+        // ============================ epilogue + compositing ============================
+        const int et = tid - RAY_THREADS;
+        const int g = et / GROUP;
+        const int row = et - g * GROUP;
+        const long long ray_raw = (long long)blockIdx.x * RAY_THREADS + et;
+        const bool valid = ray_raw < P.n_rays;
+        const size_t ray = valid ? (size_t)ray_raw : (size_t)(P.n_rays - 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp % 4) * 32) << 16) + (uint32_t)(g * HID);
+        float dn[3];
+        {
+            float d0 = P.dirs[ray * 3], d1 = P.dirs[ray * 3 + 1], d2 = P.dirs[ray * 3 + 2];
+            float nrm = fmaxf(sqrtf(d0 * d0 + d1 * d1 + d2 * d2), 1e-12f);
+            dn[0] = d0 / nrm, dn[1] = d1 / nrm, dn[2] = d2 / nrm;
+        }
+        // per-ray constant of the radiance pre-activation: br + Wr[:, H:] . PE(dn) + 0.6 * wr . b_eff
+        float rd[3];
+        {
+            const int nh = P.n_harm, E = 3 * (2 * nh + 1);
+            const float* sDir = sF + F32_DIR;
+            const float* br = sDir + 3 * E;
+            rd[0] = br[0] + sF[F32_MISC + 1], rd[1] = br[1] + sF[F32_MISC + 2], rd[2] = br[2] + sF[F32_MISC + 3];
+            for (int c = 0; c < 3; ++c) {
+                float freq = 1.f;
+                for (int k = 0; k < nh; ++k) {
+                    float e = dn[c] * freq;
+                    float sn = sinf(e), cs = cosf(e);
+                    int ms = c * nh + k, mc = 3 * nh + c * nh + k;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + ms] * sn + sDir[i * E + mc] * cs;
+                    freq *= 2.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + 6 * nh + c] * dn[c];
+            }
+        }
+        int gs = 0;
+        float w_tot = 0.f;  // sum_{i=1}^{S1-2} (w_i + eps), accumulated during the coarse pass
+        for (int pass = 0; pass < P.n_passes; ++pass) {
+            const int S = pass == 0 ? S1 : S2;
+            const bool last = pass == P.n_passes - 1;
             float cum = 0.f, opac_prev = 0.f, af[3] = {0.f, 0.f, 0.f}, ad = 0.f;
             float* wout = last ? P.weights : P.p_weights;
             float* lout = (pass == 1) ? P.lengths_out : nullptr;
-            float z_cur = next_z();
-            float z_nxt = (S > 1) ? next_z() : z_cur;
-            produce(z_cur);
-            for (int s = 0; s < S; ++s) {
-                const float sig = sig_n;
-                float r0 = rd[0] + lin_n[0], r1 = rd[1] + lin_n[1], r2 = rd[2] + lin_n[2];
-                if (s + 1 < S)  // warm L1 with the next point's corners while this step's MMA / epilogue run
-                    prefetch_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_nxt * d[0]) * P.inv_x,
-                                      (o[1] + z_nxt * d[1]) * P.inv_y, (o[2] + z_nxt * d[2]) * P.inv_z);
-                mbar_wait(&mma_done[g], phase_a);
-                phase_a ^= 1;
+            for (int s = 0; s < S; ++s, ++gs) {
+                const int buf = gs & 1;
+                mbar_wait(a_full(g, buf), (gs >> 1) & 1);   // direct S -> E ordering for the PR scalars
+                const float* pr = sPR + (size_t)(g * 2 + buf) * PR_FLOATS + row;
+                const float sig = pr[0];
+                float r0 = rd[0] + pr[1 * GROUP], r1 = rd[1] + pr[2 * GROUP], r2 = rd[2] + pr[3 * GROUP];
+                const float z_s = pr[4 * GROUP], z_n = pr[5 * GROUP];
+                mbar_wait(tm_full(g), gs & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float q0 = 0.f, q1 = 0.f, q2 = 0.f;  // second set of accumulators: 6 independent FMA chains
                 {
@@ -455,13 +505,10 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                         consume(tb, j0 + 32);
                     }
                 }
-                // the accumulator and the operand row are free again: start the next depth step's MMA now
-                const float z_s = z_cur, z_n = z_nxt;
-                if (s + 1 < S) {
-                    z_cur = z_nxt;
-                    z_nxt = (s + 2 < S) ? next_z() : z_cur;
-                    produce(z_cur);
-                }
+                // accumulator and scalar slot are free: release them before the (long) compositing math
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(tm_free(g));
+                mbar_arrive(pr_free(g, buf));
                 float rgb0 = 1.f / (1.f + expf(-holo_leaky(r0 + q0)));
                 float rgb1 = 1.f / (1.f + expf(-holo_leaky(r1 + q1)));
                 float rgb2 = 1.f / (1.f + expf(-holo_leaky(r2 + q2)));
@@ -478,9 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 if (valid) {
                     if (wout) wout[ray * S + s] = w;
                     if (lout) lout[ray * S + s] = z_s;
-                    if (!last) {
-                        P.scratch_w[(size_t)s * P.n_rays + ray] = w;
-                    }
+                    if (!last) P.scratch_w[(size_t)s * P.n_rays + ray] = w;
                 }
                 if (!last && s >= 1 && s <= S1 - 2) w_tot += w + eps;
             }
@@ -497,12 +542,16 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 if (Dp) Dp[ray] = ad;
                 if (M) M[ray] = mask;
             }
-            __syncwarp();
+            if (!last) {
+                sWtot[g * GROUP + row] = w_tot;
+                __threadfence_block();
+                mbar_arrive(pass_done(g));   // release: the coarse weights (global scratch) and w_tot are visible
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (warp == RAY_THREADS / 32) {
+    if (warp == 16) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
