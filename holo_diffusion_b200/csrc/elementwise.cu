@@ -47,8 +47,12 @@ extern "C" int holo_transpose2d(const float* src, float* dst, int rows, int cols
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
                                                         int C2, long long V, int vox_per_block,
-                                                        double* __restrict__ acc) {
+                                                        double* __restrict__ acc, double* __restrict__ acc_zero) {
     extern __shared__ float sh[];  // [vstep][2C] per-thread partials, then [2C] totals
+    // ping-pong accumulators: while this GroupNorm accumulates into `acc`, block 0 clears the buffer the NEXT one
+    // will use (its previous reader, the preceding fused apply, has completed in stream order)
+    if (acc_zero && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) acc_zero[i] = 0.0;
     const int C = C1 + C2;
     const int cq = C / 4;  // float4 lanes per voxel
     long long v0 = (long long)blockIdx.x * vox_per_block;
@@ -91,8 +95,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     }
 }
 
-extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64,
-                             void* stream) {
+static int gn_stats_launch(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64,
+                           double* acc_zero, void* stream) {
     int C = C1 + C2;
     HOLO_CHECK_ARG(x1 && acc64 && V > 0, "holo_gn_stats: bad args");
     HOLO_CHECK_ARG(C % 32 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 1024, "holo_gn_stats: C=%d+%d unsupported", C1, C2);
@@ -105,9 +109,19 @@ extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, l
     int blocks = holo_cdiv(V, vpb);
     const int vstep = threads / (C / 4);
     size_t smem = (size_t)(vstep > 1 ? vstep : 1) * 2 * C * sizeof(float);
-    gn_stats_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb, acc64);
+    gn_stats_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb, acc64, acc_zero);
     HOLO_CHECK_LAUNCH("holo_gn_stats");
     return HOLO_OK;
+}
+
+extern "C" int holo_gn_stats(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64,
+                             void* stream) {
+    return gn_stats_launch(x1, C1, x2, C2, V, acc64, nullptr, stream);
+}
+extern "C" int holo_gn_stats_pp(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64,
+                                double* acc64_next, void* stream) {
+    HOLO_CHECK_ARG(acc64_next && acc64_next != acc64, "holo_gn_stats_pp: need a distinct buffer to clear");
+    return gn_stats_launch(x1, C1, x2, C2, V, acc64, acc64_next, stream);
 }
 
 // per-channel affine from the statistics:  y = x * a[c] + b[c]
@@ -193,6 +207,93 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
                 make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
         }
     }
+}
+
+// GroupNorm apply with the finalize step folded in: every CTA derives the per-channel affine (gamma, beta, FiLM,
+// statistics) into shared memory, then streams its share of the tensor.  Saves one launch per GroupNorm.
+template <bool SILU>
+__global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                      long long V, const double* __restrict__ acc, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ film, float eps,
+                                      float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
+    extern __shared__ float s_ab[];  // a[C], b[C]
+    __shared__ double s_acc[64];
+    const int C = C1 + C2;
+    if (threadIdx.x < 64) {
+        double t = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += acc[r * 64 + threadIdx.x];
+        s_acc[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int cpg = C / 32;
+    const double count = (double)V * (double)cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        int g = c / cpg;
+        double mean = s_acc[g * 2] / count;
+        double var = s_acc[g * 2 + 1] / count - mean * mean;
+        if (var < 0) var = 0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float aa = rstd * gamma[c];
+        float bb = beta[c] - (float)mean * aa;
+        if (film) {
+            float sc = 1.f + film[c], sh = film[C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        s_ab[c] = aa, s_ab[C + c] = bb;
+    }
+    __syncthreads();
+    const long long total4 = V * (C / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long v = i / (C / 4);
+        int c = (int)(i % (C / 4)) * 4;
+        float4 xv = (c < C1) ? *reinterpret_cast<const float4*>(x1 + v * C1 + c)
+                             : *reinterpret_cast<const float4*>(x2 + v * C2 + (c - C1));
+        float4 av = *reinterpret_cast<const float4*>(s_ab + c);
+        float4 bv = *reinterpret_cast<const float4*>(s_ab + C + c);
+        float4 r;
+        r.x = xv.x * av.x + bv.x, r.y = xv.y * av.y + bv.y, r.z = xv.z * av.z + bv.z, r.w = xv.w * av.w + bv.w;
+        if (SILU) r.x = holo_silu(r.x), r.y = holo_silu(r.y), r.z = holo_silu(r.z), r.w = holo_silu(r.w);
+        if (y) *reinterpret_cast<float4*>(y + v * C + c) = r;
+        if (y_hi) {
+            float rr[4] = {r.x, r.y, r.z, r.w};
+            uint16_t hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat16 h = __float2bfloat16_rn(rr[k]);
+                __nv_bfloat16 l = __float2bfloat16_rn(rr[k] - __bfloat162float(h));
+                hi[k] = *reinterpret_cast<uint16_t*>(&h);
+                lo[k] = *reinterpret_cast<uint16_t*>(&l);
+            }
+            *reinterpret_cast<uint2*>(y_hi + v * C + c) =
+                make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+            *reinterpret_cast<uint2*>(y_lo + v * C + c) =
+                make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+        }
+    }
+}
+
+extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
+                                   const float* gamma, const float* beta, const float* film_scale_shift, float eps,
+                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream) {
+    int C = C1 + C2;
+    HOLO_CHECK_ARG(x1 && acc64 && gamma && beta && (y || y_hi_bf16) && V > 0, "holo_gn_apply_fused: bad args");
+    HOLO_CHECK_ARG(C % 32 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 4096, "holo_gn_apply_fused: C=%d+%d unsupported", C1, C2);
+    HOLO_CHECK_ARG((y_hi_bf16 == nullptr) == (y_lo_bf16 == nullptr), "holo_gn_apply_fused: hi/lo must come together");
+    long long total4 = V * (C / 4);
+    int blocks = holo_cdiv(total4, 256 * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    size_t smem = 2 * (size_t)C * sizeof(float);
+    if (silu)
+        gn_apply_fused_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(
+            x1, C1, x2, C2, V, acc64, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16);
+    else
+        gn_apply_fused_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(
+            x1, C1, x2, C2, V, acc64, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16);
+    HOLO_CHECK_LAUNCH("holo_gn_apply_fused");
+    return HOLO_OK;
 }
 
 extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a,
@@ -412,33 +513,36 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 __global__ void act_range_kernel(const float* __restrict__ x, long long V, int C, int act,
                                  float* __restrict__ y_cl, float* __restrict__ y_cf, int* __restrict__ stats) {
     __shared__ float tile[32][33];
+    __shared__ float s_mn[8], s_mx[8];
+    __shared__ int s_nan[8];
     float mn = INFINITY, mx = -INFINITY;
     int nan = 0;
-    // tile: 32 voxels x 32 channels; blockDim (32, 8)
-    long long v0 = (long long)blockIdx.x * 32;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        for (int i = threadIdx.y; i < 32; i += 8) {
-            long long v = v0 + i;
-            int c = c0 + threadIdx.x;
-            if (v < V && c < C) {
-                float a = x[v * C + c];
-                if (act == 1) a = tanhf(a);
-                else if (act == 2) a = fminf(fmaxf(a, -1.f), 1.f);
-                if (a != a) nan++;
-                mn = fminf(mn, a), mx = fmaxf(mx, a);
-                if (y_cl) y_cl[v * C + c] = a;
-                tile[i][threadIdx.x] = a;
-            }
-        }
-        __syncthreads();
-        if (y_cf) {
+    // tile: 32 voxels x 32 channels; blockDim (32, 8); every block walks several voxel tiles (grid-stride)
+    for (long long v0 = (long long)blockIdx.x * 32; v0 < V; v0 += (long long)gridDim.x * 32) {
+        for (int c0 = 0; c0 < C; c0 += 32) {
             for (int i = threadIdx.y; i < 32; i += 8) {
-                int c = c0 + i;
-                long long v = v0 + threadIdx.x;
-                if (v < V && c < C) y_cf[(size_t)c * V + v] = tile[threadIdx.x][i];
+                long long v = v0 + i;
+                int c = c0 + threadIdx.x;
+                if (v < V && c < C) {
+                    float a = x[v * C + c];
+                    if (act == 1) a = tanhf(a);
+                    else if (act == 2) a = fminf(fmaxf(a, -1.f), 1.f);
+                    if (a != a) nan++;
+                    mn = fminf(mn, a), mx = fmaxf(mx, a);
+                    if (y_cl) y_cl[v * C + c] = a;
+                    tile[i][threadIdx.x] = a;
+                }
             }
+            __syncthreads();
+            if (y_cf) {
+                for (int i = threadIdx.y; i < 32; i += 8) {
+                    int c = c0 + i;
+                    long long v = v0 + threadIdx.x;
+                    if (v < V && c < C) y_cf[(size_t)c * V + v] = tile[threadIdx.x][i];
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     if (stats) {
 #pragma unroll
@@ -447,7 +551,10 @@ __global__ void act_range_kernel(const float* __restrict__ x, long long V, int C
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             nan += __shfl_xor_sync(0xffffffffu, nan, o);
         }
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) s_mn[threadIdx.y] = mn, s_mx[threadIdx.y] = mx, s_nan[threadIdx.y] = nan;
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {  // one set of atomics per block
+            for (int w = 1; w < 8; ++w) mn = fminf(mn, s_mn[w]), mx = fmaxf(mx, s_mx[w]), nan += s_nan[w];
             if (mn != INFINITY) atomicMin(&stats[0], float_to_ordered(mn));
             if (mx != -INFINITY) atomicMax(&stats[1], float_to_ordered(mx));
             if (nan) atomicAdd(&stats[2], nan);
@@ -472,7 +579,9 @@ extern "C" int holo_range_init(int* stats4, void* stream) {
 extern "C" int holo_act_range(const float* x_cl, long long V, int C, int act, float* y_cl, float* y_cf, int* stats4,
                               void* stream) {
     HOLO_CHECK_ARG(x_cl && V > 0 && C > 0 && act >= 0 && act <= 2, "holo_act_range: bad args");
-    act_range_kernel<<<holo_cdiv(V, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(x_cl, V, C, act, y_cl, y_cf, stats4);
+    int blocks = holo_cdiv(V, 32);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    act_range_kernel<<<blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(x_cl, V, C, act, y_cl, y_cf, stats4);
     HOLO_CHECK_LAUNCH("holo_act_range");
     return HOLO_OK;
 }

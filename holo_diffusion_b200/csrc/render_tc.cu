@@ -256,6 +256,11 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
         uint4* dst = reinterpret_cast<uint4*>(smem + OFF_B1);
         for (int i = tid; i < (IMG_BYTES - OFF_B1) / 16; i += THREADS) dst[i] = src[i];
     }
+    {   // operand buffers start zeroed: for C = 16 the chunks of channels 16..31 are never written
+        uint4* z0 = reinterpret_cast<uint4*>(smem + OFF_A0);
+        uint4* z1 = reinterpret_cast<uint4*>(smem + OFF_A2);
+        for (int i = tid; i < 2 * 16 * 1024 / 16; i += THREADS) z0[i] = make_uint4(0, 0, 0, 0), z1[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid == 0) {
         for (int g = 0; g < 2; ++g) {
             mbar_init(a_full(g, 0), GROUP), mbar_init(a_full(g, 1), GROUP);
@@ -306,21 +311,31 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
         }
     } else if (warp < 8) {
         // ============================ samplers ============================
+        // Lane l OWNS ray l of the warp (depth stream), but the gather is warp-cooperative: QPR = C/4 lanes share one
+        // ray, each loading its own 16-byte channel quad of the 8 corner lines.  A warp-level LDG.128 then touches
+        // 32/QPR lines instead of 32 (the thread-per-ray gather spent ~2000 L1 wavefronts per warp and step -- it, not
+        // the MLP, bounded the kernel), and every lane ends up holding 4 channels of the sampled feature, which is
+        // exactly the granularity of the operand row pieces, so no transposition is needed.
+        constexpr int QPR = C / 4;        // lanes per ray
+        constexpr int RPI = 32 / QPR;     // rays per cooperative iteration
         const int g = warp / 4;
-        const int row = tid - g * GROUP;
+        const int row = tid - g * GROUP;  // row owned by this lane
+        const int q = lane % QPR, sub = lane / QPR;
         const long long ray_raw = (long long)blockIdx.x * RAY_THREADS + tid;
         const size_t ray = ray_raw < P.n_rays ? (size_t)ray_raw : (size_t)(P.n_rays - 1);  // idle lanes shadow the last ray
-        const int sw = row % 8;
-        const size_t row_off = (size_t)(row / 8) * 1024 + (row % 8) * 128;
-        uint8_t* a_row0 = smem + (g ? OFF_A1 : OFF_A0) + row_off;
-        uint8_t* a_row1 = smem + (g ? OFF_A3 : OFF_A2) + row_off;
-        const float* wsig = sF + F32_WSIG;
-        const float* lin = sF + F32_LIN;
+        uint8_t* a_base0 = smem + (g ? OFF_A1 : OFF_A0);
+        uint8_t* a_base1 = smem + (g ? OFF_A3 : OFF_A2);
         const float b_sigma = sF[F32_MISC];
+        // this lane's slice of the density row and of the linear radiance map (channels 4q .. 4q+3)
+        const float4 ws = *reinterpret_cast<const float4*>(sF + F32_WSIG + 4 * q);
+        const float4 la = *reinterpret_cast<const float4*>(sF + F32_LIN + 4 * q);
+        const float4 lb = *reinterpret_cast<const float4*>(sF + F32_LIN + 32 + 4 * q);
+        const float4 lc = *reinterpret_cast<const float4*>(sF + F32_LIN + 64 + 4 * q);
         float o[3], d[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) o[i] = P.origins[ray * 3 + i], d[i] = P.dirs[ray * 3 + i];
         const float* zin = P.lengths + ray * S1;
+        const int D = P.D, H = P.Hh, W = P.Ww;
         int gs = 0;
         for (int pass = 0; pass < P.n_passes; ++pass) {
             const int S = pass == 0 ? S1 : S2;
@@ -379,46 +394,69 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
             float z_nxt = (S > 1) ? next_z() : z_cur;
             for (int s = 0; s < S; ++s, ++gs) {
                 const int buf = gs & 1;
-                if (s + 1 < S)  // warm L1 with the next point's corners
-                    prefetch_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_nxt * d[0]) * P.inv_x,
-                                      (o[1] + z_nxt * d[1]) * P.inv_y, (o[2] + z_nxt * d[2]) * P.inv_z);
-                float x[32];
-                sample_point<C>(P.grid, P.D, P.Hh, P.Ww, (o[0] + z_cur * d[0]) * P.inv_x, (o[1] + z_cur * d[1]) * P.inv_y,
-                                (o[2] + z_cur * d[2]) * P.inv_z, x);
-                float s0 = b_sigma, s1 = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
-#pragma unroll
-                for (int c4 = 0; c4 < C / 4; ++c4) {
-                    const float4 ws = *reinterpret_cast<const float4*>(wsig + 4 * c4);
-                    const float4 la = *reinterpret_cast<const float4*>(lin + 4 * c4);
-                    const float4 lb = *reinterpret_cast<const float4*>(lin + 32 + 4 * c4);
-                    const float4 lc = *reinterpret_cast<const float4*>(lin + 64 + 4 * c4);
-                    const float x0 = x[4 * c4], x1 = x[4 * c4 + 1], x2 = x[4 * c4 + 2], x3 = x[4 * c4 + 3];
-                    s0 = fmaf(ws.x, x0, s0), s1 = fmaf(ws.y, x1, s1), s0 = fmaf(ws.z, x2, s0), s1 = fmaf(ws.w, x3, s1);
-                    l0 = fmaf(la.x, x0, l0), l0 = fmaf(la.y, x1, l0), l0 = fmaf(la.z, x2, l0), l0 = fmaf(la.w, x3, l0);
-                    l1 = fmaf(lb.x, x0, l1), l1 = fmaf(lb.y, x1, l1), l1 = fmaf(lb.z, x2, l1), l1 = fmaf(lb.w, x3, l1);
-                    l2 = fmaf(lc.x, x0, l2), l2 = fmaf(lc.y, x1, l2), l2 = fmaf(lc.z, x2, l2), l2 = fmaf(lc.w, x3, l2);
-                }
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float a0 = x[2 * c], a1 = x[2 * c + 1];
-                    float h0 = __bfloat162float(__float2bfloat16_rn(a0)), h1 = __bfloat162float(__float2bfloat16_rn(a1));
-                    hi[c] = pack_bf16x2(a0, a1);
-                    lo[c] = pack_bf16x2(a0 - h0, a1 - h1);
-                }
-                // both buffers of this step's parity must have been drained by the epilogue (step gs - 2)
+                // local (grid_sample) coordinates of the point this lane owns
+                const float plx = (o[0] + z_cur * d[0]) * P.inv_x, ply = (o[1] + z_cur * d[1]) * P.inv_y,
+                            plz = (o[2] + z_cur * d[2]) * P.inv_z;
+                // the slot must have been drained by the epilogue of step gs - 2 before anything is written
                 if (gs >= 2) mbar_wait(pr_free(g, buf), ((gs >> 1) - 1) & 1);
-                uint8_t* a_row = buf ? a_row1 : a_row0;
-                // row = [x_hi (4 chunks) | x_lo (4 chunks)], 16-byte chunk c lands at chunk (c ^ (row % 8))  (SWIZZLE_128B)
+                uint8_t* a_base = buf ? a_base1 : a_base0;
+                float* prb = sPR + (size_t)(g * 2 + buf) * PR_FLOATS;
+#pragma unroll 2
+                for (int it = 0; it < QPR; ++it) {
+                    const int rl = it * RPI + sub;          // lane that owns the ray handled now
+                    const float lx = __shfl_sync(0xffffffffu, plx, rl);
+                    const float ly = __shfl_sync(0xffffffffu, ply, rl);
+                    const float lz = __shfl_sync(0xffffffffu, plz, rl);
+                    // ATen grid_sampler_3d, bilinear, zeros padding, align_corners=True
+                    const float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
+                    const float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
+                    const float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
+                    const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+                    const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)W + 1.f);
+                    const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)H + 1.f);
+                    const int z0 = (int)fminf(fmaxf(fz0, -2.f), (float)D + 1.f);
+                    const float wx1 = ix - fx0, wy1 = iy - fy0, wz1 = iz - fz0;
+                    const float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy, wz0 = (fz0 + 1.f) - iz;
+                    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    *reinterpret_cast<uint4*>(a_row + ((c ^ sw) * 16)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(a_row + (((c + 4) ^ sw) * 16)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    for (int corner = 0; corner < 8; ++corner) {
+                        const int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
+                        const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+                        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
+                        const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
+                        w = ok ? w : 0.f;   // zeros padding: clamped address, weight 0 (0 * finite = 0 exactly)
+                        const int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1), zc = min(max(zz, 0), D - 1);
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(P.grid + (((size_t)zc * H + yc) * W + xc) * C) + q);
+                        x4.x = fmaf(v.x, w, x4.x), x4.y = fmaf(v.y, w, x4.y), x4.z = fmaf(v.z, w, x4.z), x4.w = fmaf(v.w, w, x4.w);
+                    }
+                    // partial dot products over this lane's 4 channels, reduced over the QPR lanes of the ray
+                    float ps = fmaf(ws.x, x4.x, fmaf(ws.y, x4.y, fmaf(ws.z, x4.z, ws.w * x4.w)));
+                    float p0 = fmaf(la.x, x4.x, fmaf(la.y, x4.y, fmaf(la.z, x4.z, la.w * x4.w)));
+                    float p1 = fmaf(lb.x, x4.x, fmaf(lb.y, x4.y, fmaf(lb.z, x4.z, lb.w * x4.w)));
+                    float p2 = fmaf(lc.x, x4.x, fmaf(lc.y, x4.y, fmaf(lc.z, x4.z, lc.w * x4.w)));
+#pragma unroll
+                    for (int off = QPR / 2; off > 0; off >>= 1) {
+                        ps += __shfl_xor_sync(0xffffffffu, ps, off);
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, off);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, off);
+                        p2 += __shfl_xor_sync(0xffffffffu, p2, off);
+                    }
+                    // operand row pieces: [x_hi (chunks 0..3) | x_lo (chunks 4..7)], this lane owns 8 bytes of each
+                    const int R = (warp % 4) * 32 + rl;   // row of the group's M tile
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(x4.x)), h1 = __bfloat162float(__float2bfloat16_rn(x4.y));
+                    const float h2 = __bfloat162float(__float2bfloat16_rn(x4.z)), h3 = __bfloat162float(__float2bfloat16_rn(x4.w));
+                    const uint2 hi = make_uint2(pack_bf16x2(x4.x, x4.y), pack_bf16x2(x4.z, x4.w));
+                    const uint2 lo = make_uint2(pack_bf16x2(x4.x - h0, x4.y - h1), pack_bf16x2(x4.z - h2, x4.w - h3));
+                    uint8_t* arow = a_base + (size_t)(R / 8) * 1024 + (R % 8) * 128;
+                    const int swz = R % 8;
+                    *reinterpret_cast<uint2*>(arow + (((q >> 1) ^ swz) * 16) + (q & 1) * 8) = hi;
+                    *reinterpret_cast<uint2*>(arow + (((4 + (q >> 1)) ^ swz) * 16) + (q & 1) * 8) = lo;
+                    if (q == 0) {
+                        prb[0 * GROUP + R] = holo_leaky(b_sigma + ps);
+                        prb[1 * GROUP + R] = p0, prb[2 * GROUP + R] = p1, prb[3 * GROUP + R] = p2;
+                    }
                 }
-                float* pr = sPR + (size_t)(g * 2 + buf) * PR_FLOATS + row;
-                pr[0 * GROUP] = holo_leaky(s0 + s1);
-                pr[1 * GROUP] = l0, pr[2 * GROUP] = l1, pr[3 * GROUP] = l2;
-                pr[4 * GROUP] = z_cur, pr[5 * GROUP] = z_nxt;
+                prb[4 * GROUP + row] = z_cur, prb[5 * GROUP + row] = z_nxt;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(a_full(g, buf));
                 z_cur = z_nxt;

@@ -134,6 +134,17 @@ def gn_stats(x1, C1, x2, C2, V, acc):
     lib().call("holo_gn_stats", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64), _stream())
 
 
+def gn_stats_pp(x1, C1, x2, C2, V, acc, acc_next):
+    lib().call("holo_gn_stats_pp", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64),
+               _ptr(acc_next, torch.float64), _stream())
+
+
+def gn_apply_fused(x1, C1, x2, C2, V, acc, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None):
+    lib().call("holo_gn_apply_fused", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta),
+               _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16),
+               _stream())
+
+
 def gn_finalize(acc, gamma, beta, film, C, V, a, b, eps=1e-5):
     lib().call("holo_gn_finalize", _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta), _ptr(film), C, V, float(eps),
                _ptr(a), _ptr(b), _stream())

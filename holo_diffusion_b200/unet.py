@@ -209,10 +209,9 @@ class UNetExecutor:
         """GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation.  Returns (fp32, hi, lo)."""
         dev = act.x1.device
         C, V = act.C, act.V
-        ops.gn_stats(act.x1, act.c1, act.x2, act.c2, V, self._acc)
-        a = torch.empty(C, device=dev)
-        b = torch.empty(C, device=dev)
-        ops.gn_finalize(self._acc, norm.weight.detach(), norm.bias.detach(), film, C, V, a, b, norm.eps)
+        acc, nxt = self._acc[self._acc_i], self._acc[self._acc_i ^ 1]
+        self._acc_i ^= 1
+        ops.gn_stats_pp(act.x1, act.c1, act.x2, act.c2, V, acc, nxt)   # accumulates into acc, clears nxt
         y = y_hi = y_lo = None
         if want_split:
             assert C % 64 == 0
@@ -220,7 +219,8 @@ class UNetExecutor:
             y_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
         else:
             y = torch.empty(V, C, device=dev)
-        ops.gn_apply(act.x1, act.c1, act.x2, act.c2, V, a, b, silu, y, y_hi, y_lo)
+        ops.gn_apply_fused(act.x1, act.c1, act.x2, act.c2, V, acc, norm.weight.detach(), norm.bias.detach(), film,
+                           norm.eps, silu, y, y_hi, y_lo)
         return y, y_hi, y_lo
 
     def _split_raw(self, act: _Act, pc: _PackedConv, ups: bool = False):
@@ -366,7 +366,10 @@ class UNetExecutor:
         p = self.p
         dev = x_cl.device
         if self._acc is None or self._acc.device != dev:
-            self._acc = torch.zeros(512, dtype=torch.float64, device=dev)
+            self._acc = torch.zeros(2, 512, dtype=torch.float64, device=dev)
+            self._acc_i = 0
+        self._acc_i = 0
+        self._acc[0].zero_()  # ping-pong GroupNorm accumulators: buffer 0 starts every forward clean (1 memset)
         mc = p.model_channels
         e0 = torch.empty(1, mc, device=dev)
         ops.timestep_embedding(t, mc, e0)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 105
+#define HOLO_B200_VERSION 106
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -102,6 +102,13 @@ int holo_gn_finalize(double* acc64, const float* gamma, const float* beta, const
                      long long V, float eps, float* a, float* b, void* stream);
 int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a, const float* b,
                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
+/* Two-launch form used by the UNet executor: stats_pp accumulates into acc64 and clears acc64_next (ping-pong, so no
+ * separate zeroing launch); apply_fused derives the affine inside every CTA (finalize folded in) and applies it. */
+int holo_gn_stats_pp(const float* x1, int C1, const float* x2, int C2, long long V, double* acc64, double* acc64_next,
+                     void* stream);
+int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
+                        const float* gamma, const float* beta, const float* film_scale_shift, float eps, int silu,
+                        float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
 /* fp32 cat(x1 (V,C1), x2 (V,C2)) -> bf16 hi/lo (Vout,Cpad): consumes the skip concat in place, zero-pads channels
  * to Cpad; upsample2x folds F.interpolate(nearest, x2) of the (Din,Hin,Win) volume (Upsample.forward,
  * unet.py:94-97), Vout = 8 V. */

@@ -78,6 +78,29 @@ def test_groupnorm(C1, C2, R, film, silu):
     assert rel_err(hi.float() + lo.float(), y) < 2e-5
 
 
+def test_groupnorm_fused_pingpong():
+    """holo_gn_stats_pp + holo_gn_apply_fused (finalize folded into apply, ping-pong accumulators)."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    C, R = 192, 6
+    V = R ** 3
+    acc = torch.zeros(2, 512, dtype=torch.float64, device="cuda")
+    acc[1] += 7.0  # garbage in the buffer the first call must clear
+    for it in range(3):
+        x = torch.randn(1, C, R, R, R, generator=g) * (1 + it) - 0.3 * it
+        gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        fl = torch.randn(2 * C, generator=g) * 0.3
+        ref = F.group_norm(x, 32, gamma, beta, 1e-5) * (1 + fl[:C].view(1, C, 1, 1, 1)) + fl[C:].view(1, C, 1, 1, 1)
+        ref = F.silu(ref)
+        cur, nxt = acc[it & 1], acc[(it & 1) ^ 1]
+        x1, x2 = _cl(x[:, :128]), _cl(x[:, 128:])
+        ops.gn_stats_pp(x1, 128, x2, 64, V, cur, nxt)
+        y = torch.empty(V, C, device="cuda")
+        ops.gn_apply_fused(x1, 128, x2, 64, V, cur, gamma.cuda(), beta.cuda(), fl.cuda(), 1e-5, True, y)
+        assert float(nxt.abs().max()) == 0.0
+        assert rel_err(_from_cl(y, C, (R, R, R)), ref) < 1e-5
+
+
 @pytest.mark.parametrize("T,heads,ch", [(64, 2, 256), (512, 2, 128), (200, 1, 32), (4096, 2, 64)])
 def test_attention(T, heads, ch):
     from holo_diffusion_b200 import ops
