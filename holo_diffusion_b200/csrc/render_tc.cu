@@ -44,7 +44,9 @@ constexpr int OFF_A3 = OFF_A2 + 16 * 1024;
 constexpr int OFF_PR = OFF_A3 + 16 * 1024;   // [group][buf][6][128] floats: sigma, lin0..2, z, z_next handed S -> E
 constexpr int PR_FLOATS = 6 * GROUP;
 constexpr int OFF_WTOT = OFF_PR + 2 * 2 * PR_FLOATS * 4;  // [group][128] cdf normaliser handed E -> S between passes
-constexpr int OFF_BAR = OFF_WTOT + 2 * GROUP * 4;         // mbarriers + tmem slot
+constexpr int CI_STRIDE = 20;                              // floats per ray: 8 corner voxel indices + 8 weights (+ pad)
+constexpr int OFF_CI = OFF_WTOT + 2 * GROUP * 4;           // [8 sampler warps][32 rays][CI_STRIDE]
+constexpr int OFF_BAR = OFF_CI + 8 * 32 * CI_STRIDE * 4;   // mbarriers + tmem slot
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
         for (int i = 0; i < 3; ++i) o[i] = P.origins[ray * 3 + i], d[i] = P.dirs[ray * 3 + i];
         const float* zin = P.lengths + ray * S1;
         const int D = P.D, H = P.Hh, W = P.Ww;
+        float* ci_warp = reinterpret_cast<float*>(smem + OFF_CI) + (size_t)warp * 32 * CI_STRIDE;
         int gs = 0;
         for (int pass = 0; pass < P.n_passes; ++pass) {
             const int S = pass == 0 ? S1 : S2;
@@ -394,19 +397,10 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
             float z_nxt = (S > 1) ? next_z() : z_cur;
             for (int s = 0; s < S; ++s, ++gs) {
                 const int buf = gs & 1;
-                // local (grid_sample) coordinates of the point this lane owns
-                const float plx = (o[0] + z_cur * d[0]) * P.inv_x, ply = (o[1] + z_cur * d[1]) * P.inv_y,
-                            plz = (o[2] + z_cur * d[2]) * P.inv_z;
-                // the slot must have been drained by the epilogue of step gs - 2 before anything is written
-                if (gs >= 2) mbar_wait(pr_free(g, buf), ((gs >> 1) - 1) & 1);
-                uint8_t* a_base = buf ? a_base1 : a_base0;
-                float* prb = sPR + (size_t)(g * 2 + buf) * PR_FLOATS;
-#pragma unroll 2
-                for (int it = 0; it < QPR; ++it) {
-                    const int rl = it * RPI + sub;          // lane that owns the ray handled now
-                    const float lx = __shfl_sync(0xffffffffu, plx, rl);
-                    const float ly = __shfl_sync(0xffffffffu, ply, rl);
-                    const float lz = __shfl_sync(0xffffffffu, plz, rl);
+                // ---- owner lane: corner voxel indices (clamped) and trilinear weights of its point, once per step
+                {
+                    const float lx = (o[0] + z_cur * d[0]) * P.inv_x, ly = (o[1] + z_cur * d[1]) * P.inv_y,
+                                lz = (o[2] + z_cur * d[2]) * P.inv_z;
                     // ATen grid_sampler_3d, bilinear, zeros padding, align_corners=True
                     const float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
                     const float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
@@ -417,29 +411,70 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                     const int z0 = (int)fminf(fmaxf(fz0, -2.f), (float)D + 1.f);
                     const float wx1 = ix - fx0, wy1 = iy - fy0, wz1 = iz - fz0;
                     const float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy, wz0 = (fz0 + 1.f) - iz;
-                    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int idx[8];
+                    float wt[8];
 #pragma unroll
                     for (int corner = 0; corner < 8; ++corner) {
                         const int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
                         const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-                        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
+                        const float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
                         const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
-                        w = ok ? w : 0.f;   // zeros padding: clamped address, weight 0 (0 * finite = 0 exactly)
+                        wt[corner] = ok ? w : 0.f;   // zeros padding: clamped address, weight 0 (0 * finite = 0 exactly)
                         const int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1), zc = min(max(zz, 0), D - 1);
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(P.grid + (((size_t)zc * H + yc) * W + xc) * C) + q);
-                        x4.x = fmaf(v.x, w, x4.x), x4.y = fmaf(v.y, w, x4.y), x4.z = fmaf(v.z, w, x4.z), x4.w = fmaf(v.w, w, x4.w);
+                        idx[corner] = (zc * H + yc) * W + xc;
                     }
-                    // partial dot products over this lane's 4 channels, reduced over the QPR lanes of the ray
-                    float ps = fmaf(ws.x, x4.x, fmaf(ws.y, x4.y, fmaf(ws.z, x4.z, ws.w * x4.w)));
-                    float p0 = fmaf(la.x, x4.x, fmaf(la.y, x4.y, fmaf(la.z, x4.z, la.w * x4.w)));
-                    float p1 = fmaf(lb.x, x4.x, fmaf(lb.y, x4.y, fmaf(lb.z, x4.z, lb.w * x4.w)));
-                    float p2 = fmaf(lc.x, x4.x, fmaf(lc.y, x4.y, fmaf(lc.z, x4.z, lc.w * x4.w)));
+                    float* ci = ci_warp + lane * CI_STRIDE;
+                    *reinterpret_cast<int4*>(ci + 0) = make_int4(idx[0], idx[1], idx[2], idx[3]);
+                    *reinterpret_cast<int4*>(ci + 4) = make_int4(idx[4], idx[5], idx[6], idx[7]);
+                    *reinterpret_cast<float4*>(ci + 8) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+                    *reinterpret_cast<float4*>(ci + 12) = make_float4(wt[4], wt[5], wt[6], wt[7]);
+                }
+                __syncwarp();
+                // the slot must have been drained by the epilogue of step gs - 2 before anything is written
+                if (gs >= 2) mbar_wait(pr_free(g, buf), ((gs >> 1) - 1) & 1);
+                uint8_t* a_base = buf ? a_base1 : a_base0;
+                float* prb = sPR + (size_t)(g * 2 + buf) * PR_FLOATS;
+#pragma unroll 2
+                for (int it = 0; it < QPR; ++it) {
+                    const int rl = it * RPI + sub;          // lane that owns the ray handled now
+                    const float* ci = ci_warp + rl * CI_STRIDE;
+                    const int4 i0 = *reinterpret_cast<const int4*>(ci + 0), i1 = *reinterpret_cast<const int4*>(ci + 4);
+                    const float4 w0 = *reinterpret_cast<const float4*>(ci + 8), w1 = *reinterpret_cast<const float4*>(ci + 12);
+                    const int idx[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+                    const float wt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float4 v[8];
 #pragma unroll
-                    for (int off = QPR / 2; off > 0; off >>= 1) {
-                        ps += __shfl_xor_sync(0xffffffffu, ps, off);
-                        p0 += __shfl_xor_sync(0xffffffffu, p0, off);
-                        p1 += __shfl_xor_sync(0xffffffffu, p1, off);
-                        p2 += __shfl_xor_sync(0xffffffffu, p2, off);
+                    for (int corner = 0; corner < 8; ++corner)   // 8 coalesced 16-byte gathers in flight
+                        v[corner] = __ldg(reinterpret_cast<const float4*>(P.grid + (size_t)idx[corner] * C) + q);
+                    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int corner = 0; corner < 8; ++corner) {
+                        x4.x = fmaf(v[corner].x, wt[corner], x4.x), x4.y = fmaf(v[corner].y, wt[corner], x4.y);
+                        x4.z = fmaf(v[corner].z, wt[corner], x4.z), x4.w = fmaf(v[corner].w, wt[corner], x4.w);
+                    }
+                    // partial dot products over this lane's 4 channels ...
+                    float pv[4];
+                    pv[0] = fmaf(ws.x, x4.x, fmaf(ws.y, x4.y, fmaf(ws.z, x4.z, ws.w * x4.w)));
+                    pv[1] = fmaf(la.x, x4.x, fmaf(la.y, x4.y, fmaf(la.z, x4.z, la.w * x4.w)));
+                    pv[2] = fmaf(lb.x, x4.x, fmaf(lb.y, x4.y, fmaf(lb.z, x4.z, lb.w * x4.w)));
+                    pv[3] = fmaf(lc.x, x4.x, fmaf(lc.y, x4.y, fmaf(lc.z, x4.z, lc.w * x4.w)));
+                    // ... reduce-scattered over the QPR lanes of the ray: after the butterfly each lane pair holds ONE
+                    // complete sum (4 + 2 [+ 1] shuffles instead of 12)
+                    int vidx = 0;
+                    {
+                        const bool up = (q & (QPR / 2)) != 0;
+                        const float s0 = up ? pv[0] : pv[2], s1 = up ? pv[1] : pv[3];
+                        float k0 = up ? pv[2] : pv[0], k1 = up ? pv[3] : pv[1];
+                        k0 += __shfl_xor_sync(0xffffffffu, s0, QPR / 2);
+                        k1 += __shfl_xor_sync(0xffffffffu, s1, QPR / 2);
+                        vidx = up ? 2 : 0;
+                        const bool up2 = (q & (QPR / 4)) != 0;
+                        const float s2 = up2 ? k0 : k1;
+                        float k = up2 ? k1 : k0;
+                        k += __shfl_xor_sync(0xffffffffu, s2, QPR / 4);
+                        vidx += up2 ? 1 : 0;
+                        if (QPR == 8) k += __shfl_xor_sync(0xffffffffu, k, 1);
+                        pv[0] = k;
                     }
                     // operand row pieces: [x_hi (chunks 0..3) | x_lo (chunks 4..7)], this lane owns 8 bytes of each
                     const int R = (warp % 4) * 32 + rl;   // row of the group's M tile
@@ -451,11 +486,10 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                     const int swz = R % 8;
                     *reinterpret_cast<uint2*>(arow + (((q >> 1) ^ swz) * 16) + (q & 1) * 8) = hi;
                     *reinterpret_cast<uint2*>(arow + (((4 + (q >> 1)) ^ swz) * 16) + (q & 1) * 8) = lo;
-                    if (q == 0) {
-                        prb[0 * GROUP + R] = holo_leaky(b_sigma + ps);
-                        prb[1 * GROUP + R] = p0, prb[2 * GROUP + R] = p1, prb[3 * GROUP + R] = p2;
-                    }
+                    if (QPR == 4 || (q & 1) == 0)
+                        prb[vidx * GROUP + R] = vidx == 0 ? holo_leaky(b_sigma + pv[0]) : pv[0];
                 }
+                __syncwarp();   // the corner scratch is rewritten by the owners in the next step
                 prb[4 * GROUP + row] = z_cur, prb[5 * GROUP + row] = z_nxt;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(a_full(g, buf));
