@@ -6,7 +6,7 @@
 // Same contract and reference citations as render.cu (holo_render_fwd); this kernel is selected for C in {16, 32}
 // with the shipped 256-wide density net.  Per depth step and group of 128 rays:
 //   ray threads : sample x (fp32) -> sigma (fp32 CUDA cores) -> write [x_hi | x_lo] as one 128-byte swizzled row
-//   MMA warp    : D[128 x 256] = [x_hi|x_lo].[W_hi|W_hi]^T + x_hi.W_lo^T                          (6 UMMAs, TMEM)
+//   MMA warp    : D[128 x 256] = [x_hi|x_lo].[W_hi|W_hi]^T + x_hi.W_lo^T + 1.[b_hi + b_lo]^T      (7 UMMAs, TMEM)
 //   ray threads : tcgen05.ld the row, rgb_pre = lin(x) + sum_j 0.4 wr_j |t_j|   (leaky(t) = 0.6 t + 0.4 |t|, the
 //                 linear part 0.6 wr.(W x + b) is a 3 x C map folded at pack time), sigmoid, compositing.
 // Two groups per CTA ping-pong so one group's MMA hides behind the other's CUDA-core work.  The refiner is
@@ -29,12 +29,14 @@ constexpr int OFF_A0 = 0;                 // [128][128B]  group 0 operand rows
 constexpr int OFF_A1 = 16 * 1024;         // group 1
 constexpr int OFF_B1 = 32 * 1024;         // [256][128B]  [W_hi | W_hi]
 constexpr int OFF_B2 = 64 * 1024;         // [256][128B]  [W_lo | 0]
-constexpr int OFF_F32 = 96 * 1024;        // fp32 parameter block (see pack kernel)
+constexpr int OFF_ONES = 96 * 1024;       // [128][128B]  [1, 1, 0, ...]
+constexpr int OFF_BB = 112 * 1024;        // [256][128B]  [b_hi, b_lo, 0, ...]
+constexpr int OFF_F32 = 144 * 1024;       // fp32 parameter block (see pack kernel)
 constexpr int F32_WSIG = 0;               // [32] density row of W_eff
 constexpr int F32_LIN = 32;               // [3][32]  0.6 * wr . W_eff[:256]
 constexpr int F32_MISC = 128;             // b_sigma, lin_const[3]
-constexpr int F32_EP = 132;               // [256] float4 (0.4 wr[0][j], 0.4 wr[1][j], 0.4 wr[2][j], b_eff[j])
-constexpr int F32_DIR = 132 + 1024;       // [3][E] + br[3]   (E <= 27)
+constexpr int F32_EP = 132;               // [256][3] 0.4 * wr[i][j] stored j-major
+constexpr int F32_DIR = 132 + 768;        // [3][E] + br[3]   (E <= 27)
 constexpr int F32_COUNT = F32_DIR + 3 * 27 + 3;
 constexpr int IMG_BYTES = OFF_F32 + ((F32_COUNT * 4 + 15) / 16) * 16;
 constexpr int OFF_A2 = ((IMG_BYTES + 1023) / 1024) * 1024;  // second operand buffer of group 0 / 1 (double buffering)
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
     // Warp-specialised pipeline per group of 128 rays (two groups per CTA):
     //   sampler warps  : depth stream (coarse / merged fine) -> trilinear gather -> sigma, linear radiance part ->
     //                    operand row [x_hi | x_lo] into A[buf], scalars into PR[buf]          (step s + 1)
-    //   MMA warp       : 6 UMMAs into the group's TMEM accumulator                            (step s)
+    //   MMA warp       : 7 UMMAs into the group's TMEM accumulator                            (step s)
     //   epilogue warps : TMEM row -> radiance -> emission-absorption compositing, outputs     (step s - 1)
     // so the three stages of consecutive depth steps overlap and 16 ray warps (instead of 8) hide each other's
     // gather / TMEM / barrier latencies.
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(GROUP >> 4) << 24);
         const uint32_t a0 = smem_u32(smem + (g ? OFF_A1 : OFF_A0)), a1 = smem_u32(smem + (g ? OFF_A3 : OFF_A2));
         const uint32_t b1 = smem_u32(smem + OFF_B1), b2 = smem_u32(smem + OFF_B2);
+        const uint32_t on = smem_u32(smem + OFF_ONES), bb = smem_u32(smem + OFF_BB);
         const uint32_t d = tmem_base + (uint32_t)(g * HID);
         for (int gs = 0; gs < total_steps; ++gs) {
             const int buf = gs & 1;
@@ -298,7 +301,8 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint32_t a = buf ? a1 : a0;
-                umma(d, sw128_desc(a), sw128_desc(b2), idesc, 0);                        // x_hi . W_lo, K 0..15 (starts the tile)
+                umma(d, sw128_desc(on), sw128_desc(bb), idesc, 0);                       // bias (starts the tile)
+                umma(d, sw128_desc(a), sw128_desc(b2), idesc, 1);                        // x_hi . W_lo, K 0..15
                 umma(d, sw128_desc(a + 32), sw128_desc(b2 + 32), idesc, 1);              //              K 16..31
 #pragma unroll
                 for (int k = 0; k < 4; ++k)                                              // [x_hi|x_lo] . [W_hi|W_hi]
@@ -550,13 +554,16 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 {
                     uint32_t ta[32], tb[32];
                     auto consume = [&](const uint32_t (&t)[32], int j0) {
-                        const float4* ep = reinterpret_cast<const float4*>(sF + F32_EP) + j0;
+                        const float4* ep = reinterpret_cast<const float4*>(sF + F32_EP + j0 * 3);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {  // hidden unit: t = |h + b|, three FMAs (two chains)
-                            const float4 e0 = ep[j], e1 = ep[j + 1];
-                            const float t0 = fabsf(__uint_as_float(t[j]) + e0.w), t1 = fabsf(__uint_as_float(t[j + 1]) + e1.w);
+                        for (int q = 0; q < 8; ++q) {  // 4 hidden units = 12 coefficients = 3 float4
+                            float4 e0 = ep[q * 3 + 0], e1 = ep[q * 3 + 1], e2 = ep[q * 3 + 2];
+                            float t0 = fabsf(__uint_as_float(t[q * 4 + 0])), t1 = fabsf(__uint_as_float(t[q * 4 + 1]));
+                            float t2 = fabsf(__uint_as_float(t[q * 4 + 2])), t3 = fabsf(__uint_as_float(t[q * 4 + 3]));
                             r0 = fmaf(e0.x, t0, r0), r1 = fmaf(e0.y, t0, r1), r2 = fmaf(e0.z, t0, r2);
-                            q0 = fmaf(e1.x, t1, q0), q1 = fmaf(e1.y, t1, q1), q2 = fmaf(e1.z, t1, q2);
+                            q0 = fmaf(e0.w, t1, q0), q1 = fmaf(e1.x, t1, q1), q2 = fmaf(e1.y, t1, q2);
+                            r0 = fmaf(e1.z, t2, r0), r1 = fmaf(e1.w, t2, r1), r2 = fmaf(e2.x, t2, r2);
+                            q0 = fmaf(e2.y, t3, q0), q1 = fmaf(e2.z, t3, q1), q2 = fmaf(e2.w, t3, q2);
                         }
                     };
                     tmem_ld32_async(taddr, ta);
@@ -574,14 +581,14 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(tm_free(g));
                 mbar_arrive(pr_free(g, buf));
-                // ex2.approx-based exp (rel. error ~2^-22, far inside the 1e-4 parity bar) instead of the ~20-instruction
-                // expf for the three sigmoids (no cancellation there)
+                // ex2.approx-based exp (rel. error ~2^-22, far inside the 1e-4 parity bar) for the three sigmoids; the
+                // opacity terms below keep the full-precision expf because 1 - exp(-x) cancels for thin samples
                 float rgb0 = __fdividef(1.f, 1.f + __expf(-holo_leaky(r0 + q0)));
                 float rgb1 = __fdividef(1.f, 1.f + __expf(-holo_leaky(r1 + q1)));
                 float rgb2 = __fdividef(1.f, 1.f + __expf(-holo_leaky(r2 + q2)));
                 float delta = (s + 1 < S) ? (z_n - z_s) : P.bg_opacity;
                 float wd = delta * fmaxf(sig, 0.f);
-                float capped = 1.f - expf(-wd);   // full-precision exp here: 1 - exp(-x) cancels for thin samples
+                float capped = 1.f - expf(-wd);
                 cum += wd;
                 float opac = 1.f - expf(-cum);
                 float absorb = (s == 0) ? 1.f : (1.f - opac_prev);
@@ -638,6 +645,8 @@ __global__ void pack_render_tc_fill_kernel(const double* __restrict__ A, const d
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __nv_bfloat16* b1 = reinterpret_cast<__nv_bfloat16*>(img + OFF_B1);
     __nv_bfloat16* b2 = reinterpret_cast<__nv_bfloat16*>(img + OFF_B2);
+    __nv_bfloat16* on = reinterpret_cast<__nv_bfloat16*>(img + OFF_ONES);
+    __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(img + OFF_BB);
     float* f32 = reinterpret_cast<float*>(img + OFF_F32);
     for (int i = tid; i < HID * 32; i += nth) {
         int j = i / 32, k = i % 32;
@@ -649,10 +658,18 @@ __global__ void pack_render_tc_fill_kernel(const double* __restrict__ A, const d
         b2[sw128_off(j, k * 2) / 2] = l;
     }
     for (int j = tid; j < HID; j += nth) {
-        f32[F32_EP + j * 4 + 0] = 0.4f * Wr[0 * (HID + E) + j];
-        f32[F32_EP + j * 4 + 1] = 0.4f * Wr[1 * (HID + E) + j];
-        f32[F32_EP + j * 4 + 2] = 0.4f * Wr[2 * (HID + E) + j];
-        f32[F32_EP + j * 4 + 3] = (float)c[j];   // hidden bias, added in the epilogue
+        float b = (float)c[j];
+        __nv_bfloat16 h = __float2bfloat16_rn(b);
+        bb[sw128_off(j, 0) / 2] = h;
+        bb[sw128_off(j, 2) / 2] = __float2bfloat16_rn(b - __bfloat162float(h));
+        // 0.4 * wr[i][j], j-major triples
+        f32[F32_EP + j * 3 + 0] = 0.4f * Wr[0 * (HID + E) + j];
+        f32[F32_EP + j * 3 + 1] = 0.4f * Wr[1 * (HID + E) + j];
+        f32[F32_EP + j * 3 + 2] = 0.4f * Wr[2 * (HID + E) + j];
+    }
+    for (int r = tid; r < GROUP; r += nth) {
+        on[sw128_off(r, 0) / 2] = __float2bfloat16_rn(1.f);
+        on[sw128_off(r, 2) / 2] = __float2bfloat16_rn(1.f);
     }
     for (int k = tid; k < 32; k += nth) f32[F32_WSIG + k] = (k < C) ? (float)A[(size_t)HID * C + k] : 0.f;
     for (int i = tid; i < 3 * 32; i += nth) {
