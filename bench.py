@@ -65,37 +65,52 @@ def workload_config(a, n_gpus):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
 def cpu_reference_step(a, rows_sample: int, seed=0):
-    """One bounded sample of the step on the CPU: full UNet forward + tanh, render of `rows_sample` image rows
-    (chunked like configs/teddybear.yaml:112), scaled to the full image.  Returns (seconds_per_view, detail)."""
+    """One BOUNDED sample of the step on the host cores (the reference algorithm = the oracle port):
+    the UNet forward + tanh on a half-resolution grid (R/2)^3 scaled by 8 (conv FLOPs scale exactly with the voxel
+    count; attention, 3.7 % of the FLOPs, scales faster, so this slightly favours the CPU), and the render of
+    `rows_sample` image rows (chunked like configs/teddybear.yaml:112) scaled to the full image.
+    Returns (seconds_per_view, detail)."""
     from fixtures import make_grid, make_mlp
     from oracle import render_oracle as ro
     from oracle import unet_oracle as uo
     torch.set_num_threads(os.cpu_count())
     C, R, HW, S = a.channels, a.resol, a.image, a.pts
-    sd = uo.make_unet_state_dict(C, C, seed=2)
-    mlp = make_mlp(C)
-    grid = make_grid(C, R, seed)
+    key = (C, R, HW, S)
+    if key not in _CPU_CACHE:  # weights / inputs are built once, outside the timed region
+        Rh = R // 2 if R >= 32 else R
+        _CPU_CACHE[key] = (uo.make_unet_state_dict(C, C, seed=2), make_mlp(C), make_grid(C, Rh, seed), make_grid(C, R, seed), Rh)
+    sd, mlp, grid_h, grid, Rh = _CPU_CACHE[key]
+    scale = (R / Rh) ** 3
     t0 = time.perf_counter()
     with torch.no_grad():
-        g = torch.tanh(uo.unet_forward(sd, grid, torch.zeros(1, dtype=torch.long)))
-    t_unet = time.perf_counter() - t0
+        torch.tanh(uo.unet_forward(sd, grid_h, torch.zeros(1, dtype=torch.long)))
+    t_unet = (time.perf_counter() - t0) * scale
     cams = ro.simple_360_cameras(8)
     b = ro.sample_rays(cams[0], HW, HW, S)
     rows = list(range(0, HW, max(1, HW // rows_sample)))[:rows_sample]
     sub = ro.OracleRayBundle(b.origins[:, rows], b.directions[:, rows], b.lengths[:, rows], b.xys[:, rows])
     t1 = time.perf_counter()
     with torch.no_grad():
-        ro.render_chunked(mlp, g, sub, R, 8.0, a.passes, a.fine, chunk_size_grid=163840)
+        ro.render_chunked(mlp, grid, sub, R, 8.0, a.passes, a.fine, chunk_size_grid=163840)
     t_render = (time.perf_counter() - t1) * (HW / len(rows))
-    return t_unet + t_render, {"t_unet_s": round(t_unet, 3), "t_render_full_est_s": round(t_render, 3), "rows": len(rows)}
+    return t_unet + t_render, {"t_unet_full_est_s": round(t_unet, 3), "t_render_full_est_s": round(t_render, 3),
+                               "rows": len(rows), "unet_sample_resol": Rh}
+
+
+def _cpu_sample_text(a, det):
+    return (f"UNet fwd on a {det['unet_sample_resol']}^3 grid x{(a.resol // det['unet_sample_resol']) ** 3} + "
+            f"{det['rows']}/{a.image} image rows rendered (chunk 163840) x{a.image // det['rows']}; oracle port, torch CPU")
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = max(4, a.image // 16)
+    rows = max(4, a.image // 32)
     for _ in range(min(a.warmup, 1)):
         cpu_reference_step(a, rows)
     ts, det = [], None
@@ -104,7 +119,7 @@ def run_reference(a):
         ts.append(t)
     sec = sum(ts) / len(ts)
     v = 1.0 / sec
-    sample = f"full UNet fwd + {det['rows']}/{a.image} image rows rendered (chunk 163840), render time scaled to the full view"
+    sample = _cpu_sample_text(a, det)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "views/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
@@ -338,9 +353,10 @@ def run_ours(a):
                         "product (hi*hi + hi*lo + lo*hi), see executed_*"}
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        sec, det = cpu_reference_step(a, max(4, a.image // 16))
+        cpu_reference_step(a, max(4, a.image // 32))  # warm-up (builds the fixtures, pages in the weights)
+        sec, det = cpu_reference_step(a, max(4, a.image // 32))
         cpu = {"value": 1.0 / sec, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"full UNet fwd + {det['rows']}/{a.image} image rows rendered, render time scaled to the full view", **det}
+               "sample": _cpu_sample_text(a, det), **det}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": a.steps,
                "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",

@@ -22,7 +22,7 @@ constexpr int HID = 256;
 constexpr int GROUP = 128;            // rays per group (= UMMA M)
 constexpr int RAY_THREADS = 2 * GROUP;      // rays per CTA
 // warp roles: [0, 256) samplers (thread = ray), [256, 512) epilogue/compositing (thread = ray), [512, 576) MMA issuers
-constexpr int THREADS = 2 * RAY_THREADS + 64;
+constexpr int THREADS = 2 * RAY_THREADS + 128;  // warps 16,17 issue MMAs; 18,19 only complete the warpgroup for setmaxnreg
 
 // shared-memory image (byte offsets; every UMMA tile 1024-aligned)
 constexpr int OFF_A0 = 0;                 // [128][128B]  group 0 operand rows
@@ -286,7 +286,13 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
     const int total_steps = S1 + (P.n_passes > 1 ? S2 : 0);
     const float eps = 1e-5f;
 
-    if (warp >= 16) {
+    // register re-balancing (per warpgroup of 4 warps): the 16 ray warps take 120 registers, the MMA warpgroup 24
+    if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+
+    if (warp >= 18) {
+        // idle filler warps of the MMA warpgroup
+    } else if (warp >= 16) {
         // ============================ MMA issuer of group g ============================
         const int g = warp - 16;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(GROUP >> 4) << 24);
