@@ -234,9 +234,11 @@ def run_ours(a):
     def pack_images(preds):
         return torch.cat([preds["images_render"][0], preds["depths_render"][0], preds["masks_render"][0]], 0).contiguous()
 
+    def step_local():  # no collective: used by the rank-0-only instrumentation passes
+        return pack_images(model(camera=cam_dev, voxel_features=grid_dev))
+
     def step_device():
-        preds = model(camera=cam_dev, voxel_features=grid_dev)
-        img = pack_images(preds)
+        img = step_local()
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, img)
         return img
@@ -286,7 +288,7 @@ def run_ours(a):
 
     model.use_cuda_graph = False
     counter["n"] = 0
-    step_device()
+    step_local()
     torch.cuda.synchronize()
     launches_per_step = counter["n"]  # C-ABI launches of one view, counted on an eager (non-graph) step
     model.use_cuda_graph = not a.no_graph
@@ -306,10 +308,10 @@ def run_ours(a):
         rec = []
         orig_tc, orig_simt = ops.conv3d_tc, ops.conv3d_simt
 
-        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None, stride=1):
+        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None, stride=1, stats=None):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo, stride)
+            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo, stride, stats)
             e.record()
             rec.append(("tc", 2.0 * (dims[0] // stride) * (dims[1] // stride) * (dims[2] // stride) * Cout * Cin * k ** 3, s, e))
             return rc
@@ -324,7 +326,7 @@ def run_ours(a):
         ops.conv3d_tc, ops.conv3d_simt = tc, simt
         model.use_cuda_graph = False
         for _ in range(3):
-            step_device()
+            step_local()
         torch.cuda.synchronize()
         ops.conv3d_tc, ops.conv3d_simt = orig_tc, orig_simt
         peaks = {}

@@ -35,7 +35,7 @@ struct Cfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 2);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*GN partials*/;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // [hi*hi + lo*hi | hi*lo]
 };
 
@@ -151,6 +151,7 @@ struct TcParams {
     float* out;
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
+    double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor (no split-K)
 };
 
 template <int BLOCK_N>
@@ -170,6 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint64_t* tmem_full_bar = empty_bar + n_stages;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_stat = reinterpret_cast<float*>(smem + n_stages * C::STAGE_BYTES + 256);  // [2][BLOCK_N] sum, sumsq
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int tiles_w = P.W / P.tw, tiles_h = P.H / P.th;
@@ -286,14 +288,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int q = warp % 4;  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
         const bool row_ok = r < rows;
+        const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
+        const bool do_stats = P.stats != nullptr && !split;
+        int stat_n0 = -1;
+        auto flush_stats = [&]() {   // all 128 epilogue threads: smem partials -> global fp64, then clear
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (stat_n0 >= 0)
+                for (int i = et; i < 2 * BLOCK_N; i += 128) {
+                    const int which = i / BLOCK_N, c = i % BLOCK_N;
+                    atomicAdd(&P.stats[(size_t)(stat_n0 + c) * 2 + which], (double)s_stat[i]);
+                }
+            for (int i = et; i < 2 * BLOCK_N; i += 128) s_stat[i] = 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        if (do_stats) flush_stats();  // clears the partials
         int local = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
             int w0, h0, d0, n0, it_begin, it_end, z;
             decode(item, w0, h0, d0, n0, it_begin, it_end, z);
+            if (do_stats && n0 != stat_n0) {
+                if (stat_n0 >= 0) flush_stats();
+                stat_n0 = n0;
+            }
             const int buf = local & 1;
             const uint32_t t_base = tmem_base + (uint32_t)(buf * C::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
             const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
-            const size_t v = ((size_t)d * P.H + h) * P.W + w;
+            const size_t v = row_ok ? ((size_t)d * P.H + h) * P.W + w : 0;
             const bool lead = z == 0;
             mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
             tc_fence_after();
@@ -302,7 +322,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 uint32_t acc[16], acc2[16];
                 tmem_ld16(t_base + (uint32_t)c0, acc);
                 tmem_ld16(t_base + (uint32_t)(BLOCK_N + c0), acc2);
-                if (!row_ok) continue;
                 const int n = n0 + c0;
                 float vals[16];
 #pragma unroll
@@ -314,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
                     }
                 }
-                if (P.residual && lead) {
+                if (P.residual && lead && row_ok) {
                     const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -322,30 +341,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
                     }
                 }
-                if (P.out && split) {
-                    float* op = P.out + v * P.out_pitch + n;
+                if (row_ok) {
+                    if (P.out && split) {
+                        float* op = P.out + v * P.out_pitch + n;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
-                } else if (P.out) {
-                    float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
+                        for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
+                    } else if (P.out) {
+                        float4* op = reinterpret_cast<float4*>(P.out + v * P.out_pitch + n);
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4)
-                        op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
-                }
-                if (P.out_hi) {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        __nv_bfloat16 h0b = __float2bfloat16_rn(vals[2 * j]), h1b = __float2bfloat16_rn(vals[2 * j + 1]);
-                        __nv_bfloat16 l0b = __float2bfloat16_rn(vals[2 * j] - __bfloat162float(h0b));
-                        __nv_bfloat16 l1b = __float2bfloat16_rn(vals[2 * j + 1] - __bfloat162float(h1b));
-                        hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-                        lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
                     }
-                    uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
-                    uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
-                    hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    if (P.out_hi) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            __nv_bfloat16 h0b = __float2bfloat16_rn(vals[2 * j]), h1b = __float2bfloat16_rn(vals[2 * j + 1]);
+                            __nv_bfloat16 l0b = __float2bfloat16_rn(vals[2 * j] - __bfloat162float(h0b));
+                            __nv_bfloat16 l1b = __float2bfloat16_rn(vals[2 * j + 1] - __bfloat162float(h1b));
+                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                        }
+                        uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
+                        uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
+                        hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                if (do_stats) {
+                    // GroupNorm statistics of the tensor being written: column sums over the warp's 32 rows by a
+                    // butterfly reduce-scatter (16 values -> one complete column per lane pair), then shared atomics
+                    float sv[16], qv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sv[j] = row_ok ? vals[j] : 0.f, qv[j] = sv[j] * sv[j];
+                    int col = 0;
+#pragma unroll
+                    for (int lvl = 16, n_keep = 8; lvl >= 2; lvl >>= 1, n_keep >>= 1) {
+                        const bool up = (lane & lvl) != 0;
+#pragma unroll
+                        for (int i = 0; i < n_keep; ++i) {
+                            const float ss = up ? sv[i] : sv[i + n_keep], sq = up ? qv[i] : qv[i + n_keep];
+                            float ks = up ? sv[i + n_keep] : sv[i], kq = up ? qv[i + n_keep] : qv[i];
+                            ks += __shfl_xor_sync(0xffffffffu, ss, lvl);
+                            kq += __shfl_xor_sync(0xffffffffu, sq, lvl);
+                            sv[i] = ks, qv[i] = kq;
+                        }
+                        col += up ? n_keep : 0;
+                    }
+                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+                    qv[0] += __shfl_xor_sync(0xffffffffu, qv[0], 1);
+                    if ((lane & 1) == 0) {
+                        atomicAdd(&s_stat[c0 + col], sv[0]);
+                        atomicAdd(&s_stat[BLOCK_N + c0 + col], qv[0]);
+                    }
                 }
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): hand the buffer back
@@ -353,6 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        if (do_stats) flush_stats();
     }
     __syncthreads();
     if (warp == 1) {
@@ -416,7 +465,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     TcParams Q = P;
     Q.m_tiles = tiles, Q.n_blocks = P.Cout / BLOCK_N, Q.nsplit = nsplit;
     Q.stages = Q.iters_per_split < Cfg<BLOCK_N>::STAGES ? Q.iters_per_split : Cfg<BLOCK_N>::STAGES;
-    const int smem = Q.stages * Cfg<BLOCK_N>::STAGE_BYTES + 1024 + 256;
+    const int smem = Q.stages * Cfg<BLOCK_N>::STAGE_BYTES + 1024 + 256 + 1024;
     // persistent grid: as many CTAs as fit on the chip (shared memory and the 512 TMEM columns bound the residency)
     static int n_sm = 0;
     if (!n_sm) {
@@ -443,7 +492,8 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
 static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int Din, int Hin,
                         int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
-                        void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0) {
+                        void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
+                        double* stats = nullptr) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -500,15 +550,19 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.tw = tw, P.th = th, P.td = td, P.stride = stride, P.iters_per_split = per;
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
+    P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     if (nsplit > 1 && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
+    int rc;
     switch (block_n) {
-        case 128: return launch<128>(ah, al, bh, bl, P, tiles, nsplit, st);
-        case 64: return launch<64>(ah, al, bh, bl, P, tiles, nsplit, st);
-        case 32: return launch<32>(ah, al, bh, bl, P, tiles, nsplit, st);
-        default: return launch<16>(ah, al, bh, bl, P, tiles, nsplit, st);
+        case 128: rc = launch<128>(ah, al, bh, bl, P, tiles, nsplit, st); break;
+        case 64: rc = launch<64>(ah, al, bh, bl, P, tiles, nsplit, st); break;
+        case 32: rc = launch<32>(ah, al, bh, bl, P, tiles, nsplit, st); break;
+        default: rc = launch<16>(ah, al, bh, bl, P, tiles, nsplit, st); break;
     }
+    if (rc == HOLO_OK && stats && !P.stats) return 1;  // done, but the statistics were not produced (split-K / pitch)
+    return rc;
 }
 
 int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, const void* w_hi,
@@ -517,13 +571,13 @@ int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int 
 
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
-                              float* out, void* out_hi_bf16, void* out_lo_bf16, void* stream) {
+                              float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, void* stream) {
     const int taps = ksize * ksize * ksize;
     // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
     // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
     // (both are bound by the SS-mode UMMA operand fetch at N = 64, not by L2), so it is off by default.
     static const bool no_halo = getenv("HOLO_CONV_HALO") == nullptr;
-    if (!no_halo && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
+    if (!no_halo && !stats_ch && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
         (out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr) && W % 8 == 0 && H % 16 == 0 && D % 2 == 0 &&
         Cout % 64 == 0 && Cin % 64 == 0 && (long long)(W / 8) * (H / 16) * (D / 2) * (Cout / 64) >= 120) {
         int rc = holo_conv3d_tc_halo(x_hi, x_lo, Cin, D, H, W, w_hi, w_lo, bias, residual, Cout, out, out_hi_bf16,
@@ -531,7 +585,8 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
         if (rc != HOLO_ERR_UNSUPPORTED) return rc;
     }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
-                        (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream);
+                        (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
+                        stats_ch);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,

@@ -213,20 +213,29 @@ __global__ void gn_apply_kernel(const float* __restrict__ x1, int C1, const floa
 // statistics) into shared memory, then streams its share of the tensor.  Saves one launch per GroupNorm.
 template <bool SILU>
 __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-                                      long long V, const double* __restrict__ acc, const float* __restrict__ gamma,
+                                      long long V, const double* __restrict__ acc, const double* __restrict__ ch1,
+                                      const double* __restrict__ ch2, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ film, float eps,
                                       float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
     extern __shared__ float s_ab[];  // a[C], b[C]
     __shared__ double s_acc[64];
     const int C = C1 + C2;
+    const int cpg = C / 32;
     if (threadIdx.x < 64) {
         double t = 0;
+        if (acc) {  // group statistics from holo_gn_stats (8 replicas)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += acc[r * 64 + threadIdx.x];
+            for (int r = 0; r < 8; ++r) t += acc[r * 64 + threadIdx.x];
+        } else {    // per-channel statistics left by the producing convolutions' epilogues
+            const int g = threadIdx.x / 2, which = threadIdx.x % 2;
+            for (int k = 0; k < cpg; ++k) {
+                const int c = g * cpg + k;
+                t += (c < C1) ? ch1[c * 2 + which] : ch2[(c - C1) * 2 + which];
+            }
+        }
         s_acc[threadIdx.x] = t;
     }
     __syncthreads();
-    const int cpg = C / 32;
     const double count = (double)V * (double)cpg;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         int g = c / cpg;
@@ -275,11 +284,13 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
     }
 }
 
-extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
-                                   const float* gamma, const float* beta, const float* film_scale_shift, float eps,
-                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream) {
+static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
+                                 const double* ch1, const double* ch2, const float* gamma, const float* beta,
+                                 const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
+                                 void* y_lo_bf16, void* stream) {
     int C = C1 + C2;
-    HOLO_CHECK_ARG(x1 && acc64 && gamma && beta && (y || y_hi_bf16) && V > 0, "holo_gn_apply_fused: bad args");
+    HOLO_CHECK_ARG(x1 && (acc64 || ch1) && gamma && beta && (y || y_hi_bf16) && V > 0, "holo_gn_apply_fused: bad args");
+    HOLO_CHECK_ARG(acc64 || C2 == 0 || ch2, "holo_gn_apply_fused_ch: statistics of the second source missing");
     HOLO_CHECK_ARG(C % 32 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 4096, "holo_gn_apply_fused: C=%d+%d unsupported", C1, C2);
     HOLO_CHECK_ARG((y_hi_bf16 == nullptr) == (y_lo_bf16 == nullptr), "holo_gn_apply_fused: hi/lo must come together");
     long long total4 = V * (C / 4);
@@ -288,12 +299,31 @@ extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int
     size_t smem = 2 * (size_t)C * sizeof(float);
     if (silu)
         gn_apply_fused_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(
-            x1, C1, x2, C2, V, acc64, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16);
+            x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
+            (uint16_t*)y_lo_bf16);
     else
         gn_apply_fused_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(
-            x1, C1, x2, C2, V, acc64, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16);
+            x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
+            (uint16_t*)y_lo_bf16);
     HOLO_CHECK_LAUNCH("holo_gn_apply_fused");
     return HOLO_OK;
+}
+
+extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
+                                   const float* gamma, const float* beta, const float* film_scale_shift, float eps,
+                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(acc64, "holo_gn_apply_fused: null statistics");
+    return gn_apply_fused_launch(x1, C1, x2, C2, V, acc64, nullptr, nullptr, gamma, beta, film_scale_shift, eps, silu, y,
+                                 y_hi_bf16, y_lo_bf16, stream);
+}
+
+extern "C" int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
+                                      const double* ch_stats2, long long V, const float* gamma, const float* beta,
+                                      const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
+                                      void* y_lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(ch_stats1, "holo_gn_apply_fused_ch: null statistics");
+    return gn_apply_fused_launch(x1, C1, x2, C2, V, nullptr, ch_stats1, ch_stats2, gamma, beta, film_scale_shift, eps,
+                                 silu, y, y_hi_bf16, y_lo_bf16, stream);
 }
 
 extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a,

@@ -145,6 +145,12 @@ def gn_apply_fused(x1, C1, x2, C2, V, acc, gamma, beta, film, eps, silu: bool, y
                _stream())
 
 
+def gn_apply_fused_ch(x1, C1, st1, x2, C2, st2, V, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None):
+    lib().call("holo_gn_apply_fused_ch", _ptr(x1), C1, _ptr(st1, torch.float64), _ptr(x2), C2, _ptr(st2, torch.float64), V,
+               _ptr(gamma), _ptr(beta), _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16),
+               _ptr(y_lo, torch.bfloat16), _stream())
+
+
 def gn_finalize(acc, gamma, beta, film, C, V, a, b, eps=1e-5):
     lib().call("holo_gn_finalize", _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta), _ptr(film), C, V, float(eps),
                _ptr(a), _ptr(b), _stream())
@@ -199,13 +205,14 @@ def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, 
 
 
 def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None,
-              stride: int = 1) -> int:
-    """dims = INPUT volume.  Returns the library status (0 ok, -3 unsupported shape); other errors raise."""
+              stride: int = 1, stats=None) -> int:
+    """dims = INPUT volume.  Returns the library status (0 ok, 1 ok but `stats` not produced, -3 unsupported shape);
+    other errors raise.  stats: optional zeroed fp64 (Cout, 2) tensor receiving per-channel (sum, sumsq) of the output."""
     rc = lib().try_call("holo_conv3d_tc", _ptr(x_hi, torch.bfloat16), _ptr(x_lo, torch.bfloat16), Cin, dims[0],
                         dims[1], dims[2], ksize, stride, _ptr(w_hi, torch.bfloat16), _ptr(w_lo, torch.bfloat16), _ptr(bias),
                         _ptr(residual), Cout, _ptr(out), _ptr(out_hi, torch.bfloat16), _ptr(out_lo, torch.bfloat16),
-                        _stream())
-    if rc not in (0, -3):
+                        _ptr(stats, torch.float64), _stream())
+    if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
 

@@ -114,10 +114,11 @@ class UNetParams(nn.Module):
 class _Act:
     """A channels-last activation made of one or two sources (the un-materialised skip concat)."""
 
-    __slots__ = ("x1", "c1", "x2", "c2", "dims")
+    __slots__ = ("x1", "c1", "x2", "c2", "dims", "st1", "st2")
 
-    def __init__(self, x1, c1, dims, x2=None, c2=0):
+    def __init__(self, x1, c1, dims, x2=None, c2=0, st1=None, st2=None):
         self.x1, self.c1, self.x2, self.c2, self.dims = x1, c1, x2, c2, dims
+        self.st1, self.st2 = st1, st2   # per-channel (sum, sumsq) left by the producing convolution, or None
 
     @property
     def C(self):
@@ -200,6 +201,15 @@ class UNetExecutor:
                 off += n
         return self._film_w, self._film_b
 
+    def _stats_slice(self, cout: int):
+        """(cout, 2) fp64 slice of the per-forward statistics arena (zeroed once per forward)."""
+        n = 2 * cout
+        if self._arena_off + n > self._arena.numel():
+            return None
+        st = self._arena[self._arena_off:self._arena_off + n]
+        self._arena_off += n
+        return st
+
     # -- primitive ops -------------------------------------------------------------------------------------
     def _tc_ok(self, pc: _PackedConv, out_dims) -> bool:
         """Can this convolution (stride 1, after any upsample) run on the tcgen05 kernel?"""
@@ -209,9 +219,6 @@ class UNetExecutor:
         """GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation.  Returns (fp32, hi, lo)."""
         dev = act.x1.device
         C, V = act.C, act.V
-        acc, nxt = self._acc[self._acc_i], self._acc[self._acc_i ^ 1]
-        self._acc_i ^= 1
-        ops.gn_stats_pp(act.x1, act.c1, act.x2, act.c2, V, acc, nxt)   # accumulates into acc, clears nxt
         y = y_hi = y_lo = None
         if want_split:
             assert C % 64 == 0
@@ -219,6 +226,14 @@ class UNetExecutor:
             y_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
         else:
             y = torch.empty(V, C, device=dev)
+        if act.st1 is not None and (act.x2 is None or act.st2 is not None):
+            # the producing convolutions already accumulated the statistics in their epilogues: one launch
+            ops.gn_apply_fused_ch(act.x1, act.c1, act.st1, act.x2, act.c2, act.st2, V, norm.weight.detach(),
+                                  norm.bias.detach(), film, norm.eps, silu, y, y_hi, y_lo)
+            return y, y_hi, y_lo
+        acc, nxt = self._acc[self._acc_i], self._acc[self._acc_i ^ 1]
+        self._acc_i ^= 1
+        ops.gn_stats_pp(act.x1, act.c1, act.x2, act.c2, V, acc, nxt)   # accumulates into acc, clears nxt
         ops.gn_apply_fused(act.x1, act.c1, act.x2, act.c2, V, acc, norm.weight.detach(), norm.bias.detach(), film,
                            norm.eps, silu, y, y_hi, y_lo)
         return y, y_hi, y_lo
@@ -233,7 +248,8 @@ class UNetExecutor:
         ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None, act.x2, act.c2)
         return hi, lo
 
-    def _conv_tc(self, pc: _PackedConv, hi, lo, in_dims, residual=None, want_split_out=False, stride=1) -> _Act:
+    def _conv_tc(self, pc: _PackedConv, hi, lo, in_dims, residual=None, want_split_out=False, stride=1,
+                 want_stats=True) -> _Act:
         dev = hi.device
         k = 3 if pc.taps == 27 else 1
         out_dims = tuple(d // stride for d in in_dims)
@@ -243,13 +259,14 @@ class UNetExecutor:
         if want_split_out:
             o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
             o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
+        st = self._stats_slice(pc.cout) if want_stats else None
         rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
-                           stride)
-        if rc != 0:
+                           stride, st)
+        if rc not in (0, 1):
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
         self.tc_calls += 1
-        r = _Act(out, pc.cout, out_dims)
+        r = _Act(out, pc.cout, out_dims, st1=st if rc == 0 else None)
         r_split = (o_hi, o_lo)
         return r if not want_split_out else (r, r_split)
 
@@ -311,7 +328,7 @@ class UNetExecutor:
         ch = C // heads
         pcq, pcp = self._pc(blk.qkv), self._pc(blk.proj_out)
         tc = self.use_tc and T % 128 == 0 and ch % 64 == 0 and C % 64 == 0
-        flat = _Act(act.x1, C, (1, 1, T))
+        flat = _Act(act.x1, C, (1, 1, T), st1=act.st1)
         if not tc:
             y, _, _ = self._gn(flat, blk.norm, None, False, False)
             qkv = self._conv_simt(pcq, flat, pre=y)
@@ -321,7 +338,7 @@ class UNetExecutor:
             return _Act(out.x1, C, act.dims)
         gdims = (T // 32, 4, 8)  # GEMM view of the token axis for the TMA box
         _, y_hi, y_lo = self._gn(flat, blk.norm, None, False, True)
-        qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True)
+        qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True, want_stats=False)
         S = torch.empty(T, T, device=dev)
         P_hi = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
         P_lo = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
@@ -341,7 +358,7 @@ class UNetExecutor:
         a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
         ops.split_bf16(a, T, C, C, a_hi, a_lo)
         out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
-        return _Act(out.x1, C, act.dims)
+        return _Act(out.x1, C, act.dims, st1=out.st1)
 
     def _run(self, seq: nn.Sequential, act: _Act, film_all) -> _Act:
         for layer in seq:
@@ -370,6 +387,10 @@ class UNetExecutor:
             self._acc_i = 0
         self._acc_i = 0
         self._acc[0].zero_()  # ping-pong GroupNorm accumulators: buffer 0 starts every forward clean (1 memset)
+        if getattr(self, "_arena", None) is None or self._arena.device != dev:
+            self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=dev)   # 2 MB: per-conv channel statistics
+        self._arena.zero_()
+        self._arena_off = 0
         mc = p.model_channels
         e0 = torch.empty(1, mc, device=dev)
         ops.timestep_embedding(t, mc, e0)
@@ -390,7 +411,7 @@ class UNetExecutor:
         act = self._run(p.middle_block, act, film_all)
         for blk in p.output_blocks:
             s = skips.pop()
-            act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1), film_all)
+            act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1, st1=act.st1, st2=s.st1), film_all)
         return self._conv_norm(p.out[2], act, p.out[0], None).x1
 
     @torch.no_grad()

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 106
+#define HOLO_B200_VERSION 107
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -109,6 +109,12 @@ int holo_gn_stats_pp(const float* x1, int C1, const float* x2, int C2, long long
 int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                         const float* gamma, const float* beta, const float* film_scale_shift, float eps, int silu,
                         float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
+/* Same, from the per-channel statistics the producing convolutions left behind (holo_conv3d_tc stats_ch): no
+ * statistics pass over the tensor at all.  ch_stats2 belongs to the second source of the concat. */
+int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
+                           const double* ch_stats2, long long V, const float* gamma, const float* beta,
+                           const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
+                           void* y_lo_bf16, void* stream);
 /* fp32 cat(x1 (V,C1), x2 (V,C2)) -> bf16 hi/lo (Vout,Cpad): consumes the skip concat in place, zero-pads channels
  * to Cpad; upsample2x folds F.interpolate(nearest, x2) of the (Din,Hin,Win) volume (Upsample.forward,
  * unet.py:94-97), Vout = 8 V. */
@@ -127,10 +133,12 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
  * are bf16 hi/lo pairs: x_hi/x_lo (V,Cin) channels-last over the INPUT volume (D,H,W), w_hi/w_lo [Cout][tap][Cin]
  * (K-major).  Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with
  * fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
- * shapes it does not take. */
+ * shapes it does not take.  stats_ch (optional, [Cout][2] doubles, pre-zeroed): per-channel (sum, sumsq) of the output
+ * for the GroupNorm that consumes it, accumulated in the epilogue; the call returns 1 instead of 0 when it had to
+ * split K and therefore did NOT produce them. */
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
-                   void* out_hi_bf16, void* out_lo_bf16, void* stream);
+                   void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
  * hi/lo pairs, K-major with arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.

@@ -316,6 +316,42 @@ def test_attention_tensor_core_pipeline(T, heads, ch):
     assert rel_err(out.t().cpu()[None], ref) < 5e-5
 
 
+def test_conv_tc_epilogue_statistics():
+    """Per-channel (sum, sumsq) accumulated by the conv epilogue feed GroupNorm without a statistics pass."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    Cin, Cout, dims = 64, 128, (16, 16, 32)
+    D, H, W = dims
+    V = D * H * W
+    x = torch.randn(1, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / math.sqrt(Cin * 27)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv3d(x, w, b, padding=1)
+    hi = torch.empty(V, Cin, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(_cl(x), V, Cin, Cin, hi, lo)
+    wk = w.reshape(Cout, Cin, -1).permute(0, 2, 1).contiguous().cuda()
+    w_hi = wk.to(torch.bfloat16)
+    w_lo = (wk - w_hi.float()).to(torch.bfloat16)
+    out = torch.empty(V, Cout, device="cuda")
+    st = torch.zeros(Cout, 2, dtype=torch.float64, device="cuda")
+    assert ops.conv3d_tc(hi, lo, Cin, dims, 3, w_hi, w_lo, b.cuda(), None, Cout, out, stats=st) == 0
+    torch.cuda.synchronize()
+    o = out.double()
+    assert rel_err(st[:, 0], o.sum(0)) < 1e-5 and rel_err(st[:, 1], (o * o).sum(0)) < 1e-5
+    # GroupNorm straight from those statistics == GroupNorm of the fp32 reference
+    gamma, beta = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    y = torch.empty(V, Cout, device="cuda")
+    ops.gn_apply_fused_ch(out, Cout, st, None, 0, None, V, gamma.cuda(), beta.cuda(), None, 1e-5, True, y)
+    refn = F.silu(F.group_norm(ref, 32, gamma, beta, 1e-5))
+    assert rel_err(_from_cl(y, Cout, dims), refn) < 1e-4
+    # small grids split K: statistics are then reported as "not produced" (return code 1)
+    st2 = torch.zeros(Cout, 2, dtype=torch.float64, device="cuda")
+    hs, ls = hi[: 8 * 8 * 8].contiguous(), lo[: 8 * 8 * 8].contiguous()
+    o2 = torch.empty(512, Cout, device="cuda")
+    assert ops.conv3d_tc(hs, ls, Cin, (8, 8, 8), 3, w_hi, w_lo, b.cuda(), None, Cout, o2, stats=st2) == 1
+
+
 def test_conv_tc_rejects_unsupported():
     from holo_diffusion_b200 import ops
     z = torch.zeros(64, 32, device="cuda", dtype=torch.bfloat16)
