@@ -286,8 +286,10 @@ __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P)
     const int total_steps = S1 + (P.n_passes > 1 ? S2 : 0);
     const float eps = 1e-5f;
 
-    // register re-balancing (per warpgroup of 4 warps): the 16 ray warps take 120 registers, the MMA warpgroup 24
-    if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    // register re-balancing (per warpgroup of 4 warps).  The CTA is launched with 96 registers x 640 threads; the MMA
+    // warpgroup drops to 24 and releases 4 x 32 x 72 = 9216 registers, which lets the 16 ray warps grow by
+    // 9216 / 512 = 18 -> 112 (a request the pool cannot cover would block forever).
+    if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
 
     if (warp >= 18) {
