@@ -109,18 +109,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -173,61 +161,6 @@ struct RenderTcParams {
     float* p_weights;
     float* scratch_w;  // [S][n_rays] coarse weights (two passes only)
 };
-
-// trilinear gather of C channels (C = 16 or 32) into x[32] (upper half zero for C = 16)
-template <int C>
-__device__ __forceinline__ void sample_point(const float* __restrict__ grid, int D, int H, int W, float lx, float ly,
-                                             float lz, float (&f)[32]) {
-    float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
-    float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
-    float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
-    float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
-    int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)W + 1.f);
-    int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)H + 1.f);
-    int z0 = (int)fminf(fmaxf(fz0, -2.f), (float)D + 1.f);
-    float wx1 = ix - fx0, wy1 = iy - fy0, wz1 = iz - fz0;
-    float wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy, wz0 = (fz0 + 1.f) - iz;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) f[c] = 0.f;
-    // branch-free: out-of-range corners read a clamped (valid) address with weight 0, so all gathers of a
-    // point can be in flight together (zeros padding of grid_sample; 0 * finite = 0 exactly)
-#pragma unroll
-    for (int corner = 0; corner < 8; ++corner) {
-        int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
-        int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
-        bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
-        w = ok ? w : 0.f;
-        int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1), zc = min(max(zz, 0), D - 1);
-        const float4* p = reinterpret_cast<const float4*>(grid + (((size_t)zc * H + yc) * W + xc) * C);
-#pragma unroll
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-            float4 v = __ldg(p + c4);
-            f[c4 * 4 + 0] = fmaf(v.x, w, f[c4 * 4 + 0]);
-            f[c4 * 4 + 1] = fmaf(v.y, w, f[c4 * 4 + 1]);
-            f[c4 * 4 + 2] = fmaf(v.z, w, f[c4 * 4 + 2]);
-            f[c4 * 4 + 3] = fmaf(v.w, w, f[c4 * 4 + 3]);
-        }
-    }
-}
-
-// L1 prefetch of the 8 corner lines of a point (one 128-byte line per corner at C = 32)
-template <int C>
-__device__ __forceinline__ void prefetch_point(const float* __restrict__ grid, int D, int H, int W, float lx, float ly,
-                                               float lz) {
-    float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
-    float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
-    float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
-    int x0 = (int)fminf(fmaxf(floorf(ix), -2.f), (float)W + 1.f);
-    int y0 = (int)fminf(fmaxf(floorf(iy), -2.f), (float)H + 1.f);
-    int z0 = (int)fminf(fmaxf(floorf(iz), -2.f), (float)D + 1.f);
-#pragma unroll
-    for (int corner = 0; corner < 8; ++corner) {
-        int xx = x0 + (corner & 1), yy = y0 + ((corner >> 1) & 1), zz = z0 + (corner >> 2);
-        if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(grid + (((size_t)zz * H + yy) * W + xx) * C));
-    }
-}
 
 template <int C>
 __global__ void __launch_bounds__(THREADS, 1) render_tc_kernel(RenderTcParams P) {
