@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-tc", action="store_true", help="force the exact-fp32 CUDA-core convolutions")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--e2e-first", action="store_true", help="debug: run the end-to-end timing loop before the device one")
     return ap.parse_args()
 
 
@@ -133,44 +135,58 @@ def run_reference(a):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    """SM clock / throttle-reason sampler for the timed region.  Uses NVML in-process (a polling `nvidia-smi -lms`
+    child was measured to slow a 2-rank run 3.4x); falls back to one `nvidia-smi` snapshot if NVML is unavailable."""
 
     def __init__(self, index: int):
-        self.samples, self.proc, self.index = [], None, index
+        self.samples, self.index, self._stop, self._thr, self._h, self._nv = [], index, False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
         except Exception:
-            self.proc = None
+            self._nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.2] or [s for (_, s) in self.samples[-3:]]
-        sm, mx, reasons = [], 0, set()
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+    def _poll(self):
+        nv = self._nv
+        while not self._stop:
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((time.perf_counter(), sm, mx, rs))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            time.sleep(0.1)
+
+    def stop(self, t0, t1):
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if self._nv is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                sm, mx = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": sm, "sm_max_mhz": mx, "reasons": [], "samples": 1, "source": "nvidia-smi snapshot after the run"}
+            except Exception:
+                return None
+        nv = self._nv
+        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.15] or self.samples[-3:]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted(k for k, bit in names.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(max(r[2] for r in rows)) if rows else None,
+                "reasons": reasons, "samples": len(rows), "source": "NVML, 100 ms polling during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -297,10 +313,14 @@ def run_ours(a):
     torch.cuda.synchronize()
     launches_per_step = counter["n"]  # C-ABI launches of one view, counted on an eager (non-graph) step
     model.use_cuda_graph = not a.no_graph
-    clocks = Clocks(local) if rank == 0 else None
-    ms_dev, _, clk = timed(step_device, a.steps, max(a.warmup, 3), clocks)
+    clocks = Clocks(local) if (rank == 0 and not a.no_clocks) else None
+    if a.e2e_first:
+        ms_e2e, _, _ = timed(step_e2e, a.steps, max(a.warmup, 3))
+        ms_dev, _, clk = timed(step_device, a.steps, 2, clocks)
+    else:
+        ms_dev, _, clk = timed(step_device, a.steps, max(a.warmup, 3), clocks)
+        ms_e2e, _, _ = timed(step_e2e, a.steps, 2)
     launches = launches_per_step * a.steps
-    ms_e2e, _, _ = timed(step_e2e, a.steps, 2)
     views = a.steps * world
     value = views / (ms_dev / 1e3)
     e2e = views / (ms_e2e / 1e3)
