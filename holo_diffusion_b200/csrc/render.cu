@@ -9,16 +9,8 @@
 //   pytorch3d 0.7.4 EmissionAbsorptionRaymarcher / RayPointRefiner / sample_pdf / NDCMultinomialRaysampler
 //   (un-vendored; arithmetic per SURVEY.md Appendix A).
 #include "common.cuh"
+#include "render_device.cuh"
 #include "../../include/holo_b200.h"
-
-// ------------------------------------------------------------------------------------------------
-// torch.linspace(0, 1, n)[i] in fp32 (ATen computes the upper half from the end point)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float linspace01(int i, int n) {
-    if (n == 1) return 0.0f;
-    float step = 1.0f / (float)(n - 1);
-    return (i < n / 2) ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Ray generation (NDCMultinomialRaysampler + AdaptiveRaySampler depth bounds), eval / full-grid mode.
@@ -215,101 +207,6 @@ struct RenderParams {
     int n_passes;
 };
 
-template <int C>
-__device__ __forceinline__ void sample_trilinear(const float* __restrict__ grid, int D, int H, int W, float lx,
-                                                 float ly, float lz, float (&f)[C]) {
-    // ATen grid_sampler_3d, bilinear, zeros padding, align_corners=True
-    float ix = ((lx + 1.f) / 2.f) * (float)(W - 1);
-    float iy = ((ly + 1.f) / 2.f) * (float)(H - 1);
-    float iz = ((lz + 1.f) / 2.f) * (float)(D - 1);
-    float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
-    // clamp before the int conversion so that far-away points cannot overflow (they are out of range anyway)
-    int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)W + 1.f);
-    int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)H + 1.f);
-    int z0 = (int)fminf(fmaxf(fz0, -2.f), (float)D + 1.f);
-    float x1f = fx0 + 1.f, y1f = fy0 + 1.f, z1f = fz0 + 1.f;
-    float wx0 = x1f - ix, wx1 = ix - fx0;
-    float wy0 = y1f - iy, wy1 = iy - fy0;
-    float wz0 = z1f - iz, wz1 = iz - fz0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) f[c] = 0.f;
-#pragma unroll
-    for (int corner = 0; corner < 8; ++corner) {
-        int dx = corner & 1, dy = (corner >> 1) & 1, dz = corner >> 2;
-        int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
-        float w = (dx ? wx1 : wx0) * (dy ? wy1 : wy0) * (dz ? wz1 : wz0);
-        if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) {
-            const float4* p = reinterpret_cast<const float4*>(grid + (((size_t)zz * H + yy) * W + xx) * C);
-#pragma unroll
-            for (int c4 = 0; c4 < C / 4; ++c4) {
-                float4 v = __ldg(p + c4);
-                f[c4 * 4 + 0] += v.x * w;
-                f[c4 * 4 + 1] += v.y * w;
-                f[c4 * 4 + 2] += v.z * w;
-                f[c4 * 4 + 3] += v.w * w;
-            }
-        }
-    }
-}
-
-// Decode NP points at once: sigma_raw and rgb (after sigmoid) from features.
-template <int C, int NP>
-__device__ __forceinline__ void decode_points(const float* __restrict__ sW, const float4* __restrict__ sEp,
-                                              float b_sigma, int Hd, const float (&x)[NP][C], const float (&rd)[3],
-                                              float (&sigma)[NP], float (&rgb)[NP][3]) {
-    float r[NP][3];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) r[p][0] = rd[0], r[p][1] = rd[1], r[p][2] = rd[2];
-    for (int j = 0; j < Hd; ++j) {
-        const float4* wrow = reinterpret_cast<const float4*>(sW + (size_t)j * C);
-        float4 ep = sEp[j];
-        float a0[NP], a1[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) a0[p] = ep.w, a1[p] = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-            float4 w = wrow[c4];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                a0[p] = fmaf(w.x, x[p][c4 * 4 + 0], a0[p]);
-                a1[p] = fmaf(w.y, x[p][c4 * 4 + 1], a1[p]);
-                a0[p] = fmaf(w.z, x[p][c4 * 4 + 2], a0[p]);
-                a1[p] = fmaf(w.w, x[p][c4 * 4 + 3], a1[p]);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            float h = holo_leaky(a0[p] + a1[p]);
-            r[p][0] = fmaf(ep.x, h, r[p][0]);
-            r[p][1] = fmaf(ep.y, h, r[p][1]);
-            r[p][2] = fmaf(ep.z, h, r[p][2]);
-        }
-    }
-    {
-        const float4* wrow = reinterpret_cast<const float4*>(sW + (size_t)Hd * C);
-        float a0[NP], a1[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) a0[p] = b_sigma, a1[p] = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-            float4 w = wrow[c4];
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                a0[p] = fmaf(w.x, x[p][c4 * 4 + 0], a0[p]);
-                a1[p] = fmaf(w.y, x[p][c4 * 4 + 1], a1[p]);
-                a0[p] = fmaf(w.z, x[p][c4 * 4 + 2], a0[p]);
-                a1[p] = fmaf(w.w, x[p][c4 * 4 + 3], a1[p]);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < NP; ++p) sigma[p] = holo_leaky(a0[p] + a1[p]);
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) rgb[p][i] = 1.f / (1.f + expf(-holo_leaky(r[p][i])));
-}
-
 template <int C, int NP, int RT>
 __global__ void __launch_bounds__(RT) render_fused_kernel(RenderParams P) {
     extern __shared__ __align__(16) float smem[];
@@ -341,24 +238,7 @@ __global__ void __launch_bounds__(RT) render_fused_kernel(RenderParams P) {
     }
     // per-ray part of the radiance layer: br + Wr[:, H:] . PE(dn)
     float rd[3];
-    {
-        const float* br = sDir + 3 * E;
-        rd[0] = br[0], rd[1] = br[1], rd[2] = br[2];
-        const int nh = P.n_harm;
-        for (int c = 0; c < 3; ++c) {
-            float freq = 1.f;
-            for (int k = 0; k < nh; ++k) {
-                float e = dn[c] * freq;
-                float sn = sinf(e), cs = cosf(e);
-                int ms = c * nh + k, mc = 3 * nh + c * nh + k;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + ms] * sn + sDir[i * E + mc] * cs;
-                freq *= 2.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) rd[i] += sDir[i * E + 6 * nh + c] * dn[c];
-        }
-    }
+    dir_radiance_const(sDir, E, P.n_harm, dn, rd);
 
     const int S1 = P.S;
     const int S2 = P.add_input ? P.S + P.n_fine : P.n_fine;
