@@ -33,6 +33,21 @@ class ImplicitronRender:
     mask_render: Optional[torch.Tensor] = None
 
 
+def _cat_render_outputs(outs: List[Optional[RendererOutput]], B: int, spatial) -> Optional[RendererOutput]:
+    """apply_chunked's collation: cat along the ray dimension, restore (B, *spatial, -1), recurse into prev_stage."""
+    if outs[0] is None:
+        return None
+
+    def cat(ts):
+        return None if ts[0] is None else torch.cat(ts, dim=1).reshape(B, *spatial, -1)
+
+    aux = {k: (cat([o.aux[k] for o in outs]) if torch.is_tensor(v) else v) for k, v in outs[0].aux.items()}
+    return RendererOutput(features=cat([o.features for o in outs]), depths=cat([o.depths for o in outs]),
+                          masks=cat([o.masks for o in outs]), normals=cat([o.normals for o in outs]),
+                          points=cat([o.points for o in outs]), weights=cat([o.weights for o in outs]), aux=aux,
+                          prev_stage=_cat_render_outputs([o.prev_stage for o in outs], B, spatial))
+
+
 class HoloDiffusionModel(nn.Module):
     def __init__(self, resol: int = 16, volume_extent: float = 8.0, feature_size: int = 64, num_passes: int = 2,
                  render_image_width: int = 256, render_image_height: int = 256, net_3d_enabled: bool = True,
@@ -43,7 +58,7 @@ class HoloDiffusionModel(nn.Module):
                  renderer_HoloMultiPassEmissionAbsorptionRenderer_args: Optional[dict] = None,
                  implicit_function_class_type: str = "HoloVoxelGridImplicitFunction",
                  implicit_function_HoloVoxelGridImplicitFunction_args: Optional[dict] = None,
-                 use_cuda_graph: bool = True, **unused):
+                 chunk_size_grid: int = 4096, use_cuda_graph: bool = True, **unused):
         super().__init__()
         if implicit_function_class_type != "HoloVoxelGridImplicitFunction":
             raise ValueError(f"{type(self)} supports only HoloVoxelGridImplicitFunction!")
@@ -52,6 +67,7 @@ class HoloDiffusionModel(nn.Module):
             raise NotImplementedError("plug-in type not built")
         self.resol, self.volume_extent, self.feature_size, self.num_passes = resol, volume_extent, feature_size, num_passes
         self.render_image_width, self.render_image_height = render_image_width, render_image_height
+        self.chunk_size_grid = chunk_size_grid
         self.net_3d_enabled, self.diffusion_enabled = net_3d_enabled, diffusion_enabled
         self.net_3d = None
         if net_3d_enabled:
@@ -116,10 +132,36 @@ class HoloDiffusionModel(nn.Module):
         for func in self._implicit_functions:
             func.bind_args(voxel_grid_features=voxel_features, voxel_grid_features_channels_last=grid_cl.view(R, R, R, C))
         ray_bundle = self.raysampler(cam, EvaluationMode.EVALUATION)
-        rendered = self.renderer(ray_bundle, list(self._implicit_functions), EvaluationMode.EVALUATION)
+        rendered = self._render(ray_bundle=ray_bundle, chunksize=self.chunk_size_grid,
+                                implicit_functions=list(self._implicit_functions),
+                                evaluation_mode=EvaluationMode.EVALUATION)
         for func in self._implicit_functions:
             func.unbind_args()
         return rendered, ray_bundle, voxel_features
+
+    # ------------------------------------------------------------------ GenericModel._render (chunked rendering)
+    def _render(self, *, ray_bundle: ImplicitronRayBundle, chunksize: int, **kwargs) -> RendererOutput:
+        """pytorch3d GenericModel._render + chunk_generator / apply_chunked (entered holo_diffusion_model.py:451-457):
+        rays flattened to (B, n_rays), n_chunks = ceil(n_rays * S / chunksize), rays_per_chunk = ceil(n_rays /
+        n_chunks), every RendererOutput field (and the prev_stage chain) concatenated along the ray dimension and
+        reshaped to (B, *spatial, -1).  The fused kernel materialises nothing per point, so it takes all rays in
+        one launch whatever the chunk size; chunking applies to the staged (per-plug-in) path."""
+        if chunksize <= 0 or self.renderer.is_fused(kwargs["implicit_functions"], kwargs["evaluation_mode"]):
+            return self.renderer(ray_bundle=ray_bundle, **kwargs)
+        B, *spatial, S = ray_bundle.lengths.shape
+        if S > 0 and chunksize % S != 0:
+            raise ValueError(f"chunk_size_grid ({chunksize}) should be divisible by n_pts_per_ray ({S})")
+        n = 1
+        for d in spatial:
+            n *= d
+        n_chunks = -(-n * max(S, 1) // chunksize)
+        per = -(-n // n_chunks)
+        o, d, l, xy = (ray_bundle.origins.reshape(B, n, 3), ray_bundle.directions.reshape(B, n, 3),
+                       ray_bundle.lengths.reshape(B, n, S), ray_bundle.xys.reshape(B, n, 2))
+        outs = [self.renderer(ray_bundle=ImplicitronRayBundle(o[:, a:a + per], d[:, a:a + per], l[:, a:a + per],
+                                                              xy[:, a:a + per]), **kwargs)
+                for a in range(0, n, per)]
+        return _cat_render_outputs(outs, B, spatial)
 
     def _weights_signature(self):
         return sum(p._version for p in self.parameters()), next(self.parameters()).data_ptr()

@@ -122,6 +122,70 @@ def render_fwd(grid_dhwc, volume_extent: float, packed_mlp, hidden: int, n_harmo
     return out
 
 
+def _hostf(v: Sequence[float]):
+    return (ctypes.c_float * len(v))(*[float(x) for x in v])
+
+
+def if_fwd(grid_dhwc, volume_extent: float, packed_mlp, hidden: int, n_harmonic: int, *, origins=None, dirs=None,
+           lengths=None, pts_3d=None, S: int = 1, head=None, normals: bool = False):
+    """HoloVoxelGridImplicitFunction.forward on n_points = n_rays * S points (holo_if_fwd).
+    Either (origins, dirs, lengths (n_rays,S)) or pts_3d (n_points,3) [+ dirs (n_rays,3) or None = dummy ones].
+    head = (weight (F,hidden), bias (F)) of the view-independent feature net or None."""
+    D, H, W, C = grid_dhwc.shape
+    dev = grid_dhwc.device
+    if pts_3d is not None:
+        n_points = pts_3d.shape[0]
+    else:
+        n_points = lengths.shape[0] * lengths.shape[1]
+        S = lengths.shape[1]
+    F = 0 if head is None else head[0].shape[0]
+    dens = torch.empty(n_points, device=dev)
+    feats = torch.empty(n_points, 3 + F, device=dev)
+    nrm = torch.empty(n_points, 3, device=dev) if normals else None
+    lib().call("holo_if_fwd", _ptr(grid_dhwc), D, H, W, C, float(volume_extent), _ptr(packed_mlp), hidden, n_harmonic,
+               _ptr(head[0]) if head else None, _ptr(head[1]) if head else None, F, _ptr(origins), _ptr(dirs),
+               _ptr(lengths), _ptr(pts_3d), n_points, S, _ptr(dens), _ptr(feats), _ptr(nrm), _stream())
+    return dens, feats, nrm
+
+
+def render_mlp_fwd(feats, view_dirs, packed_mlp, hidden: int, n_harmonic: int, head=None):
+    """RenderMLP.forward on (n_points, C) features and (n_points, 3) view directions (holo_render_mlp_fwd)."""
+    n_points, C = feats.shape
+    dev = feats.device
+    F = 0 if head is None else head[0].shape[0]
+    dens = torch.empty(n_points, device=dev)
+    out = torch.empty(n_points, 3 + F, device=dev)
+    lib().call("holo_render_mlp_fwd", _ptr(feats), _ptr(view_dirs), n_points, C, _ptr(packed_mlp), hidden, n_harmonic,
+               _ptr(head[0]) if head else None, _ptr(head[1]) if head else None, F, _ptr(dens), _ptr(out), _stream())
+    return dens, out
+
+
+def ea_raymarch(densities, features, lengths, bg: Sequence[float], background_opacity: float = 1e10, noise=None,
+                normals=None):
+    """EmissionAbsorptionRaymarcher on (n_rays,S) densities, (n_rays,S,Fd) features (holo_ea_raymarch)."""
+    n_rays, S = lengths.shape
+    Fd = features.shape[-1]
+    dev = lengths.device
+    out = {"features": torch.empty(n_rays, Fd, device=dev), "depths": torch.empty(n_rays, 1, device=dev),
+           "masks": torch.empty(n_rays, 1, device=dev), "weights": torch.empty(n_rays, S, device=dev),
+           "normals": torch.empty(n_rays, 3, device=dev) if normals is not None else None}
+    bgv = _hostf(bg)
+    lib().call("holo_ea_raymarch", _ptr(densities), _ptr(features), _ptr(lengths), _ptr(noise), _ptr(normals), n_rays,
+               S, Fd, ctypes.cast(bgv, ctypes.c_void_p), len(bg), float(background_opacity), _ptr(out["features"]),
+               _ptr(out["depths"]), _ptr(out["masks"]), _ptr(out["weights"]), _ptr(out["normals"]), _stream())
+    return out
+
+
+def ray_refine(lengths, weights, n_fine: int, add_input_samples: bool = True, u=None):
+    """RayPointRefiner: (n_rays,S) depths + weights -> sorted (n_rays, S + n_fine) depths (holo_ray_refine)."""
+    n_rays, S = lengths.shape
+    S2 = S + n_fine if add_input_samples else n_fine
+    out = torch.empty(n_rays, S2, device=lengths.device)
+    lib().call("holo_ray_refine", _ptr(lengths), _ptr(weights), _ptr(u), n_rays, S, n_fine,
+               1 if add_input_samples else 0, _ptr(out), _stream())
+    return out
+
+
 # ------------------------------------------------------------------ denoiser
 def transpose2d(src, rows: int, cols: int, out=None):
     if out is None:

@@ -5,9 +5,14 @@ Mirrors (class names, constructor fields, parameter names):
   * ``MLPWithInputSkips`` parameter layout          -- /root/reference/holo_diffusion/custom_modules.py:44-160
   * ``HoloMultiPassEmissionAbsorptionRenderer``     -- /root/reference/holo_diffusion/holo_multipass_ea.py:15-125
   * ``EmissionAbsorptionRaymarcher`` settings       -- /root/reference/configs/base.yaml:149-159
-Implicitron materialises (densities, features) between the implicit function and the ray marcher; here the
-seam sits at the renderer: ``HoloMultiPassEmissionAbsorptionRenderer.forward`` recognises its own implicit function
-and runs ONE kernel launch for all rays and all passes (``holo_render_fwd``).
+  * ``EmissionAbsorptionRaymarcher`` / ``RayPointRefiner`` -- pytorch3d 0.7.4 (un-vendored), invoked at
+    /root/reference/holo_diffusion/holo_multipass_ea.py:96-116
+Implicitron materialises (densities, features) between the implicit function and the ray marcher.  Two paths:
+  * fused (the hot path): ``HoloMultiPassEmissionAbsorptionRenderer.forward`` recognises its own implicit function
+    and runs ONE kernel launch for all rays and all passes (``holo_render_fwd[_tc]``);
+  * staged: every plug-in is callable on its own (``holo_if_fwd``, ``holo_ea_raymarch``, ``holo_ray_refine``) and
+    ``_run_raymarcher`` chains them exactly as the reference does -- taken for ``render_normals``, the
+    view-independent feature head, training-mode noise / stratified refinement, or a foreign plug-in.
 """
 from __future__ import annotations
 
@@ -64,23 +69,28 @@ class RenderMLP(nn.Module):
                  rnet_input_skips: Sequence[int] = (), activation_fn: str = "LEAKYRELU"):
         super().__init__()
         if feat_emb_dims != 0 or rnet_num_layers != 1 or output_feature_dims != 3:
-            raise NotImplementedError("fused renderer covers the shipped RenderMLP: identity feature embedding, "
+            raise NotImplementedError("the kernels cover the shipped RenderMLP: identity feature embedding, "
                                       "one radiance layer, RGB output")
         if str(activation_fn).upper().split(".")[-1] != "LEAKYRELU":
             raise NotImplementedError("only the LeakyReLU(0.2) hidden activation of the shipped configs is built")
-        if output_vp_independent_feature_dims != 0:
-            raise NotImplementedError("view-independent feature head: HoloDiffusionModel forces feature_dim=0 "
-                                      "(holo_diffusion_model.py:156)")
+        if not 0 <= output_vp_independent_feature_dims <= 64:
+            raise NotImplementedError("view-independent feature head of at most 64 outputs")
         self.input_dims, self.dir_emb_dims, self.dnet_hidden_dim = input_dims, dir_emb_dims, dnet_hidden_dim
+        self.output_feature_dims = output_feature_dims
+        self.output_vp_independent_feature_dims = output_vp_independent_feature_dims
         E = 3 * (2 * dir_emb_dims + 1)
         self._density_net = _MLPParams(dnet_num_layers, input_dims, dnet_hidden_dim + 1, input_dims, dnet_hidden_dim,
                                        dnet_input_skips)
         self._radiance_net = _MLPParams(1, dnet_hidden_dim + E, 3, dnet_hidden_dim + E, rnet_hidden_dim, ())
+        self._feature_net = None
+        if output_vp_independent_feature_dims > 0:  # holo_voxel_grid_implicit_function.py:94-105
+            self._feature_net = _MLPParams(1, dnet_hidden_dim, output_vp_independent_feature_dims, dnet_hidden_dim,
+                                           rnet_hidden_dim, ())
         self._packed = None
         self._packed_key = None
 
     def packed(self):
-        """Collapsed + packed weights for the render kernel, rebuilt only when a parameter changes."""
+        """Collapsed + packed weights for the render kernels, rebuilt only when a parameter changes."""
         ps = list(self.parameters())
         key = tuple((p._version, p.data_ptr()) for p in ps)
         if key != self._packed_key:
@@ -93,14 +103,37 @@ class RenderMLP(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def head(self) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        if self._feature_net is None:
+            return None
+        lin = self._feature_net.mlp[0][0]
+        return lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+
+    @torch.no_grad()
+    def forward(self, features: torch.Tensor, view_dirs: torch.Tensor):
+        """-> densities (...,1), radiance (...,3), view-independent features (...,F) or None (:107-129)."""
+        sp = features.shape[:-1]
+        packed, hidden, _, _ = self.packed()
+        dens, out = ops.render_mlp_fwd(features.reshape(-1, self.input_dims).contiguous().float(),
+                                       view_dirs.expand(*sp, 3).reshape(-1, 3).contiguous().float(), packed, hidden,
+                                       self.dir_emb_dims, self.head())
+        vp = out[:, 3:].reshape(*sp, -1) if self._feature_net is not None else None
+        return dens.view(*sp, 1), out[:, :3].reshape(*sp, 3), vp
+
+
+def grid_to_channels_last(grid_ncdhw: torch.Tensor) -> torch.Tensor:
+    """(1,C,D,H,W) -> (D,H,W,C) with the transpose kernel (one 128-byte line per voxel corner at C=32)."""
+    _, C, D, H, W = grid_ncdhw.shape
+    V = D * H * W
+    return ops.transpose2d(grid_ncdhw.contiguous().float().reshape(-1), C, V).view(D, H, W, C)
+
 
 class HoloVoxelGridImplicitFunction(nn.Module):
     def __init__(self, resol: int = 32, volume_extent: float = 8.0, n_hidden: int = 128, feature_dim: int = 64,
                  init_density_bias: float = 1e-4, render_normals: bool = False, render_mlp_args: Optional[dict] = None):
         super().__init__()
-        if render_normals:
-            raise NotImplementedError("render_normals (autograd normals) is not part of the built path")
         self.resol, self.volume_extent, self.n_hidden, self.feature_dim = resol, volume_extent, n_hidden, feature_dim
+        self.init_density_bias, self.render_normals = init_density_bias, render_normals
         args = dict(render_mlp_args or {})
         args.update(input_dims=n_hidden, output_feature_dims=3, output_vp_independent_feature_dims=feature_dim)
         self.render_mlp = RenderMLP(**args)
@@ -109,10 +142,42 @@ class HoloVoxelGridImplicitFunction(nn.Module):
     def allows_multiple_passes() -> bool:
         return True
 
-    def forward(self, *, ray_bundle=None, pts_3d=None, voxel_grid_features=None, **kwargs):
-        raise NotImplementedError(
-            "The per-point (densities, features) seam is fused away: render through "
-            "HoloMultiPassEmissionAbsorptionRenderer, which launches holo_render_fwd for this implicit function.")
+    @torch.no_grad()
+    def forward(self, *, ray_bundle: Optional[ImplicitronRayBundle] = None, fun_viewpool=None, camera=None,
+                global_code=None, run_id=None, pass_number=None, pts_3d: Optional[torch.Tensor] = None,
+                voxel_grid_features: Optional[torch.Tensor] = None,
+                voxel_grid_features_channels_last: Optional[torch.Tensor] = None, **kwargs):
+        """-> densities (...,S,1), features (...,S,3[+feature_dim]), aux {"normals": (...,S,3)} (:182-269).
+        One ``holo_if_fwd`` launch: ray points, trilinear sampling, RenderMLP and the analytic normals."""
+        assert voxel_grid_features is not None or voxel_grid_features_channels_last is not None, \
+            "voxel_grid_features must be provided!"
+        assert ray_bundle is not None or pts_3d is not None, "either ray_bundle or pts_3d must be provided!"
+        grid_cl = voxel_grid_features_channels_last
+        if grid_cl is None:
+            assert voxel_grid_features.shape[0] == 1, "only batch size of 1 is supported"
+            grid_cl = grid_to_channels_last(voxel_grid_features)
+        packed, hidden, _, _ = self.render_mlp.packed()
+        kw = dict(head=self.render_mlp.head(), normals=self.render_normals)
+        if pts_3d is None:
+            spatial = ray_bundle.lengths.shape
+            S = spatial[-1]
+            n = int(torch.Size(spatial[:-1]).numel())
+            dens, feats, nrm = ops.if_fwd(grid_cl, self.volume_extent, packed, hidden, self.render_mlp.dir_emb_dims,
+                                          origins=ray_bundle.origins.reshape(n, 3).contiguous().float(),
+                                          dirs=ray_bundle.directions.reshape(n, 3).contiguous().float(),
+                                          lengths=ray_bundle.lengths.reshape(n, S).contiguous().float(), **kw)
+        else:
+            spatial = pts_3d.shape[:-1]
+            S = spatial[-1]
+            dirs = None
+            if ray_bundle is not None:
+                dirs = ray_bundle.directions.reshape(-1, 3).contiguous().float()
+            dens, feats, nrm = ops.if_fwd(grid_cl, self.volume_extent, packed, hidden, self.render_mlp.dir_emb_dims,
+                                          dirs=dirs, pts_3d=pts_3d.reshape(-1, 3).contiguous().float(), S=S, **kw)
+        aux: Dict[str, Any] = {}
+        if nrm is not None:
+            aux["normals"] = nrm.view(*spatial, 3)
+        return dens.view(*spatial, 1), feats.view(*spatial, feats.shape[-1]), aux
 
 
 class ImplicitFunctionWrapper(nn.Module):
@@ -129,12 +194,72 @@ class ImplicitFunctionWrapper(nn.Module):
     def unbind_args(self):
         self.bound_args = {}
 
+    def forward(self, *args, **kwargs):
+        return self._fn(*args, **{**self.bound_args, **kwargs})
 
-def grid_to_channels_last(grid_ncdhw: torch.Tensor) -> torch.Tensor:
-    """(1,C,D,H,W) -> (D,H,W,C) with the transpose kernel (one 128-byte line per voxel corner at C=32)."""
-    _, C, D, H, W = grid_ncdhw.shape
-    V = D * H * W
-    return ops.transpose2d(grid_ncdhw.contiguous().float().reshape(-1), C, V).view(D, H, W, C)
+
+class EmissionAbsorptionRaymarcher(nn.Module):
+    """pytorch3d 0.7.4 EmissionAbsorptionRaymarcher (configs/base.yaml:149-159) over ``holo_ea_raymarch``."""
+
+    def __init__(self, surface_thickness: int = 1, bg_color: Sequence[float] = (0.0,), replicate_last_interval: bool = False,
+                 background_opacity: float = 1e10, density_relu: bool = True, blend_output: bool = False):
+        super().__init__()
+        if surface_thickness != 1 or replicate_last_interval or not density_relu or blend_output:
+            raise NotImplementedError("ray marcher kernels cover the shipped settings (configs/base.yaml:150-159)")
+        self.surface_thickness, self.replicate_last_interval = surface_thickness, replicate_last_interval
+        self.density_relu, self.blend_output = density_relu, blend_output
+        self.bg_color = tuple(float(x) for x in bg_color)
+        self.background_opacity = float(background_opacity)
+
+    @torch.no_grad()
+    def forward(self, rays_densities: torch.Tensor, rays_features: torch.Tensor, aux: Dict[str, Any],
+                ray_lengths: torch.Tensor, ray_deltas: Optional[torch.Tensor] = None, density_noise_std: float = 0.0,
+                **kwargs) -> RendererOutput:
+        if ray_deltas is not None:
+            raise NotImplementedError("explicit ray_deltas")
+        spatial = ray_lengths.shape[:-1]
+        S = ray_lengths.shape[-1]
+        n = int(torch.Size(spatial).numel())
+        Fd = rays_features.shape[-1]
+        if len(self.bg_color) not in (1, Fd):
+            raise ValueError(f"Wrong number of background color channels: {len(self.bg_color)} for {Fd} features")
+        dens = rays_densities.reshape(n, S).contiguous().float()
+        noise = None
+        if density_noise_std > 0.0:
+            noise = (torch.randn_like(dens) * density_noise_std).contiguous()
+        aux = dict(aux)
+        normals = aux.get("normals")
+        o = ops.ea_raymarch(dens, rays_features.reshape(n, S, Fd).contiguous().float(),
+                            ray_lengths.reshape(n, S).contiguous().float(), self.bg_color, self.background_opacity,
+                            noise=noise, normals=None if normals is None else normals.reshape(n, S, 3).contiguous())
+        if normals is not None:
+            # the reference multiplies and sums in Python (holo_multipass_ea.py:104-109); the kernel did it already
+            aux.pop("normals")
+            aux["rendered_normals"] = o["normals"].view(*spatial, 3)
+        return RendererOutput(features=o["features"].view(*spatial, Fd), depths=o["depths"].view(*spatial, 1),
+                              masks=o["masks"].view(*spatial, 1), weights=o["weights"].view(*spatial, S), aux=aux)
+
+
+class RayPointRefiner:
+    """pytorch3d 0.7.4 RayPointRefiner (+ sample_pdf) over ``holo_ray_refine``; random_sampling draws the
+    uniforms with torch's generator (training), otherwise u = linspace(0, 1, n_pts_per_ray)."""
+
+    def __init__(self, n_pts_per_ray: int, random_sampling: bool, add_input_samples: bool = True):
+        self.n_pts_per_ray, self.random_sampling, self.add_input_samples = n_pts_per_ray, random_sampling, add_input_samples
+
+    @torch.no_grad()
+    def __call__(self, input_ray_bundle: ImplicitronRayBundle, ray_weights: torch.Tensor, **kwargs) -> ImplicitronRayBundle:
+        z = input_ray_bundle.lengths
+        spatial = z.shape[:-1]
+        S = z.shape[-1]
+        n = int(torch.Size(spatial).numel())
+        u = None
+        if self.random_sampling:
+            u = torch.rand(n, self.n_pts_per_ray, device=z.device)
+        new = ops.ray_refine(z.reshape(n, S).contiguous().float(), ray_weights.reshape(n, S).contiguous().float(),
+                             self.n_pts_per_ray, self.add_input_samples, u)
+        return ImplicitronRayBundle(input_ray_bundle.origins, input_ray_bundle.directions, new.view(*spatial, -1),
+                                    input_ray_bundle.xys, input_ray_bundle.camera_ids, input_ray_bundle.camera_counts)
 
 
 class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
@@ -142,41 +267,50 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
                  stratified_sampling_coarse_training: bool = True, stratified_sampling_coarse_evaluation: bool = False,
                  append_coarse_samples_to_fine: bool = True, density_noise_std_train: float = 1.0,
                  return_weights: bool = False, raymarcher_class_type: str = "EmissionAbsorptionRaymarcher",
-                 raymarcher_EmissionAbsorptionRaymarcher_args: Optional[dict] = None, use_tensor_cores: bool = True):
+                 raymarcher_EmissionAbsorptionRaymarcher_args: Optional[dict] = None, use_tensor_cores: bool = True,
+                 fused: bool = True):
         super().__init__()
-        self.use_tensor_cores = use_tensor_cores
+        self.use_tensor_cores, self.fused = use_tensor_cores, fused
         if raymarcher_class_type != "EmissionAbsorptionRaymarcher":
-            raise NotImplementedError("only EmissionAbsorptionRaymarcher is fused")
-        rm = dict(surface_thickness=1, bg_color=(0.0,), replicate_last_interval=False, background_opacity=1e10,
-                  density_relu=True, blend_output=False)
-        rm.update(raymarcher_EmissionAbsorptionRaymarcher_args or {})
-        if rm["surface_thickness"] != 1 or rm["replicate_last_interval"] or not rm["density_relu"] or rm["blend_output"]:
-            raise NotImplementedError("fused ray marcher covers the shipped settings (configs/base.yaml:150-159)")
-        bg = tuple(float(x) for x in rm["bg_color"])
+            raise NotImplementedError("only EmissionAbsorptionRaymarcher is built")
+        self.raymarcher = EmissionAbsorptionRaymarcher(**(raymarcher_EmissionAbsorptionRaymarcher_args or {}))
+        bg = self.raymarcher.bg_color
         self.bg_color = bg * 3 if len(bg) == 1 else bg
-        self.background_opacity = float(rm["background_opacity"])
+        self.background_opacity = self.raymarcher.background_opacity
         self.n_pts_per_ray_fine_evaluation = n_pts_per_ray_fine_evaluation
         self.n_pts_per_ray_fine_training = n_pts_per_ray_fine_training
+        self.stratified_sampling_coarse_training = stratified_sampling_coarse_training
         self.stratified_sampling_coarse_evaluation = stratified_sampling_coarse_evaluation
         self.append_coarse_samples_to_fine = append_coarse_samples_to_fine
         self.density_noise_std_train = density_noise_std_train
         self.return_weights = return_weights
+        self._refiners = {
+            EvaluationMode.TRAINING: RayPointRefiner(n_pts_per_ray_fine_training, stratified_sampling_coarse_training,
+                                                     append_coarse_samples_to_fine),
+            EvaluationMode.EVALUATION: RayPointRefiner(n_pts_per_ray_fine_evaluation,
+                                                       stratified_sampling_coarse_evaluation,
+                                                       append_coarse_samples_to_fine),
+        }
 
-    def forward(self, ray_bundle: ImplicitronRayBundle, implicit_functions: List[ImplicitFunctionWrapper],
-                evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, **kwargs) -> RendererOutput:
-        if evaluation_mode != EvaluationMode.EVALUATION:
-            raise NotImplementedError("training-mode rendering (density noise, stratified refinement) is a 'next' row")
-        if self.stratified_sampling_coarse_evaluation:
-            raise NotImplementedError("stratified coarse sampling in evaluation")
-        n_passes = len(implicit_functions)
-        if n_passes not in (1, 2):
-            raise NotImplementedError("1 or 2 rendering passes")
+    # ------------------------------------------------------------------ fused path (one launch)
+    def is_fused(self, implicit_functions: List[ImplicitFunctionWrapper], evaluation_mode: EvaluationMode) -> bool:
+        """True when the whole multi-pass render of these plug-ins is covered by the single fused kernel."""
+        if not self.fused or evaluation_mode != EvaluationMode.EVALUATION or self.stratified_sampling_coarse_evaluation:
+            return False
+        if len(implicit_functions) not in (1, 2) or type(self.raymarcher) is not EmissionAbsorptionRaymarcher:
+            return False
         w = implicit_functions[0]
-        if any(f is not w for f in implicit_functions):
-            raise NotImplementedError("all passes must share one implicit function (holo_diffusion_model.py:165-169)")
+        if not isinstance(w, ImplicitFunctionWrapper) or any(f is not w for f in implicit_functions):
+            return False
         fn = w._fn
-        if not isinstance(fn, HoloVoxelGridImplicitFunction):
-            raise NotImplementedError("fused renderer needs HoloVoxelGridImplicitFunction")
+        if type(fn) is not HoloVoxelGridImplicitFunction or fn.render_normals or fn.render_mlp.head() is not None:
+            return False
+        return "voxel_grid_features" in w.bound_args or "voxel_grid_features_channels_last" in w.bound_args
+
+    def _forward_fused(self, ray_bundle: ImplicitronRayBundle, implicit_functions) -> RendererOutput:
+        n_passes = len(implicit_functions)
+        w = implicit_functions[0]
+        fn = w._fn
         grid = w.bound_args.get("voxel_grid_features")
         grid_cl = w.bound_args.get("voxel_grid_features_channels_last")
         if grid_cl is None:
@@ -202,3 +336,33 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
 
         prev = wrap(out["prev"], None) if out["prev"] is not None else None
         return wrap(out, prev)
+
+    # ------------------------------------------------------------------ staged path (the reference's recursion)
+    def _run_raymarcher(self, ray_bundle, implicit_functions, prev_stage, evaluation_mode, pass_number=0):
+        """holo_multipass_ea.py:79-125, stage by stage on the per-stage kernels."""
+        density_noise_std = self.density_noise_std_train if evaluation_mode == EvaluationMode.TRAINING else 0.0
+        if_output = implicit_functions[0](ray_bundle=ray_bundle, pass_number=pass_number)
+        output = self.raymarcher(*if_output, ray_lengths=ray_bundle.lengths, density_noise_std=density_noise_std)
+        output.prev_stage = prev_stage
+        weights = output.weights
+        if "rendered_normals" in output.aux:
+            output.normals = output.aux.pop("rendered_normals")
+        elif "normals" in output.aux:  # a foreign ray marcher that passed the per-point normals through
+            output.normals = (output.aux.pop("normals") * weights[..., None]).sum(dim=-2)
+        output.aux["lengths"] = ray_bundle.lengths
+        if not self.return_weights:
+            output.weights = None
+        if len(implicit_functions) > 1:
+            fine_ray_bundle = self._refiners[evaluation_mode](ray_bundle, weights)
+            output = self._run_raymarcher(fine_ray_bundle, implicit_functions[1:], output, evaluation_mode,
+                                          pass_number=pass_number + 1)
+        return output
+
+    @torch.no_grad()
+    def forward(self, ray_bundle: ImplicitronRayBundle, implicit_functions: List[ImplicitFunctionWrapper],
+                evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, **kwargs) -> RendererOutput:
+        if not implicit_functions:
+            raise ValueError("EA renderer expects implicit functions")
+        if self.is_fused(implicit_functions, evaluation_mode):
+            return self._forward_fused(ray_bundle, implicit_functions)
+        return self._run_raymarcher(ray_bundle, list(implicit_functions), None, evaluation_mode)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 107
+#define HOLO_B200_VERSION 108
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -84,6 +84,40 @@ int holo_render_fwd_tc(const float* grid_dhwc, int D, int H, int W, int C, float
                        float background_opacity, float* features, float* depths, float* masks, float* weights,
                        float* lengths_out, float* prev_features, float* prev_depths, float* prev_masks,
                        float* prev_weights, float* scratch_weights, void* stream);
+
+/* Per-stage renderer ops: the reference's plug-in seams as separately callable kernels.  The fused launches above
+ * are the hot path; these carry `render_normals`, the view-independent feature head, explicit `pts_3d`,
+ * training-mode density noise / stratified refinement and user-supplied stages in between.
+ *
+ * holo_if_fwd replaces HoloVoxelGridImplicitFunction.forward (holo_voxel_grid_implicit_function.py:182-269):
+ * points = origins + lengths * dirs over (n_rays, S) -- or explicit pts_3d (n_points, 3), in which case dirs may be
+ * NULL (dummy all-ones directions, :228-236) -- trilinear sample, RenderMLP; n_points = n_rays * S.
+ * head_w (n_head, hidden) / head_b: the single-layer view-independent feature net (:94-105), n_head in 0..64.
+ * densities (n_points), features (n_points, 3 + n_head) = [rgb | head]; normals (n_points, 3) or NULL =
+ * RenderMLP.get_normals (:131-145), computed analytically (the density net is affine in the sampled feature). */
+int holo_if_fwd(const float* grid_dhwc, int D, int H, int W, int C, float volume_extent, const float* packed_mlp,
+                int hidden, int n_harmonic, const float* head_w, const float* head_b, int n_head,
+                const float* origins, const float* dirs, const float* lengths, const float* pts_3d,
+                long long n_points, int S, float* densities, float* features, float* normals, void* stream);
+/* RenderMLP.forward(features, view_dirs) (holo_voxel_grid_implicit_function.py:107-129): feats (n_points, C),
+ * view_dirs (n_points, 3) used as given. */
+int holo_render_mlp_fwd(const float* feats, const float* view_dirs, long long n_points, int C,
+                        const float* packed_mlp, int hidden, int n_harmonic, const float* head_w,
+                        const float* head_b, int n_head, float* densities, float* features, void* stream);
+/* EmissionAbsorptionRaymarcher.forward (pytorch3d 0.7.4; configs/base.yaml:149-159; invoked
+ * holo_multipass_ea.py:96-100) for surface_thickness 1, replicate_last_interval False, density_relu True,
+ * blend_output False.  densities (n_rays,S), features (n_rays,S,feat_dim), lengths (n_rays,S); density_noise
+ * (n_rays,S) or NULL is added before the relu (density_noise_std * randn drawn by the caller, :87-91);
+ * normals (n_rays,S,3) or NULL -> out_normals (n_rays,3) = sum_s w n (:104-109).  bg_host: n_bg = 1 or feat_dim. */
+int holo_ea_raymarch(const float* densities, const float* features, const float* lengths,
+                     const float* density_noise, const float* normals, int n_rays, int S, int feat_dim,
+                     const float* bg_host, int n_bg, float background_opacity, float* out_features,
+                     float* out_depths, float* out_masks, float* out_weights, float* out_normals, void* stream);
+/* RayPointRefiner.forward + sample_pdf (pytorch3d 0.7.4; configs/base.yaml:142-146; invoked
+ * holo_multipass_ea.py:115-116).  u (n_rays, n_fine) caller-drawn uniforms (training, stratified) or NULL =
+ * linspace(0, 1, n_fine) (evaluation).  lengths_out (n_rays, S + n_fine) sorted (n_fine if !add_input_samples). */
+int holo_ray_refine(const float* lengths, const float* weights, const float* u, int n_rays, int S, int n_fine,
+                    int add_input_samples, float* lengths_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Denoiser (guided_diffusion UNetModel, unet.py:566-837) building blocks

@@ -190,14 +190,9 @@ def leaky(x):
     return F.leaky_relu(x, 0.2)
 
 
-def render_mlp(params: Dict[str, torch.Tensor], feats: torch.Tensor, dirs: torch.Tensor, dir_emb: int = 4):
-    """RenderMLP.forward (holo_voxel_grid_implicit_function.py:107-129) over MLPWithInputSkips
-    (custom_modules.py:91-113,133-160): the hidden activation lands on the LAST layer only, every
-    earlier layer gets the (Identity) last activation; skip concat cat((y, z)) at layer 2.
-
-    params keys follow the reference state dict: ``_density_net.mlp.{i}.0.{weight,bias}``,
-    ``_radiance_net.mlp.0.0.{weight,bias}``.  feats (P,C), dirs (P,3) already normalised.
-    Returns densities (P,1), rgb (P,3)."""
+def density_net(params: Dict[str, torch.Tensor], feats: torch.Tensor) -> torch.Tensor:
+    """MLPWithInputSkips.forward (custom_modules.py:133-160) for RenderMLP._density_net: the hidden activation
+    lands on the LAST layer only (:108-112), skip concat cat((y, z)) at layer 2.  Returns (P, hidden + 1)."""
     n_layers = 1 + max(int(k.split(".")[2]) for k in params if k.startswith("_density_net.mlp."))
     skips = (2,)
     y = feats
@@ -207,21 +202,58 @@ def render_mlp(params: Dict[str, torch.Tensor], feats: torch.Tensor, dirs: torch
         y = F.linear(y, params[f"_density_net.mlp.{li}.0.weight"], params[f"_density_net.mlp.{li}.0.bias"])
         if li == n_layers - 1:
             y = leaky(y)
+    return y
+
+
+def render_mlp(params: Dict[str, torch.Tensor], feats: torch.Tensor, dirs: torch.Tensor, dir_emb: int = 4,
+               return_head: bool = False):
+    """RenderMLP.forward (holo_voxel_grid_implicit_function.py:107-129).
+
+    params keys follow the reference state dict: ``_density_net.mlp.{i}.0.{weight,bias}``,
+    ``_radiance_net.mlp.0.0.{weight,bias}``, optional ``_feature_net.mlp.0.0.{weight,bias}`` (the single-layer
+    view-independent head, :94-105; being the last layer it gets the LeakyReLU).  feats (P,C), dirs (P,3) used as
+    given.  Returns densities (P,1), rgb (P,3) [, head features (P,F) or None]."""
+    y = density_net(params, feats)
     mlp_feats, dens = y[..., :-1], y[..., -1:]
     pe = harmonic_embedding(dirs, dir_emb)
     r = F.linear(torch.cat([mlp_feats, pe], -1), params["_radiance_net.mlp.0.0.weight"],
                  params["_radiance_net.mlp.0.0.bias"])
-    return dens, torch.sigmoid(leaky(r))
+    rgb = torch.sigmoid(leaky(r))
+    if not return_head:
+        return dens, rgb
+    head = None
+    if "_feature_net.mlp.0.0.weight" in params:
+        head = leaky(F.linear(mlp_feats, params["_feature_net.mlp.0.0.weight"], params["_feature_net.mlp.0.0.bias"]))
+    return dens, rgb, head
 
 
-def implicit_function(params, grid, bundle: OracleRayBundle, resol: int, extent: float):
-    """HoloVoxelGridImplicitFunction.forward: returns densities (...,S,1), features (...,S,3)."""
-    pts = ray_points(bundle)
+def density_normals(params, grid, pts: torch.Tensor, resol: int, extent: float) -> torch.Tensor:
+    """RenderMLP.get_normals (holo_voxel_grid_implicit_function.py:131-145): normalize(d density / d point) with
+    autograd through grid_sample and the density net."""
+    with torch.enable_grad():
+        x = pts.clone()
+        x.requires_grad = True
+        f = sample_grid(grid, world_to_local(x.reshape(-1, 3), resol, extent))
+        y = density_net(params, f)[..., -1:].sum()
+        g = torch.autograd.grad(y, x)[0]
+    return F.normalize(g, dim=-1)
+
+
+def implicit_function(params, grid, bundle: Optional[OracleRayBundle], resol: int, extent: float,
+                      render_normals: bool = False, pts_3d: Optional[torch.Tensor] = None):
+    """HoloVoxelGridImplicitFunction.forward: returns densities (...,S,1), features (...,S,3[+F])
+    [, normals (...,S,3) when render_normals]."""
+    pts = ray_points(bundle) if pts_3d is None else pts_3d
     sp = pts.shape[:-1]
     f = sample_grid(grid, world_to_local(pts.reshape(-1, 3), resol, extent))
-    d = F.normalize(bundle.directions, dim=-1)[..., None, :].expand(*sp, 3).reshape(-1, 3)
-    dens, rgb = render_mlp(params, f, d)
-    return dens.reshape(*sp, 1), rgb.reshape(*sp, 3)
+    dirs = bundle.directions if bundle is not None else torch.ones(*sp[:-1], 3, dtype=pts.dtype)
+    d = F.normalize(dirs, dim=-1)[..., None, :].expand(*sp, 3).reshape(-1, 3)
+    dens, rgb, head = render_mlp(params, f, d, return_head=True)
+    feats = rgb if head is None else torch.cat([rgb, head], -1)
+    out = dens.reshape(*sp, 1), feats.reshape(*sp, -1)
+    if render_normals:
+        return out + (density_normals(params, grid, pts, resol, extent),)
+    return out
 
 
 # ----------------------------------------------------------------------------------------
@@ -236,6 +268,7 @@ class OracleRenderOut:
     weights: Optional[torch.Tensor] = None
     prev_stage: Optional["OracleRenderOut"] = None
     lengths: Optional[torch.Tensor] = None
+    normals: Optional[torch.Tensor] = None
 
 
 def ea_raymarch(dens, feats, lengths, bg=(1.0, 1.0, 1.0), background_opacity=1e10, noise=None) -> OracleRenderOut:
@@ -292,17 +325,23 @@ def refine_lengths(lengths, weights, n_fine: int, add_input=True, u=None):
 
 
 def render_multipass(params, grid, bundle: OracleRayBundle, resol: int, extent: float, n_passes: int = 2,
-                     n_fine: int = 16, bg=(1.0, 1.0, 1.0)) -> OracleRenderOut:
-    """HoloMultiPassEmissionAbsorptionRenderer._run_raymarcher (holo_multipass_ea.py:79-125), eval mode."""
+                     n_fine: int = 16, bg=(1.0, 1.0, 1.0), render_normals: bool = False, noise=None,
+                     u=None) -> OracleRenderOut:
+    """HoloMultiPassEmissionAbsorptionRenderer._run_raymarcher (holo_multipass_ea.py:79-125).
+    Evaluation mode by default; training mode = ``noise`` (list per pass of density_noise_std * randn, :87-91)
+    and ``u`` (stratified refinement uniforms) supplied by the caller."""
     prev = None
     b = bundle
     for p in range(n_passes):
-        dens, feats = implicit_function(params, grid, b, resol, extent)
-        out = ea_raymarch(dens, feats, b.lengths, bg)
+        o = implicit_function(params, grid, b, resol, extent, render_normals=render_normals)
+        dens, feats = o[0], o[1]
+        out = ea_raymarch(dens, feats, b.lengths, bg, noise=None if noise is None else noise[p])
+        if render_normals:
+            out.normals = (o[2] * out.weights[..., None]).sum(-2)  # holo_multipass_ea.py:104-109
         out.prev_stage = prev
         prev = out
         if p + 1 < n_passes:
-            b = OracleRayBundle(b.origins, b.directions, refine_lengths(b.lengths, out.weights, n_fine), b.xys)
+            b = OracleRayBundle(b.origins, b.directions, refine_lengths(b.lengths, out.weights, n_fine, u=u), b.xys)
     return out
 
 
