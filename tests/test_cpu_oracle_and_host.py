@@ -107,7 +107,7 @@ def test_abi_exports_every_declared_symbol():
     for name in protos:
         assert hasattr(cdll, name), f"libholo_b200.so does not export {name}"
     L = _lib.lib()
-    assert L.cdll.holo_version() == 107
+    assert L.cdll.holo_version() == L._header_version()
     assert L.cdll.holo_render_mlp_packed_floats(256, 32, 27) == (257 * 32 + 4 * 256 + 4 + 81 + 3 + 3) // 4 * 4
 
 
