@@ -508,6 +508,56 @@ extern "C" int holo_ddpm_step(const float* model_out, const float* x_t, const fl
     return HOLO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// DDIM step (gaussian_diffusion.py:645-693) and its reverse ODE (:695-731) for a START_X model:
+//   x0 = clamp(model_out);  eps = (sqrt_recip_ac[t] x_t - x0) / sqrt_recipm1_ac[t]
+//   sigma = eta sqrt((1 - ab_to) / (1 - ab)) sqrt(1 - ab / ab_to)          (ab_to = alphas_cumprod_prev[t])
+//   x_{t-1} = x0 sqrt(ab_to) + sqrt(1 - ab_to - sigma^2) eps + [t != 0] sigma noise
+// reverse: ab_to = alphas_cumprod_next[t], sigma = 0, no noise.
+// ------------------------------------------------------------------------------------------------
+__global__ void ddim_step_kernel(const float* __restrict__ model_out, const float* __restrict__ x_t,
+                                 const float* __restrict__ noise, const long long* __restrict__ t,
+                                 const float* __restrict__ ac, const float* __restrict__ ac_to,
+                                 const float* __restrict__ sqrt_recip, const float* __restrict__ sqrt_recipm1,
+                                 float eta, long long per_sample, int n_batch, int clip,
+                                 float* __restrict__ x_out, float* __restrict__ pred_x0) {
+    long long total = per_sample * n_batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long tt = t[i / per_sample];
+        float ab = ac[tt], abt = ac_to[tt];
+        float sigma = 0.f;
+        if (eta != 0.f) sigma = eta * sqrtf((1.f - abt) / (1.f - ab)) * sqrtf(1.f - ab / abt);
+        float m = model_out[i];
+        if (clip) m = fminf(fmaxf(m, -1.f), 1.f);
+        float x = x_t[i];
+        float eps = (sqrt_recip[tt] * x - m) / sqrt_recipm1[tt];
+        float r = m * sqrtf(abt) + sqrtf(1.f - abt - sigma * sigma) * eps;
+        if (noise && tt != 0) r += sigma * noise[i];
+        x_out[i] = r;
+        if (pred_x0) pred_x0[i] = m;
+    }
+}
+
+extern "C" int holo_ddim_step(const float* model_out, const float* x_t, const float* noise, const long long* t_i64,
+                              const float* alphas_cumprod, const float* alphas_cumprod_to,
+                              const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                              float eta, long long per_sample, int n_batch, int clip_denoised, float* x_out,
+                              float* pred_xstart, void* stream) {
+    HOLO_CHECK_ARG(model_out && x_t && t_i64 && alphas_cumprod && alphas_cumprod_to && sqrt_recip_alphas_cumprod &&
+                       sqrt_recipm1_alphas_cumprod && x_out,
+                   "holo_ddim_step: null arg");
+    HOLO_CHECK_ARG(per_sample > 0 && n_batch > 0 && eta >= 0.f, "holo_ddim_step: bad sizes / eta");
+    int blocks = holo_cdiv(per_sample * n_batch, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ddim_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(model_out, x_t, noise, t_i64, alphas_cumprod,
+                                                               alphas_cumprod_to, sqrt_recip_alphas_cumprod,
+                                                               sqrt_recipm1_alphas_cumprod, eta, per_sample, n_batch,
+                                                               clip_denoised, x_out, pred_xstart);
+    HOLO_CHECK_LAUNCH("holo_ddim_step");
+    return HOLO_OK;
+}
+
 // q_sample: x_t = sqrt_ac[t]*x0 + sqrt_1m_ac[t]*eps   (gaussian_diffusion.py:209-227)
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                 const long long* __restrict__ t, const float* __restrict__ sa,

@@ -35,6 +35,11 @@ class ImplicitronGaussianDiffusion:
         ac_prev = np.append(1.0, ac[:-1])
         post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
         self.tables64 = {
+            "alphas_cumprod": ac,
+            "alphas_cumprod_prev": ac_prev,
+            "alphas_cumprod_next": np.append(ac[1:], 0.0),
+            "sqrt_recip_alphas_cumprod": np.sqrt(1.0 / ac),
+            "sqrt_recipm1_alphas_cumprod": np.sqrt(1.0 / ac - 1),
             "sqrt_alphas_cumprod": np.sqrt(ac),
             "sqrt_one_minus_alphas_cumprod": np.sqrt(1.0 - ac),
             "posterior_variance": post_var,
@@ -123,6 +128,60 @@ class ImplicitronGaussianDiffusion:
                                     model_kwargs=model_kwargs, noise_sampler=noise_sampler)
                 yield out
                 img = out["sample"]
+
+    # ------------------------------------------------------------------ DDIM (gaussian_diffusion.py:645-815)
+    def ddim_sample(self, model: Callable, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                    eta=0.0):
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn")
+        model_out = model(x, t, **(model_kwargs or {}))
+        noise = torch.randn_like(x)  # drawn whatever eta is, as the reference does (:682)
+        tab = self._tables(x.device)
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        ops.ddim_step(model_out.contiguous(), x.contiguous(), noise, t.contiguous(), tab["alphas_cumprod"],
+                      tab["alphas_cumprod_prev"], tab["sqrt_recip_alphas_cumprod"], tab["sqrt_recipm1_alphas_cumprod"],
+                      eta, clip_denoised, sample, x0)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def ddim_reverse_sample(self, model: Callable, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn")
+        model_out = model(x, t, **(model_kwargs or {}))
+        tab = self._tables(x.device)
+        sample, x0 = torch.empty_like(x), torch.empty_like(x)
+        ops.ddim_step(model_out.contiguous(), x.contiguous(), None, t.contiguous(), tab["alphas_cumprod"],
+                      tab["alphas_cumprod_next"], tab["sqrt_recip_alphas_cumprod"], tab["sqrt_recipm1_alphas_cumprod"],
+                      0.0, clip_denoised, sample, x0)
+        return {"sample": sample, "pred_xstart": x0}
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0):
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else torch.randn(*shape, device=device)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        for i in indices:
+            t = torch.full((shape[0],), i, device=device, dtype=torch.int64)
+            with torch.no_grad():
+                out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                       cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+                yield out
+                img = out["sample"]
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0):
+        final = None
+        for sample in self.ddim_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
+                                                        denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                                        model_kwargs=model_kwargs, device=device, progress=progress,
+                                                        eta=eta):
+            final = sample
+        return final["sample"]
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, return_all_samples=False, max_iter=None,

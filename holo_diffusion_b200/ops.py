@@ -315,6 +315,13 @@ def ddpm_step(model_out, x_t, noise, t, coef1, coef2, logvar, clip: bool, x_prev
                _ptr(coef2), _ptr(logvar), per, n_batch, 1 if clip else 0, _ptr(x_prev), _ptr(pred_x0), _stream())
 
 
+def ddim_step(model_out, x_t, noise, t, ac, ac_to, sqrt_recip, sqrt_recipm1, eta: float, clip: bool, x_out, pred_x0=None):
+    n_batch = t.numel()
+    lib().call("holo_ddim_step", _ptr(model_out), _ptr(x_t), _ptr(noise), _ptr(t, torch.int64), _ptr(ac), _ptr(ac_to),
+               _ptr(sqrt_recip), _ptr(sqrt_recipm1), float(eta), model_out.numel() // n_batch, n_batch, 1 if clip else 0,
+               _ptr(x_out), _ptr(pred_x0), _stream())
+
+
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1m_ac, out):
     n_batch = t.numel()
     lib().call("holo_q_sample", _ptr(x0), _ptr(noise), _ptr(t, torch.int64), _ptr(sqrt_ac), _ptr(sqrt_1m_ac),

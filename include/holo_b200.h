@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 108
+#define HOLO_B200_VERSION 109
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -208,6 +208,14 @@ int holo_linear_rows(const float* x, const float* W, const float* b, int M, int 
 int holo_ddpm_step(const float* model_out, const float* x_t, const float* noise, const long long* t_i64,
                    const float* coef1, const float* coef2, const float* logvar, long long per_sample, int n_batch,
                    int clip_denoised, float* x_prev, float* pred_xstart, void* stream);
+/* ddim_sample -- gaussian_diffusion.py:645-693 -- and ddim_reverse_sample -- :695-731 -- for a START_X model.
+ * alphas_cumprod_to = alphas_cumprod_prev (forward; noise (may be NULL) scaled by sigma(eta)) or alphas_cumprod_next
+ * (reverse ODE: pass eta = 0, noise = NULL). */
+int holo_ddim_step(const float* model_out, const float* x_t, const float* noise, const long long* t_i64,
+                   const float* alphas_cumprod, const float* alphas_cumprod_to,
+                   const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod, float eta,
+                   long long per_sample, int n_batch, int clip_denoised, float* x_out, float* pred_xstart,
+                   void* stream);
 /* q_sample -- gaussian_diffusion.py:209-227. */
 int holo_q_sample(const float* x0, const float* noise, const long long* t_i64, const float* sqrt_ac,
                   const float* sqrt_1m_ac, long long per_sample, int n_batch, float* out, void* stream);

@@ -6,6 +6,8 @@
                            seeded fixtures of ``oracle.unet_oracle.make_unet_state_dict``; pins oracle + CUDA path.
 * ``unet_keys.json``    -- the reference module's state-dict keys and shapes (checkpoint compatibility).
 * ``diffusion_ref.npz`` -- the reference ``GaussianDiffusion`` tables and p_sample / q_sample outputs.
+* ``ddim_ref.npz``      -- the reference ``GaussianDiffusion.ddim_sample`` (eta 0 and 0.5) / ``ddim_reverse_sample``
+                           outputs (``python tests/golden/make_golden.py --only-ddim`` writes just this file).
 * ``render_golden.npz`` -- outputs of ``oracle.render_oracle`` on a tiny scene (regression pin of the restatement;
                            the renderer has no reference-side vectors: parity unpinned, see oracle/__init__.py).
 """
@@ -48,7 +50,37 @@ def ref_unet(c):
     return net.eval(), sd
 
 
+def _ref_diffusion():
+    return GaussianDiffusion(betas=get_named_beta_schedule("linear", 1000, 0.0001, 0.02), model_mean_type=ModelMeanType.START_X,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE, rescale_timesteps=False)
+
+
+def make_ddim():
+    gd = _ref_diffusion()
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(3, 4, 4, 4, 4, generator=g)
+    model = lambda z, t: torch.tanh(1.7 * z) * 1.3  # noqa: E731  (exercises the clamp)
+    t = torch.tensor([0, 412, 999])
+    d = dict(x=x.numpy(), t=t.numpy())
+    for k in ("alphas_cumprod", "alphas_cumprod_prev", "alphas_cumprod_next", "sqrt_recip_alphas_cumprod",
+              "sqrt_recipm1_alphas_cumprod"):
+        d[k] = getattr(gd, k)
+    for eta in (0.0, 0.5):
+        torch.manual_seed(123)  # ddim_sample draws th.randn_like(x) from the global generator
+        r = gd.ddim_sample(model, x, t, clip_denoised=True, eta=eta)
+        d[f"ddim_eta{eta}"] = r["sample"].numpy()
+    torch.manual_seed(123)
+    d["noise"] = torch.randn_like(x).numpy()
+    r = gd.ddim_reverse_sample(model, x, t, clip_denoised=True)
+    d["ddim_reverse"] = r["sample"].numpy()
+    d["pred_xstart"] = r["pred_xstart"].numpy()
+    np.savez_compressed(os.path.join(HERE, "ddim_ref.npz"), **d)
+
+
 def main():
+    make_ddim()
+    if "--only-ddim" in sys.argv:
+        return
     out = {}
     keys = {}
     for name, c in CASES.items():

@@ -41,14 +41,23 @@ def test_unet_oracle_matches_reference_vectors(name, t):
 
 def test_diffusion_oracle_matches_reference_vectors():
     g = np.load(os.path.join(GOLD, "diffusion_ref.npz"))
+    g2 = np.load(os.path.join(GOLD, "ddim_ref.npz"))
     tab = do.schedule_tables()
     for k in tab:
-        assert np.array_equal(tab[k], g[k]), k  # fp64 tables, bit-exact
+        assert np.array_equal(tab[k], g[k] if k in g else g2[k]), k  # fp64 tables, bit-exact
     x, noise, t = torch.from_numpy(g["x"]), torch.from_numpy(g["noise"]), torch.from_numpy(g["t"])
     out = do.p_sample(tab, lambda z, tt: torch.tanh(1.7 * z) * 1.3, x, t, noise)
     assert torch.equal(out["sample"], torch.from_numpy(g["p_sample"]))
     assert torch.equal(out["pred_xstart"], torch.from_numpy(g["pred_xstart"]))
     assert torch.equal(do.q_sample(tab, x, t, noise), torch.from_numpy(g["q_sample"]))
+    # DDIM (forward eta 0 / 0.5, reverse ODE) against the reference's ddim_sample / ddim_reverse_sample
+    x, noise, t = torch.from_numpy(g2["x"]), torch.from_numpy(g2["noise"]), torch.from_numpy(g2["t"])
+    model = lambda z, tt: torch.tanh(1.7 * z) * 1.3  # noqa: E731
+    for eta in (0.0, 0.5):
+        assert torch.equal(do.ddim_sample(tab, model, x, t, noise, eta=eta)["sample"], torch.from_numpy(g2[f"ddim_eta{eta}"]))
+    rev = do.ddim_sample(tab, model, x, t, noise, reverse=True)
+    assert torch.equal(rev["sample"], torch.from_numpy(g2["ddim_reverse"]))
+    assert torch.equal(rev["pred_xstart"], torch.from_numpy(g2["pred_xstart"]))
 
 
 def test_render_oracle_regression_and_properties():
