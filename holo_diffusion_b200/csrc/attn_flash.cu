@@ -1,0 +1,494 @@
+// Fused (flash-style) QKVAttention over voxel tokens on tcgen05 for sm_100a: the T x T logits never leave the SM.
+//
+// Reference op replaced: QKVAttentionLegacy.forward -- /root/reference/holo_diffusion/guided_diffusion/unet.py:438-455
+//   qkv (B*H, 3*ch, T) -> q, k, v;  w = softmax((q s)^T (k s));  a = w v,   s = ch^-1/4.
+//
+// One CTA = 128 queries of one head.  Keys/values stream through shared memory in 64-key tiles (TMA, SWIZZLE_128B):
+//   S = Q K^T        tcgen05.mma kind::f16, 3xBF16 split (hi.hi + hi.lo + lo.hi), fp32 accumulator in TMEM (double-buffered)
+//   P = exp2(s^2 log2e (S - rowmax))  fp32 in registers, written back to shared memory as a bf16 hi/lo A operand
+//   O += P V         tcgen05.mma, 3xBF16 split, fp32 accumulator in TMEM across all key tiles
+// The softmax is EXACT two-pass rather than online: pass A streams K only and reduces the row maxima, pass B
+// recomputes S, exponentiates against the final maximum and accumulates O with no rescaling of the TMEM
+// accumulator (1.5x the tensor work of one pass; the tensor pipe is not what bounds this kernel at T <= 4096).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = softmax + epilogue
+// (thread <-> query row <-> TMEM lane).
+#include "common.cuh"
+#include "../../include/holo_b200.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int BM = 128;  // queries per CTA (UMMA M)
+constexpr int BN = 64;   // keys per tile = one 128-byte swizzle row of P
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 256;  // S0 [0,64) | S1 [64,128) | O [128, 128+ch)
+constexpr int O_COL = 128;
+
+template <int CH>
+struct FCfg {
+    static constexpr int SLABS = CH / 64;
+    static constexpr int Q_HALF = SLABS * BM * 128;  // bytes of q_hi (then q_lo)
+    static constexpr int K_HALF = SLABS * BN * 128;
+    static constexpr int V_HALF = CH * 128;
+    static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = 2 * V_HALF;
+    static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+    static constexpr int STAGES = CH == 64 ? 3 : 2;
+    static constexpr int P_HALF = BM * 128;
+    static constexpr int P_BYTES = 2 * P_HALF;
+    static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers (same conventions as conv_tc.cu)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 B apart (see conv_tc.cu)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+}
+
+struct FlashParams {
+    int T, C, heads;
+    float scale_log2;  // ch^-1/2 * log2(e): logits are (q s).(k s) = s^2 q.k
+    float* out;        // (T, C) fp32 or null
+    __nv_bfloat16* out_hi;  // (T, C) bf16 hi/lo split of the result, or null
+    __nv_bfloat16* out_lo;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                  const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
+                  const __grid_constant__ CUtensorMap map_v_hi, const __grid_constant__ CUtensorMap map_v_lo,
+                  FlashParams P) {
+    using F = FCfg<CH>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* q_smem = smem;                                   // [q_hi slabs | q_lo slabs]
+    uint8_t* kv_smem = smem + F::Q_BYTES;                     // STAGES x [k_hi | k_lo | v_hi | v_lo]
+    uint8_t* p_smem = kv_smem + F::STAGES * F::STAGE_BYTES;   // [p_hi | p_lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + F::P_BYTES);
+    uint64_t* kv_full = bars;                     // [STAGES]
+    uint64_t* kv_empty = kv_full + F::STAGES;     // [STAGES]
+    uint64_t* s_full = kv_empty + F::STAGES;      // [2]
+    uint64_t* s_empty = s_full + 2;               // [2]
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* p_empty = p_full + 1;
+    uint64_t* q_full = p_empty + 1;
+    uint64_t* o_full = q_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.x * BM;
+    const int head = blockIdx.y;
+    const int NT = P.T / BN;        // key tiles per pass
+    const int n_jobs = 2 * NT;      // S jobs: pass A (max) then pass B (exp + PV)
+    const int col_q = head * 3 * CH, col_k = col_q + CH;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v_lo) : "memory");
+        for (int s = 0; s < F::STAGES; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&s_full[b], 1), mbar_init(&s_empty[b], 4);
+        mbar_init(p_full, 128);
+        mbar_init(p_empty, 1);
+        mbar_init(q_full, 1);
+        mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            mbar_expect_tx(q_full, (uint32_t)F::Q_BYTES);
+#pragma unroll
+            for (int sl = 0; sl < F::SLABS; ++sl) {
+                tma_load_2d(q_smem + sl * (BM * 128), &map_q_hi, q_full, col_q + sl * 64, m0);
+                tma_load_2d(q_smem + F::Q_HALF + sl * (BM * 128), &map_q_lo, q_full, col_q + sl * 64, m0);
+            }
+            for (int j = 0; j < n_jobs; ++j) {
+                const int stage = j % F::STAGES;
+                const uint32_t phase = (uint32_t)(j / F::STAGES) & 1u;
+                const bool with_v = j >= NT;
+                const int n0 = (with_v ? j - NT : j) * BN;
+                mbar_wait(&kv_empty[stage], phase ^ 1u);
+                uint8_t* st = kv_smem + stage * F::STAGE_BYTES;
+                mbar_expect_tx(&kv_full[stage], (uint32_t)(F::K_BYTES + (with_v ? F::V_BYTES : 0)));
+#pragma unroll
+                for (int sl = 0; sl < F::SLABS; ++sl) {
+                    tma_load_2d(st + sl * (BN * 128), &map_k_hi, &kv_full[stage], col_k + sl * 64, n0);
+                    tma_load_2d(st + F::K_HALF + sl * (BN * 128), &map_k_lo, &kv_full[stage], col_k + sl * 64, n0);
+                }
+                if (with_v) {
+                    tma_load_2d(st + F::K_BYTES, &map_v_hi, &kv_full[stage], n0, head * CH);
+                    tma_load_2d(st + F::K_BYTES + F::V_HALF, &map_v_lo, &kv_full[stage], n0, head * CH);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc_s = idesc_bf16(BN);
+        constexpr uint32_t idesc_o = idesc_bf16(CH);
+        const uint32_t q_base = smem_u32(q_smem);
+        const uint32_t p_base = smem_u32(p_smem);
+        // S job j: wait for its K tile and for the softmax warps to have drained the S buffer, then 3 x SLABS x 4 UMMAs
+        auto issue_s = [&](int j) {
+            const int stage = j % F::STAGES;
+            const int b = j & 1;
+            mbar_wait(&kv_full[stage], (uint32_t)(j / F::STAGES) & 1u);
+            mbar_wait(&s_empty[b], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+                const uint32_t k_base = smem_u32(kv_smem + stage * F::STAGE_BYTES);
+#pragma unroll
+                for (int sl = 0; sl < F::SLABS; ++sl)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t a_hi = q_base + sl * (BM * 128) + k * 32, a_lo = a_hi + F::Q_HALF;
+                        const uint32_t b_hi = k_base + sl * (BN * 128) + k * 32, b_lo = b_hi + F::K_HALF;
+                        const uint64_t dah = sw128_desc(a_hi), dbh = sw128_desc(b_hi);
+                        umma(d, dah, dbh, idesc_s, (sl | k) != 0);
+                        umma(d, dah, sw128_desc(b_lo), idesc_s, 1);
+                        umma(d, sw128_desc(a_lo), dbh, idesc_s, 1);
+                    }
+                umma_commit(&s_full[b]);
+                if (j < NT) umma_commit(&kv_empty[stage]);  // pass A: the stage holds K only, free it now
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        for (int j = 0; j < NT; ++j) issue_s(j);  // pass A
+        issue_s(NT);                               // pass B prologue
+        for (int i = 0; i < NT; ++i) {
+            const int j = NT + i;
+            if (i + 1 < NT) issue_s(j + 1);        // S of the next tile overlaps the softmax of this one
+            const int stage = j % F::STAGES;
+            mbar_wait(p_full, (uint32_t)i & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + O_COL;
+                const uint32_t v_base = smem_u32(kv_smem + stage * F::STAGE_BYTES + F::K_BYTES);
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k) {
+                    const uint32_t a_hi = p_base + k * 32, a_lo = a_hi + F::P_HALF;
+                    const uint32_t b_hi = v_base + k * 32, b_lo = b_hi + F::V_HALF;
+                    const uint64_t dah = sw128_desc(a_hi), dbh = sw128_desc(b_hi);
+                    umma(d, dah, dbh, idesc_o, (i | k) != 0);
+                    umma(d, dah, sw128_desc(b_lo), idesc_o, 1);
+                    umma(d, sw128_desc(a_lo), dbh, idesc_o, 1);
+                }
+                umma_commit(p_empty);
+                umma_commit(&kv_empty[stage]);
+                if (i == NT - 1) umma_commit(o_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= softmax + epilogue =================
+        const int q = warp % 4;             // TMEM lane quarter of this warp
+        const int row = q * 32 + lane;      // query row of the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float mx = -INFINITY;
+        uint32_t v[32];
+        // ---- pass A: row maxima of the raw logits
+        for (int j = 0; j < NT; ++j) {
+            const int b = j & 1;
+            mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tmem_ld32(lane_addr + (uint32_t)(b * BN + h * 32), v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
+        }
+        // ---- pass B: P = exp2(scale (S - max)), row sums, P -> shared memory as the bf16 hi/lo A operand of P V
+        const float msc = mx * P.scale_log2;
+        float l0 = 0.f, l1 = 0.f;
+        uint8_t* prow_hi = p_smem + (size_t)(row / 8) * 1024 + (row % 8) * 128;
+        uint8_t* prow_lo = prow_hi + F::P_HALF;
+        const int swz = row % 8;
+        for (int i = 0; i < NT; ++i) {
+            const int j = NT + i;
+            const int b = j & 1;
+            mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            uint32_t hi[32], lo[32];  // 64 keys = 32 bf16x2 each
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tmem_ld32(lane_addr + (uint32_t)(b * BN + h * 32), v);
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = exp2f(fmaf(__uint_as_float(v[c]), P.scale_log2, -msc));
+                    const float p1 = exp2f(fmaf(__uint_as_float(v[c + 1]), P.scale_log2, -msc));
+                    l0 += p0, l1 += p1;
+                    split2(p0, p1, hi[h * 16 + c / 2], lo[h * 16 + c / 2]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);      // S buffer drained (values live in registers now)
+            mbar_wait(p_empty, ((uint32_t)i & 1u) ^ 1u);  // P V of the previous tile has consumed the P buffer
+#pragma unroll
+            for (int ck = 0; ck < 8; ++ck) {               // 16-byte chunk ck = keys 8 ck .. 8 ck + 7
+                const int off = (ck ^ swz) * 16;
+                *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[ck * 4], hi[ck * 4 + 1], hi[ck * 4 + 2], hi[ck * 4 + 3]);
+                *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[ck * 4], lo[ck * 4 + 1], lo[ck * 4 + 2], lo[ck * 4 + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA (async proxy)
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / rowsum -> global (fp32 and / or the bf16 hi/lo split the projection conv consumes)
+        const float inv = 1.0f / (l0 + l1);
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const int t = m0 + row;
+        const bool ok = t < P.T;
+        const size_t obase = (size_t)t * P.C + (size_t)head * CH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CH; c0 += 32) {
+            tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
+            if (ok) {
+                float f[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]) * inv;
+                if (P.out) {
+                    float4* op = reinterpret_cast<float4*>(P.out + obase + c0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) op[c4] = make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
+                }
+                if (P.out_hi) {
+                    uint32_t oh[16], ol[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) split2(f[2 * c], f[2 * c + 1], oh[c], ol[c]);
+                    uint4* hp = reinterpret_cast<uint4*>(P.out_hi + obase + c0);
+                    uint4* lp = reinterpret_cast<uint4*>(P.out_lo + obase + c0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        hp[c4] = make_uint4(oh[c4 * 4], oh[c4 * 4 + 1], oh[c4 * 4 + 2], oh[c4 * 4 + 3]);
+                        lp[c4] = make_uint4(ol[c4 * 4], ol[c4 * 4 + 1], ol[c4 * 4 + 2], ol[c4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// V (T, ch) slices of the head-major qkv tensor -> V^T (heads*ch, T) bf16 hi/lo, K-major for the P V product
+__global__ void v_transpose_split_kernel(const float* __restrict__ qkv, int T, int heads, int ch,
+                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int C = heads * ch;
+    const int c0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        float val = 0.f;
+        if (t < T && c < C) val = qkv[(size_t)t * 3 * C + (size_t)(c / ch) * 3 * ch + 2 * ch + (c % ch)];
+        tile[i][threadIdx.x] = val;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        if (t < T && c < C) {
+            const float val = tile[threadIdx.x][i];
+            const __nv_bfloat16 h = __float2bfloat16_rn(val);
+            hi[(size_t)c * T + t] = h;
+            lo[(size_t)c * T + t] = __float2bfloat16_rn(val - __bfloat162float(h));
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor (rows, cols), row pitch in elements, box (64 cols = 128 B, box_rows), SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long pitch, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int CH>
+int launch_flash(const CUtensorMap* maps, const FlashParams& P, cudaStream_t st) {
+    auto k = attn_flash_kernel<CH>;
+    HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<CH>::SMEM_BYTES),
+              "holo_attention_flash");
+    dim3 grid((unsigned)((P.T + BM - 1) / BM), (unsigned)P.heads);
+    k<<<grid, NTHREADS, FCfg<CH>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
+    HOLO_CHECK_LAUNCH("holo_attention_flash");
+    return HOLO_OK;
+}
+
+}  // namespace
+
+extern "C" int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi_bf16,
+                                      void* vt_lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(qkv_cl && vt_hi_bf16 && vt_lo_bf16 && T > 0 && heads > 0 && ch > 0, "holo_v_transpose_split: bad args");
+    dim3 grid(holo_cdiv((long long)heads * ch, 32), holo_cdiv(T, 32));
+    v_transpose_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(qkv_cl, T, heads, ch, (__nv_bfloat16*)vt_hi_bf16,
+                                                                            (__nv_bfloat16*)vt_lo_bf16);
+    HOLO_CHECK_LAUNCH("holo_v_transpose_split");
+    return HOLO_OK;
+}
+
+extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
+                                    const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
+                                    void* out_lo_bf16, void* stream) {
+    HOLO_CHECK_ARG(qkv_hi_bf16 && qkv_lo_bf16 && vt_hi_bf16 && vt_lo_bf16, "holo_attention_flash: null input");
+    HOLO_CHECK_ARG(out_cl || out_hi_bf16, "holo_attention_flash: no output requested");
+    HOLO_CHECK_ARG((out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr), "holo_attention_flash: hi/lo outputs come together");
+    if (!(ch == 64 || ch == 128) || T < BN || T % BN != 0 || heads < 1) {
+        holo_set_error("holo_attention_flash: unsupported shape T=%d heads=%d ch=%d (ch 64|128, T %% 64 == 0)", T, heads, ch);
+        return HOLO_ERR_UNSUPPORTED;
+    }
+    const int C = heads * ch;
+    CUtensorMap maps[6];
+    int e = make_map(&maps[0], qkv_hi_bf16, T, 3LL * C, 3LL * C, BM);
+    if (!e) e = make_map(&maps[1], qkv_lo_bf16, T, 3LL * C, 3LL * C, BM);
+    if (!e) e = make_map(&maps[2], qkv_hi_bf16, T, 3LL * C, 3LL * C, BN);
+    if (!e) e = make_map(&maps[3], qkv_lo_bf16, T, 3LL * C, 3LL * C, BN);
+    if (!e) e = make_map(&maps[4], vt_hi_bf16, C, T, T, ch);
+    if (!e) e = make_map(&maps[5], vt_lo_bf16, C, T, T, ch);
+    if (e) {
+        holo_set_error("holo_attention_flash: cuTensorMapEncodeTiled failed (%d)", e);
+        return HOLO_ERR_CUDA;
+    }
+    FlashParams P;
+    P.T = T, P.C = C, P.heads = heads;
+    P.scale_log2 = (1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
+    P.out = out_cl, P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
+    cudaStream_t st = (cudaStream_t)stream;
+    return ch == 64 ? launch_flash<64>(maps, P, st) : launch_flash<128>(maps, P, st);
+}

@@ -281,6 +281,21 @@ def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, ou
     return rc
 
 
+def v_transpose_split(qkv, T, heads, ch, vt_hi, vt_lo):
+    lib().call("holo_v_transpose_split", _ptr(qkv), T, heads, ch, _ptr(vt_hi, torch.bfloat16), _ptr(vt_lo, torch.bfloat16),
+               _stream())
+
+
+def attention_flash(qkv_hi, qkv_lo, vt_hi, vt_lo, T, heads, ch, out=None, out_hi=None, out_lo=None) -> int:
+    """Fused attention on tcgen05 (holo_attention_flash).  Returns 0, or -3 for a shape the kernel does not take."""
+    bf = torch.bfloat16
+    rc = lib().try_call("holo_attention_flash", _ptr(qkv_hi, bf), _ptr(qkv_lo, bf), _ptr(vt_hi, bf), _ptr(vt_lo, bf), T,
+                        heads, ch, _ptr(out), _ptr(out_hi, bf), _ptr(out_lo, bf), _stream())
+    if rc not in (0, -3):
+        raise HoloError(f"holo_attention_flash failed ({rc}): {lib().cdll.holo_last_error().decode()}")
+    return rc
+
+
 def attention_simt(qkv, T, heads, ch, out):
     lib().call("holo_attention_simt", _ptr(qkv), T, heads, ch, _ptr(out), _stream())
 

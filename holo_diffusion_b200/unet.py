@@ -11,6 +11,7 @@ that affine, skip-concat consumed in place, nearest-upsample folded into the fol
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -168,6 +169,8 @@ class UNetExecutor:
     def __init__(self, params: UNetParams, use_tensor_cores: bool = True):
         self.p = params
         self.use_tc = use_tensor_cores
+        # HOLO_ATTN_FLASH=0 falls back to the three-launch S / softmax / PV pipeline (A/B measurements)
+        self.use_flash = os.environ.get("HOLO_ATTN_FLASH", "1") != "0"
         self._convs: Dict[int, _PackedConv] = {}
         self._film_version = None
         self._film_w = self._film_b = None
@@ -339,6 +342,19 @@ class UNetExecutor:
         gdims = (T // 32, 4, 8)  # GEMM view of the token axis for the TMA box
         _, y_hi, y_lo = self._gn(flat, blk.norm, None, False, True)
         qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True, want_stats=False)
+        if self.use_flash and ch in (64, 128):
+            # fused attention: one launch for all heads, logits never leave the SM; the result comes back already
+            # split into the bf16 hi/lo pair the projection conv consumes
+            vt_hi = torch.empty(C, T, device=dev, dtype=torch.bfloat16)
+            vt_lo = torch.empty(C, T, device=dev, dtype=torch.bfloat16)
+            ops.v_transpose_split(qkv.x1, T, heads, ch, vt_hi, vt_lo)
+            a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+            a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+            rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, ch, None, a_hi, a_lo)
+            assert rc == 0
+            self.tc_calls += 1
+            out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
+            return _Act(out.x1, C, act.dims, st1=out.st1)
         S = torch.empty(T, T, device=dev)
         P_hi = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
         P_lo = torch.empty(T, T, device=dev, dtype=torch.bfloat16)

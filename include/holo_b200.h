@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 109
+#define HOLO_B200_VERSION 110
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -187,6 +187,18 @@ int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_
                        void* stream);
 int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, int cols, void* hi_bf16,
                               void* lo_bf16, void* stream);
+
+/* Fused (flash-style) QKVAttentionLegacy.forward -- unet.py:438-455 -- on tcgen05: one launch for all heads, the
+ * T x T logits stay in TMEM / shared memory (exact two-pass softmax, 3xBF16 operand splits, fp32 accumulation).
+ * qkv_hi/lo (T, heads*3*ch) bf16 hi/lo of the head-major [q|k|v] tensor (the qkv convolution's split output);
+ * vt_hi/lo (heads*ch, T) bf16 hi/lo of V^T, produced by holo_v_transpose_split from the fp32 qkv tensor.
+ * out_cl (T, heads*ch) fp32 and/or out_hi/lo its bf16 split (what the projection conv consumes); either may be NULL.
+ * ch in {64, 128}, T % 64 == 0; other shapes return HOLO_ERR_UNSUPPORTED (-3). */
+int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi_bf16, void* vt_lo_bf16,
+                           void* stream);
+int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
+                         const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
+                         void* out_lo_bf16, void* stream);
 
 /* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);

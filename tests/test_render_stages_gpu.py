@@ -129,7 +129,7 @@ def test_refiner_matches_oracle(S, n_fine, add, random):
     out = ops.ray_refine(z.cuda(), w.cuda(), n_fine, add, None if u is None else u.cuda())
     assert out.shape == ref32.shape
     assert bool((out[:, 1:] >= out[:, :-1]).all())
-    assert rel_err(out, ref64) < 3 * rel_err(ref32, ref64) + 1e-5
+    assert rel_err(out, ref64) < 3 * rel_err(ref32, ref64) + TOL  # cdf summation order differs from torch.cumsum
 
 
 def _model(C, R, HW, S, n_passes, n_fine, **kw):

@@ -316,6 +316,62 @@ def test_attention_tensor_core_pipeline(T, heads, ch):
     assert rel_err(out.t().cpu()[None], ref) < 5e-5
 
 
+@pytest.mark.parametrize("T,heads,ch,amp", [(512, 2, 128, 1.0), (4096, 2, 64, 1.0), (256, 1, 64, 3.0), (64, 1, 64, 1.0),
+                                            (192, 3, 128, 2.0), (1024, 1, 128, 1.0)])
+def test_attention_flash(T, heads, ch, amp):
+    """Fused attention (holo_attention_flash: S, softmax and PV in one tcgen05 kernel) against the fp32 einsum.
+    amp > 1 makes the logits large (max-subtraction matters); T = 64 / 192 leave the last query tile half empty."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    C = heads * ch
+    qkv = torch.randn(1, heads * 3 * ch, T, generator=g) * amp
+    q, k, v = qkv.reshape(heads, 3 * ch, T).split(ch, 1)
+    s = 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bct,bcs->bts", (q * s).double(), (k * s).double()), -1)
+    ref = torch.einsum("bts,bcs->bct", w, v.double()).reshape(1, -1, T)
+    x = qkv[0].t().contiguous().cuda()          # (T, 3C)
+    hi = torch.empty(T, 3 * C, device="cuda", dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(x, T, 3 * C, 3 * C, hi, lo)
+    vt_hi = torch.empty(C, T, device="cuda", dtype=torch.bfloat16)
+    vt_lo = torch.empty_like(vt_hi)
+    ops.v_transpose_split(x, T, heads, ch, vt_hi, vt_lo)
+    torch.cuda.synchronize()
+    vt = (vt_hi.float() + vt_lo.float()).cpu()
+    assert rel_err(vt, torch.cat([v[h] for h in range(heads)], 0)) < 1e-5
+    out = torch.full((T, C), float("nan"), device="cuda")
+    o_hi = torch.empty(T, C, device="cuda", dtype=torch.bfloat16)
+    o_lo = torch.empty_like(o_hi)
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, out, o_hi, o_lo) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out.t().cpu()[None], ref) < 5e-5
+    assert rel_err((o_hi.float() + o_lo.float()).t().cpu()[None], ref) < 5e-5
+    # repeatable bit for bit (no atomics, fixed summation order)
+    out2 = torch.empty_like(out)
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, out2, None, None) == 0
+    assert torch.equal(out, out2)
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, 32, out2, None, None) == -3
+
+
+@pytest.mark.parametrize("flash", ["1", "0"])
+def test_unet_base_args_32_attention_paths(flash, monkeypatch):
+    """Base UNet args on a 32^3 grid: the 8^3 level (T = 512, ch = 64) takes the tensor-core attention -- the
+    fused kernel (HOLO_ATTN_FLASH=1, default) or the S / softmax / PV pipeline (=0); both against the oracle."""
+    monkeypatch.setenv("HOLO_ATTN_FLASH", flash)
+    kw = dict(model_channels=64, num_res_blocks=2, channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(4, 8), num_heads=2)
+    sd = uo.make_unet_state_dict(16, 16, seed=2)
+    net = _build(16, 32, True, **kw)
+    net._net.load_state_dict(sd, strict=True)
+    net.cuda()
+    assert net._exec.use_flash == (flash == "1")
+    x = torch.tanh(torch.randn(1, 16, 32, 32, 32, generator=torch.Generator().manual_seed(0)))
+    tt = torch.full((1,), 0, dtype=torch.long)
+    ref = uo.unet_forward(sd, x, tt)
+    out = net(x.cuda(), tt.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < TOL
+
+
 def test_conv_tc_epilogue_statistics():
     """Per-channel (sum, sumsq) accumulated by the conv epilogue feed GroupNorm without a statistics pass."""
     from holo_diffusion_b200 import ops
