@@ -11,8 +11,12 @@
 // recomputes S, exponentiates against the final maximum and accumulates O with no rescaling of the TMEM
 // accumulator (1.5x the tensor work of one pass; the tensor pipe is not what bounds this kernel at T <= 4096).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = softmax + epilogue
-// (thread <-> query row <-> TMEM lane).
+// Pass A only needs a stabiliser close to the true maximum (softmax is invariant to it), so it multiplies the bf16
+// hi parts only (1 MMA per K step instead of 3).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = softmax + epilogue:
+// two warps per TMEM lane quarter, each thread owns one query row and HALF of the tile's 64 key columns (one warp
+// per scheduler was issue/latency bound: 130 us per T = 4096 block, see profiles/).
 #include "common.cuh"
 #include "../../include/holo_b200.h"
 #include <cuda.h>
@@ -22,7 +26,8 @@ namespace {
 
 constexpr int BM = 128;  // queries per CTA (UMMA M)
 constexpr int BN = 64;   // keys per tile = one 128-byte swizzle row of P
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;
+constexpr int SOFTMAX_THREADS = 256;
 constexpr int TMEM_COLS = 256;  // S0 [0,64) | S1 [64,128) | O [128, 128+ch)
 constexpr int O_COL = 128;
 
@@ -127,11 +132,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// (a, b) -> packed bf16x2 hi and lo parts, a in the low half: 2 packed converts + 2 subtractions
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, relative error 2^-22
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 struct FlashParams {
@@ -180,8 +192,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v_lo) : "memory");
         for (int s = 0; s < F::STAGES; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
-        for (int b = 0; b < 2; ++b) mbar_init(&s_full[b], 1), mbar_init(&s_empty[b], 4);
-        mbar_init(p_full, 128);
+        for (int b = 0; b < 2; ++b) mbar_init(&s_full[b], 1), mbar_init(&s_empty[b], SOFTMAX_THREADS / 32);
+        mbar_init(p_full, SOFTMAX_THREADS);
         mbar_init(p_empty, 1);
         mbar_init(q_full, 1);
         mbar_init(o_full, 1);
@@ -249,8 +261,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                         const uint32_t b_hi = k_base + sl * (BN * 128) + k * 32, b_lo = b_hi + F::K_HALF;
                         const uint64_t dah = sw128_desc(a_hi), dbh = sw128_desc(b_hi);
                         umma(d, dah, dbh, idesc_s, (sl | k) != 0);
-                        umma(d, dah, sw128_desc(b_lo), idesc_s, 1);
-                        umma(d, sw128_desc(a_lo), dbh, idesc_s, 1);
+                        if (j >= NT) {  // pass B: the full 3xBF16 product; pass A: hi.hi is enough for the stabiliser
+                            umma(d, dah, sw128_desc(b_lo), idesc_s, 1);
+                            umma(d, sw128_desc(a_lo), dbh, idesc_s, 1);
+                        }
                     }
                 umma_commit(&s_full[b]);
                 if (j < NT) umma_commit(&kv_empty[stage]);  // pass A: the stage holds K only, free it now
@@ -288,25 +302,28 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     } else {
         // ================= softmax + epilogue =================
         const int q = warp % 4;             // TMEM lane quarter of this warp
+        const int half = (warp - 2) / 4;    // which 32 of the tile's 64 key columns (and which half of O's columns)
         const int row = q * 32 + lane;      // query row of the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* xch = reinterpret_cast<float*>(p_smem);  // [2][128] exchange between the two column halves of a row
         float mx = -INFINITY;
         uint32_t v[32];
-        // ---- pass A: row maxima of the raw logits
+        // ---- pass A: row maxima of the (bf16 hi.hi) logits
         for (int j = 0; j < NT; ++j) {
             const int b = j & 1;
             mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
+            tmem_ld32(lane_addr + (uint32_t)(b * BN + half * 32), v);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                tmem_ld32(lane_addr + (uint32_t)(b * BN + h * 32), v);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-            }
+            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[b]);
         }
+        xch[half * BM + row] = mx;                       // the P buffer is idle until pass B
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(xch[row], xch[BM + row]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read before P tiles overwrite the scratch
         // ---- pass B: P = exp2(scale (S - max)), row sums, P -> shared memory as the bf16 hi/lo A operand of P V
         const float msc = mx * P.scale_log2;
         float l0 = 0.f, l1 = 0.f;
@@ -318,40 +335,39 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             const int b = j & 1;
             mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-            uint32_t hi[32], lo[32];  // 64 keys = 32 bf16x2 each
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                tmem_ld32(lane_addr + (uint32_t)(b * BN + h * 32), v);
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const float p0 = exp2f(fmaf(__uint_as_float(v[c]), P.scale_log2, -msc));
-                    const float p1 = exp2f(fmaf(__uint_as_float(v[c + 1]), P.scale_log2, -msc));
-                    l0 += p0, l1 += p1;
-                    split2(p0, p1, hi[h * 16 + c / 2], lo[h * 16 + c / 2]);
-                }
-            }
+            uint32_t hi[16], lo[16];  // 32 keys = 16 bf16x2 each
+            tmem_ld32(lane_addr + (uint32_t)(b * BN + half * 32), v);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[b]);      // S buffer drained (values live in registers now)
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(v[c]), P.scale_log2, -msc));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(v[c + 1]), P.scale_log2, -msc));
+                l0 += p0, l1 += p1;
+                split2(p0, p1, hi[c / 2], lo[c / 2]);
+            }
             mbar_wait(p_empty, ((uint32_t)i & 1u) ^ 1u);  // P V of the previous tile has consumed the P buffer
 #pragma unroll
-            for (int ck = 0; ck < 8; ++ck) {               // 16-byte chunk ck = keys 8 ck .. 8 ck + 7
-                const int off = (ck ^ swz) * 16;
-                *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[ck * 4], hi[ck * 4 + 1], hi[ck * 4 + 2], hi[ck * 4 + 3]);
-                *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[ck * 4], lo[ck * 4 + 1], lo[ck * 4 + 2], lo[ck * 4 + 3]);
+            for (int c = 0; c < 4; ++c) {                  // 16-byte chunk ck = keys 8 ck .. 8 ck + 7
+                const int off = ((half * 4 + c) ^ swz) * 16;
+                *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]);
+                *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA (async proxy)
             mbar_arrive(p_full);
         }
         // ---- epilogue: O / rowsum -> global (fp32 and / or the bf16 hi/lo split the projection conv consumes)
-        const float inv = 1.0f / (l0 + l1);
-        mbar_wait(o_full, 0);
+        mbar_wait(o_full, 0);                            // all MMAs retired: the P buffer is free again
         tc_fence_after();
+        xch[half * BM + row] = l0 + l1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = 1.0f / (xch[row] + xch[BM + row]);
         const int t = m0 + row;
         const bool ok = t < P.T;
         const size_t obase = (size_t)t * P.C + (size_t)head * CH;
 #pragma unroll 1
-        for (int c0 = 0; c0 < CH; c0 += 32) {
+        for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
             tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
             if (ok) {
                 float f[32];

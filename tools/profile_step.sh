@@ -9,5 +9,7 @@ ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:render_tc_kernel -s 1 -c 1 -o gpurun_out/prof_render_tc -f \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_flash_kernel -s 11 -c 2 -o gpurun_out/prof_attn_flash -f \
+    python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
 fi
 ls -la gpurun_out
