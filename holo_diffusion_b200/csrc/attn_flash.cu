@@ -39,10 +39,14 @@ struct FCfg {
     static constexpr int V_HALF = CH * 128;
     static constexpr int Q_BYTES = 2 * Q_HALF, K_BYTES = 2 * K_HALF, V_BYTES = 2 * V_HALF;
     static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
-    static constexpr int STAGES = CH == 64 ? 3 : 2;
+    // the K/V ring must cover the TMA round trip: a stage is held from its load until P V of that tile retires
+    // (3 stages stalled every tile of pass B by ~0.4 us at ch = 64)
+    static constexpr int STAGES = CH == 64 ? 4 : 2;
     static constexpr int P_HALF = BM * 128;
-    static constexpr int P_BYTES = 2 * P_HALF;
-    static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int P_BYTES = 2 * P_HALF;       // one P tile: [p_hi | p_lo]
+    static constexpr int PBUF = CH == 64 ? 2 : 1;    // P double-buffered where shared memory allows (ch = 64): with a
+                                                     // single buffer softmax(i+1) -> P V(i) -> softmax... serialises
+    static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + PBUF * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------- PTX wrappers (same conventions as conv_tc.cu)
@@ -165,15 +169,15 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* q_smem = smem;                                   // [q_hi slabs | q_lo slabs]
     uint8_t* kv_smem = smem + F::Q_BYTES;                     // STAGES x [k_hi | k_lo | v_hi | v_lo]
-    uint8_t* p_smem = kv_smem + F::STAGES * F::STAGE_BYTES;   // [p_hi | p_lo]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + F::P_BYTES);
+    uint8_t* p_smem = kv_smem + F::STAGES * F::STAGE_BYTES;   // PBUF x [p_hi | p_lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + F::PBUF * F::P_BYTES);
     uint64_t* kv_full = bars;                     // [STAGES]
     uint64_t* kv_empty = kv_full + F::STAGES;     // [STAGES]
     uint64_t* s_full = kv_empty + F::STAGES;      // [2]
     uint64_t* s_empty = s_full + 2;               // [2]
-    uint64_t* p_full = s_empty + 2;
-    uint64_t* p_empty = p_full + 1;
-    uint64_t* q_full = p_empty + 1;
+    uint64_t* p_full = s_empty + 2;               // [2]
+    uint64_t* p_empty = p_full + 2;               // [2]
+    uint64_t* q_full = p_empty + 2;
     uint64_t* o_full = q_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
@@ -193,8 +197,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v_lo) : "memory");
         for (int s = 0; s < F::STAGES; ++s) mbar_init(&kv_full[s], 1), mbar_init(&kv_empty[s], 1);
         for (int b = 0; b < 2; ++b) mbar_init(&s_full[b], 1), mbar_init(&s_empty[b], SOFTMAX_THREADS / 32);
-        mbar_init(p_full, SOFTMAX_THREADS);
-        mbar_init(p_empty, 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&p_full[b], SOFTMAX_THREADS), mbar_init(&p_empty[b], 1);
         mbar_init(q_full, 1);
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -279,21 +282,22 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             const int j = NT + i;
             if (i + 1 < NT) issue_s(j + 1);        // S of the next tile overlaps the softmax of this one
             const int stage = j % F::STAGES;
-            mbar_wait(p_full, (uint32_t)i & 1u);
+            const int pb = i % F::PBUF;
+            mbar_wait(&p_full[pb], (uint32_t)(i / F::PBUF) & 1u);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t d = tmem_base + O_COL;
                 const uint32_t v_base = smem_u32(kv_smem + stage * F::STAGE_BYTES + F::K_BYTES);
 #pragma unroll
                 for (int k = 0; k < BN / 16; ++k) {
-                    const uint32_t a_hi = p_base + k * 32, a_lo = a_hi + F::P_HALF;
+                    const uint32_t a_hi = p_base + pb * F::P_BYTES + k * 32, a_lo = a_hi + F::P_HALF;
                     const uint32_t b_hi = v_base + k * 32, b_lo = b_hi + F::V_HALF;
                     const uint64_t dah = sw128_desc(a_hi), dbh = sw128_desc(b_hi);
                     umma(d, dah, dbh, idesc_o, (i | k) != 0);
                     umma(d, dah, sw128_desc(b_lo), idesc_o, 1);
                     umma(d, sw128_desc(a_lo), dbh, idesc_o, 1);
                 }
-                umma_commit(p_empty);
+                umma_commit(&p_empty[pb]);
                 umma_commit(&kv_empty[stage]);
                 if (i == NT - 1) umma_commit(o_full);
             }
@@ -327,8 +331,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         // ---- pass B: P = exp2(scale (S - max)), row sums, P -> shared memory as the bf16 hi/lo A operand of P V
         const float msc = mx * P.scale_log2;
         float l0 = 0.f, l1 = 0.f;
-        uint8_t* prow_hi = p_smem + (size_t)(row / 8) * 1024 + (row % 8) * 128;
-        uint8_t* prow_lo = prow_hi + F::P_HALF;
+        uint8_t* prow = p_smem + (size_t)(row / 8) * 1024 + (row % 8) * 128;
         const int swz = row % 8;
         for (int i = 0; i < NT; ++i) {
             const int j = NT + i;
@@ -347,7 +350,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 l0 += p0, l1 += p1;
                 split2(p0, p1, hi[c / 2], lo[c / 2]);
             }
-            mbar_wait(p_empty, ((uint32_t)i & 1u) ^ 1u);  // P V of the previous tile has consumed the P buffer
+            const int pb = i % F::PBUF;
+            mbar_wait(&p_empty[pb], ((uint32_t)(i / F::PBUF) & 1u) ^ 1u);  // the P V that last read this buffer retired
+            uint8_t* prow_hi = prow + pb * F::P_BYTES;
+            uint8_t* prow_lo = prow_hi + F::P_HALF;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                  // 16-byte chunk ck = keys 8 ck .. 8 ck + 7
                 const int off = ((half * 4 + c) ^ swz) * 16;
@@ -355,7 +361,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 *reinterpret_cast<uint4*>(prow_lo + off) = make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA (async proxy)
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[pb]);
         }
         // ---- epilogue: O / rowsum -> global (fp32 and / or the bf16 hi/lo split the projection conv consumes)
         mbar_wait(o_full, 0);                            // all MMAs retired: the P buffer is free again
