@@ -193,25 +193,27 @@ class Clocks:
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 def build_model(a, dev):
+    """Random-init weights of the named architecture, drawn by the package's own reference-faithful initialisers
+    (Xavier-uniform Conv3d / Linear, diffusion_utils.py:77-80 and custom_modules.py:104); nothing under oracle/ is
+    touched by this arm."""
     import holo_diffusion_b200 as hd
-    from fixtures import make_mlp
-    from oracle import unet_oracle as uo  # only for the seeded state-dict FIXTURE (weights), not for compute
     un = dict(UNET_ARGS)
     un["use_tensor_cores"] = not a.no_tc
+    torch.manual_seed(2)
     model = hd.HoloDiffusionModel(
         resol=a.resol, feature_size=a.channels, num_passes=a.passes, render_image_width=a.image, render_image_height=a.image,
         net_3d_SimpleUnet3D_args=un, raysampler_AdaptiveRaySampler_args=dict(n_pts_per_ray_evaluation=a.pts),
         renderer_HoloMultiPassEmissionAbsorptionRenderer_args=dict(
             n_pts_per_ray_fine_evaluation=a.fine, raymarcher_EmissionAbsorptionRaymarcher_args=dict(bg_color=(1.0, 1.0, 1.0))))
-    model.net_3d._net.load_state_dict(uo.make_unet_state_dict(a.channels, a.channels, seed=2), strict=True)
-    model._implicit_functions[0]._fn.render_mlp.load_state_dict(make_mlp(a.channels), strict=True)
+    with torch.no_grad():  # a density head strong enough that rays saturate / stay empty (compositing is exercised)
+        head = model._implicit_functions[0]._fn.render_mlp._density_net.mlp[-1][0]
+        head.weight[-1] *= 8.0
     return model.to(dev)
 
 
 def run_ours(a):
     import holo_diffusion_b200 as hd
     from holo_diffusion_b200 import _lib
-    from fixtures import make_grid
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -238,7 +240,7 @@ def run_ours(a):
 
     model = build_model(a, dev)
     C, R, HW = a.channels, a.resol, a.image
-    grid_host = make_grid(C, R, seed=100 + rank).pin_memory()
+    grid_host = torch.tanh(torch.randn(1, C, R, R, R, generator=torch.Generator().manual_seed(100 + rank))).pin_memory()
     cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, (-0.0396, -0.8306, -0.5554), 3.2)
     cam_host = cams[[rank % 8]]
     grid_dev = grid_host.to(dev)

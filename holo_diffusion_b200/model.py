@@ -73,6 +73,7 @@ class HoloDiffusionModel(nn.Module):
         if net_3d_enabled:
             a = dict(net_3d_SimpleUnet3D_args or {})
             a.update(in_channels=feature_size, out_channels=feature_size, image_size=resol)
+            a.setdefault("use_cuda_graph", use_cuda_graph)  # the sampling loop replays the denoiser as a graph too
             self.net_3d = SimpleUnet3D(**a)
         self.diffusion = ImplicitronGaussianDiffusion(**(diffusion_args or {})) if diffusion_enabled else None
         rs = dict(raysampler_AdaptiveRaySampler_args or {})

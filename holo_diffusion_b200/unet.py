@@ -171,6 +171,9 @@ class UNetExecutor:
         self.use_tc = use_tensor_cores
         # HOLO_ATTN_FLASH=0 falls back to the three-launch S / softmax / PV pipeline (A/B measurements)
         self.use_flash = os.environ.get("HOLO_ATTN_FLASH", "1") != "0"
+        self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
+        self._graph = None
+        self._graph_key = None
         self._convs: Dict[int, _PackedConv] = {}
         self._film_version = None
         self._film_w = self._film_b = None
@@ -430,6 +433,41 @@ class UNetExecutor:
             act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1, st1=act.st1, st2=s.st1), film_all)
         return self._conv_norm(p.out[2], act, p.out[0], None).x1
 
+    # -- CUDA-graph replay of one denoiser evaluation (the 1000-step sampling loop calls it back to back) ------
+    def _weights_signature(self):
+        ps = list(self.p.parameters())
+        return sum(q._version for q in ps), ps[0].data_ptr()
+
+    def _one(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        _, C, D, H, W = x.shape
+        V = D * H * W
+        x_cl = ops.transpose2d(x.reshape(-1), C, V).view(V, C)
+        y_cl = self.forward_cl(x_cl, (D, H, W), t)
+        return ops.transpose2d(y_cl.reshape(-1), V, self.p.out_channels).view(1, self.p.out_channels, D, H, W)
+
+    def _graph_forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        dev = x.device
+        key = (str(dev), tuple(x.shape), self._weights_signature())
+        if self._graph is None or self._graph_key != key:
+            self._gx = torch.empty_like(x)
+            self._gt = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._gx.copy_(x)
+            self._gt.copy_(t)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._one(self._gx, self._gt)  # warm-up: packs the weights, sets kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._gy = self._one(self._gx, self._gt)
+            self._graph, self._graph_key = g, key
+        self._gx.copy_(x, non_blocking=True)
+        self._gt.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return self._gy.clone()  # the static output buffer is overwritten by the next replay
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """x (N, C, D, H, W), t (N,) -> (N, Cout, D, H, W); samples are independent (looped)."""
@@ -438,6 +476,8 @@ class UNetExecutor:
         outs = []
         x = x.contiguous().float()
         t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if self.use_cuda_graph and N == 1 and not torch.cuda.is_current_stream_capturing():
+            return self._graph_forward(x, t)
         for n in range(N):
             x_cl = ops.transpose2d(x[n].reshape(-1), C, V).view(V, C)
             y_cl = self.forward_cl(x_cl, (D, H, W), t[n:n + 1])
@@ -464,7 +504,7 @@ class SimpleUnet3D(Unet3DBase):
     def __init__(self, image_size: int = 64, in_channels: int = 128, out_channels: int = 128,
                  model_channels: int = 128, num_res_blocks: int = 2, channel_mult: Sequence[int] = (1, 2, 4, 8),
                  attention_resolutions: Sequence[int] = (8, 16), num_heads: int = 2, dropout: float = 0.0,
-                 homogeneous_resample: bool = True, use_tensor_cores: bool = True):
+                 homogeneous_resample: bool = True, use_tensor_cores: bool = True, use_cuda_graph: bool = False):
         super().__init__()
         if dropout != 0.0:
             raise NotImplementedError("inference path: dropout must be 0 (reference default)")
@@ -479,6 +519,9 @@ class SimpleUnet3D(Unet3DBase):
                 with torch.no_grad():
                     m.bias.zero_()
         self._exec = UNetExecutor(self._net, use_tensor_cores)
+        # replay each single-sample evaluation as one CUDA graph (~280 launches): the DDPM / DDIM loops call the
+        # denoiser 1000x back to back and are otherwise bound by the host-side launch rate
+        self._exec.use_cuda_graph = use_cuda_graph
 
     def forward(self, x, timesteps, cond_features=None):
         if cond_features is not None:

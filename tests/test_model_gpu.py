@@ -97,11 +97,14 @@ def test_ddim_steps_match_reference_vectors():
     assert fin.shape == (2, 4, 4, 4, 4) and torch.isfinite(fin).all()
 
 
-def test_short_sampling_chain_matches_oracle():
-    """4 ancestral steps t = 999, 666, 333, 0 with injected noise: CUDA UNet + fused step vs oracle UNet + oracle step."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_short_sampling_chain_matches_oracle(graph):
+    """4 ancestral steps t = 999, 666, 333, 0 with injected noise: CUDA UNet + fused step vs oracle UNet + oracle step.
+    graph=True replays every denoiser evaluation as one CUDA graph (static x / t buffers, t read on the device)."""
     import holo_diffusion_b200 as hd
     C, R = 16, 16
-    m, sd, _ = _model(C, R, 8, 4, 1, False)
+    m, sd, _ = _model(C, R, 8, 4, 1, graph)
+    assert m.net_3d._exec.use_cuda_graph == graph
     d = hd.ImplicitronGaussianDiffusion()
     tab = do.schedule_tables()
     gen = torch.Generator().manual_seed(11)
