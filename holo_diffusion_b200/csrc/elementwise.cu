@@ -216,7 +216,8 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
                                       long long V, const double* __restrict__ acc, const double* __restrict__ ch1,
                                       const double* __restrict__ ch2, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ film, float eps,
-                                      float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
+                                      float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
+                                      uint16_t* __restrict__ raw_hi, uint16_t* __restrict__ raw_lo) {
     extern __shared__ float s_ab[];  // a[C], b[C]
     __shared__ double s_acc[64];
     const int C = C1 + C2;
@@ -269,6 +270,21 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
             const float4 u0 = *reinterpret_cast<const float4*>(src + v * pitch);
             const float4 u1 = *reinterpret_cast<const float4*>(src + v * pitch + 4);
             float r[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            if (raw_hi) {
+                // the un-normalised tensor as a bf16 hi/lo pair too (operand of the ResBlock's 1x1 skip convolution,
+                // unet.py:222,255): saves the separate split pass re-reading the concat
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 hb = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+                    h[k] = *reinterpret_cast<const uint32_t*>(&hb);
+                    const float ha = __uint_as_float(h[k] << 16), hc = __uint_as_float(h[k] & 0xffff0000u);
+                    const __nv_bfloat162 lb = __floats2bfloat162_rn(r[2 * k] - ha, r[2 * k + 1] - hc);
+                    l[k] = *reinterpret_cast<const uint32_t*>(&lb);
+                }
+                *reinterpret_cast<uint4*>(raw_hi + v * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(raw_lo + v * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 r[k] = fmaf(r[k], a8[k], b8[k]);
@@ -328,9 +344,11 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
 static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                                  const double* ch1, const double* ch2, const float* gamma, const float* beta,
                                  const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                                 void* y_lo_bf16, void* stream) {
+                                 void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream) {
     int C = C1 + C2;
     HOLO_CHECK_ARG(x1 && (acc64 || ch1) && gamma && beta && (y || y_hi_bf16) && V > 0, "holo_gn_apply_fused: bad args");
+    HOLO_CHECK_ARG((raw_hi_bf16 == nullptr) == (raw_lo_bf16 == nullptr), "holo_gn_apply_fused: raw hi/lo come together");
+    HOLO_CHECK_ARG(!raw_hi_bf16 || ((C1 | C2) & 7) == 0, "holo_gn_apply_fused: raw split needs channel counts % 8 == 0");
     HOLO_CHECK_ARG(acc64 || C2 == 0 || ch2, "holo_gn_apply_fused_ch: statistics of the second source missing");
     HOLO_CHECK_ARG(C % 32 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 4096, "holo_gn_apply_fused: C=%d+%d unsupported", C1, C2);
     HOLO_CHECK_ARG((y_hi_bf16 == nullptr) == (y_lo_bf16 == nullptr), "holo_gn_apply_fused: hi/lo must come together");
@@ -351,30 +369,31 @@ static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C
     if (silu)
         gn_apply_fused_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(
             x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16);
+            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16);
     else
         gn_apply_fused_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(
             x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16);
+            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16);
     HOLO_CHECK_LAUNCH("holo_gn_apply_fused");
     return HOLO_OK;
 }
 
 extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                                    const float* gamma, const float* beta, const float* film_scale_shift, float eps,
-                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream) {
+                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* raw_hi_bf16,
+                                   void* raw_lo_bf16, void* stream) {
     HOLO_CHECK_ARG(acc64, "holo_gn_apply_fused: null statistics");
     return gn_apply_fused_launch(x1, C1, x2, C2, V, acc64, nullptr, nullptr, gamma, beta, film_scale_shift, eps, silu, y,
-                                 y_hi_bf16, y_lo_bf16, stream);
+                                 y_hi_bf16, y_lo_bf16, raw_hi_bf16, raw_lo_bf16, stream);
 }
 
 extern "C" int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
                                       const double* ch_stats2, long long V, const float* gamma, const float* beta,
                                       const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                                      void* y_lo_bf16, void* stream) {
+                                      void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream) {
     HOLO_CHECK_ARG(ch_stats1, "holo_gn_apply_fused_ch: null statistics");
     return gn_apply_fused_launch(x1, C1, x2, C2, V, nullptr, ch_stats1, ch_stats2, gamma, beta, film_scale_shift, eps,
-                                 silu, y, y_hi_bf16, y_lo_bf16, stream);
+                                 silu, y, y_hi_bf16, y_lo_bf16, raw_hi_bf16, raw_lo_bf16, stream);
 }
 
 extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a,

@@ -203,16 +203,18 @@ def gn_stats_pp(x1, C1, x2, C2, V, acc, acc_next):
                _ptr(acc_next, torch.float64), _stream())
 
 
-def gn_apply_fused(x1, C1, x2, C2, V, acc, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None):
+def gn_apply_fused(x1, C1, x2, C2, V, acc, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None,
+                   raw_hi=None, raw_lo=None):
     lib().call("holo_gn_apply_fused", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta),
                _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16),
-               _stream())
+               _ptr(raw_hi, torch.bfloat16), _ptr(raw_lo, torch.bfloat16), _stream())
 
 
-def gn_apply_fused_ch(x1, C1, st1, x2, C2, st2, V, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None):
+def gn_apply_fused_ch(x1, C1, st1, x2, C2, st2, V, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None,
+                      raw_hi=None, raw_lo=None):
     lib().call("holo_gn_apply_fused_ch", _ptr(x1), C1, _ptr(st1, torch.float64), _ptr(x2), C2, _ptr(st2, torch.float64), V,
                _ptr(gamma), _ptr(beta), _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16),
-               _ptr(y_lo, torch.bfloat16), _stream())
+               _ptr(y_lo, torch.bfloat16), _ptr(raw_hi, torch.bfloat16), _ptr(raw_lo, torch.bfloat16), _stream())
 
 
 def gn_finalize(acc, gamma, beta, film, C, V, a, b, eps=1e-5):

@@ -221,11 +221,17 @@ class UNetExecutor:
         """Can this convolution (stride 1, after any upsample) run on the tcgen05 kernel?"""
         return self.use_tc and pc.cout % 16 == 0 and pc.cout <= 4096 and _tile_ok(out_dims)
 
-    def _gn(self, act: _Act, norm: nn.GroupNorm, film, silu: bool, want_split: bool):
-        """GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation.  Returns (fp32, hi, lo)."""
+    def _gn(self, act: _Act, norm: nn.GroupNorm, film, silu: bool, want_split: bool, want_raw: bool = False):
+        """GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation.  Returns (fp32, hi, lo, raw) where raw is
+        the bf16 hi/lo pair of the UN-normalised input (want_raw; written in the same pass) or None."""
         dev = act.x1.device
         C, V = act.C, act.V
         y = y_hi = y_lo = None
+        r_hi = r_lo = None
+        if want_raw:
+            r_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+            r_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+        raw = (r_hi, r_lo) if want_raw else None
         if want_split:
             assert C % 64 == 0
             y_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
@@ -235,14 +241,14 @@ class UNetExecutor:
         if act.st1 is not None and (act.x2 is None or act.st2 is not None):
             # the producing convolutions already accumulated the statistics in their epilogues: one launch
             ops.gn_apply_fused_ch(act.x1, act.c1, act.st1, act.x2, act.c2, act.st2, V, norm.weight.detach(),
-                                  norm.bias.detach(), film, norm.eps, silu, y, y_hi, y_lo)
-            return y, y_hi, y_lo
+                                  norm.bias.detach(), film, norm.eps, silu, y, y_hi, y_lo, r_hi, r_lo)
+            return y, y_hi, y_lo, raw
         acc, nxt = self._acc[self._acc_i], self._acc[self._acc_i ^ 1]
         self._acc_i ^= 1
         ops.gn_stats_pp(act.x1, act.c1, act.x2, act.c2, V, acc, nxt)   # accumulates into acc, clears nxt
         ops.gn_apply_fused(act.x1, act.c1, act.x2, act.c2, V, acc, norm.weight.detach(), norm.bias.detach(), film,
-                           norm.eps, silu, y, y_hi, y_lo)
-        return y, y_hi, y_lo
+                           norm.eps, silu, y, y_hi, y_lo, r_hi, r_lo)
+        return y, y_hi, y_lo, raw
 
     def _split_raw(self, act: _Act, pc: _PackedConv, ups: bool = False):
         """bf16 hi/lo pair of a raw (un-normalised) activation (skip concat consumed in place), channel-padded,
@@ -295,14 +301,16 @@ class UNetExecutor:
         self.simt_calls += 1
         return _Act(out, pc.cout, od)
 
-    def _conv_norm(self, mod, act: _Act, norm, film, residual=None) -> _Act:
-        """conv(SiLU(GN(act)))  -- the in_layers / out_layers / out pattern."""
+    def _conv_norm(self, mod, act: _Act, norm, film, residual=None, want_raw: bool = False):
+        """conv(SiLU(GN(act)))  -- the in_layers / out_layers / out pattern.  want_raw: also return the bf16 hi/lo
+        pair of the raw input (or None when this shape cannot produce it) as a second value."""
         pc = self._pc(mod)
         tc = self._tc_ok(pc, act.dims) and pc.cin % 64 == 0
-        y, y_hi, y_lo = self._gn(act, norm, film, True, tc)
-        if tc:
-            return self._conv_tc(pc, y_hi, y_lo, act.dims, residual)
-        return self._conv_simt(pc, act, residual=residual, pre=y)
+        raw_ok = want_raw and tc and act.c1 % 8 == 0 and act.c2 % 8 == 0
+        y, y_hi, y_lo, raw = self._gn(act, norm, film, True, tc, raw_ok)
+        out = self._conv_tc(pc, y_hi, y_lo, act.dims, residual) if tc else \
+            self._conv_simt(pc, act, residual=residual, pre=y)
+        return (out, raw) if want_raw else out
 
     def _conv_raw(self, mod, act: _Act, stride=1, ups=False, residual=None) -> _Act:
         """conv on a raw activation (first conv, skip 1x1, Upsample/Downsample convs)."""
@@ -317,13 +325,20 @@ class UNetExecutor:
 
     # -- blocks --------------------------------------------------------------------------------------------
     def _res(self, blk: _ResParams, act: _Act, film_all) -> _Act:
-        h = self._conv_norm(blk.in_layers[2], act, blk.in_layers[0], None)
+        has_skip_conv = not isinstance(blk.skip_connection, nn.Identity)
+        h = self._conv_norm(blk.in_layers[2], act, blk.in_layers[0], None, want_raw=has_skip_conv)
+        h, raw = h if has_skip_conv else (h, None)
         off, n = self._film_slices[id(blk)]
-        if isinstance(blk.skip_connection, nn.Identity):
+        if not has_skip_conv:
             assert act.x2 is None
             skip = act.x1
         else:
-            skip = self._conv_raw(blk.skip_connection, act).x1
+            pcs = self._pc(blk.skip_connection)
+            if raw is not None and self._tc_ok(pcs, act.dims) and pcs.cin_pad == act.C:
+                # 1x1 skip conv on the raw concat: its operand pair came out of the GroupNorm pass over the same tensor
+                skip = self._conv_tc(pcs, raw[0], raw[1], act.dims).x1
+            else:
+                skip = self._conv_raw(blk.skip_connection, act).x1
         return self._conv_norm(blk.out_layers[3], h, blk.out_layers[0], film_all[off:off + n], residual=skip)
 
     def _attn(self, blk: _AttnParams, act: _Act) -> _Act:
@@ -336,14 +351,14 @@ class UNetExecutor:
         tc = self.use_tc and T % 128 == 0 and ch % 64 == 0 and C % 64 == 0
         flat = _Act(act.x1, C, (1, 1, T), st1=act.st1)
         if not tc:
-            y, _, _ = self._gn(flat, blk.norm, None, False, False)
+            y, _, _, _ = self._gn(flat, blk.norm, None, False, False)
             qkv = self._conv_simt(pcq, flat, pre=y)
             a = torch.empty(T, C, device=dev)
             ops.attention_simt(qkv.x1, T, heads, ch, a)
             out = self._conv_simt(pcp, _Act(a, C, (1, 1, T)), residual=act.x1)
             return _Act(out.x1, C, act.dims)
         gdims = (T // 32, 4, 8)  # GEMM view of the token axis for the TMA box
-        _, y_hi, y_lo = self._gn(flat, blk.norm, None, False, True)
+        _, y_hi, y_lo, _ = self._gn(flat, blk.norm, None, False, True)
         qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True, want_stats=False)
         if self.use_flash and ch in (64, 128):
             # fused attention: one launch for all heads, logits never leave the SM; the result comes back already

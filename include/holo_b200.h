@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 110
+#define HOLO_B200_VERSION 111
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -142,13 +142,16 @@ int holo_gn_stats_pp(const float* x1, int C1, const float* x2, int C2, long long
                      void* stream);
 int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                         const float* gamma, const float* beta, const float* film_scale_shift, float eps, int silu,
-                        float* y, void* y_hi_bf16, void* y_lo_bf16, void* stream);
-/* Same, from the per-channel statistics the producing convolutions left behind (holo_conv3d_tc stats_ch): no
+                        float* y, void* y_hi_bf16, void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16,
+                        void* stream);
+/* raw_hi/raw_lo (optional, C1 % 8 == C2 % 8 == 0): the UN-normalised cat(x1, x2) as a bf16 hi/lo pair as well -- the
+ * operand of the ResBlock's 1x1 skip convolution (unet.py:222,255) -- written in the same pass over the tensor.
+ * Same, from the per-channel statistics the producing convolutions left behind (holo_conv3d_tc stats_ch): no
  * statistics pass over the tensor at all.  ch_stats2 belongs to the second source of the concat. */
 int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
                            const double* ch_stats2, long long V, const float* gamma, const float* beta,
                            const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                           void* y_lo_bf16, void* stream);
+                           void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream);
 /* fp32 cat(x1 (V,C1), x2 (V,C2)) -> bf16 hi/lo (Vout,Cpad): consumes the skip concat in place, zero-pads channels
  * to Cpad; upsample2x folds F.interpolate(nearest, x2) of the (Din,Hin,Win) volume (Upsample.forward,
  * unet.py:94-97), Vout = 8 V. */
