@@ -335,10 +335,11 @@ def run_ours(a):
         rec = []
         orig_tc, orig_simt = ops.conv3d_tc, ops.conv3d_simt
 
-        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None, stride=1, stats=None):
+        def tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi=None, out_lo=None, stride=1, stats=None,
+               w_scale=1.0):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo, stride, stats)
+            rc = orig_tc(x_hi, x_lo, Cin, dims, k, w_hi, w_lo, bias, res, Cout, out, out_hi, out_lo, stride, stats, w_scale)
             e.record()
             rec.append(("tc", 2.0 * (dims[0] // stride) * (dims[1] // stride) * (dims[2] // stride) * Cout * Cin * k ** 3, s, e))
             return rc
@@ -370,7 +371,7 @@ def run_ours(a):
         kind = "tc" if "tc" in by else "simt"
         fl, ms, n = by[kind]
         ach = fl / (ms / 1e3) / 1e12
-        roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3d, 3xBF16)" if kind == "tc" else "conv_simt_kernel (fp32 CUDA cores)",
+        roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3d, 3-term fp16-pair split)" if kind == "tc" else "conv_simt_kernel (fp32 CUDA cores)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": None, "launches_per_step": n // 3, "avg_launch_us": ms * 1e3 / n,
                 "algorithmic_flops_per_launch_avg": fl / n,
@@ -378,7 +379,7 @@ def run_ours(a):
                 "executed_frac": ach * 3 / peak_tf if kind == "tc" else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md)",
                 "share_of_step_ms": {k: v[1] / 3 for k, v in by.items()},
-                "note": "achieved counts ALGORITHMIC conv FLOPs (2*V*Cout*Cin*k^3); the kernel executes 3 bf16 MMAs per "
+                "note": "achieved counts ALGORITHMIC conv FLOPs (2*V*Cout*Cin*k^3); the kernel executes 3 16-bit MMAs per "
                         "product (hi*hi + hi*lo + lo*hi), see executed_*"}
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -389,7 +390,8 @@ def run_ours(a):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": a.steps,
                "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "bf16x3 (3-term bf16 split, fp32 accumulate) convs; f32 elsewhere" if ex.tc_calls else "f32",
+               "vs_baseline": None, "dtype": (("f16x3" if ex.pair_dtype == torch.float16 else "bf16x3") + " (fp32 operands as 16-bit hi/lo pairs, 3 MMAs "
+                         "per product, fp32 accumulate) convs / attention; f32 elsewhere") if ex.tc_calls else "f32",
                "data": "synthetic", "config": workload_config(a, world),
                "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / a.steps,
                        "h2d_bytes_per_step": grid_host.numel() * 4 + 4 * (9 + 3 + 2 + 2), "d2h_bytes_per_step": img_host.numel() * 4 + 16},

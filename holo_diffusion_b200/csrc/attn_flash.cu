@@ -106,9 +106,10 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16 (format 1) or fp16 (format 0), both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_16(int n, bool f16) {
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -136,13 +137,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// (a, b) -> packed bf16x2 hi and lo parts, a in the low half: 2 packed converts + 2 subtractions
+// probabilities (a, b) in [0, 1] -> packed hi and lo halves (bf16x2, or fp16x2 without the saturation holo_split2
+// needs for unbounded values), a in the low half: 2 packed converts + 2 subtractions (+ 1 unpack for fp16)
+template <bool F16>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    if (F16) {
+        const __half2 h = __floats2half2_rn(a, b);
+        hi = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        hi = *reinterpret_cast<const uint32_t*>(&h);
+        const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+    }
 }
 __device__ __forceinline__ float ex2_approx(float x) {  // 2^x, relative error 2^-22
     float y;
@@ -154,11 +165,14 @@ struct FlashParams {
     int T, C, heads;
     float scale_log2;  // ch^-1/2 * log2(e): logits are (q s).(k s) = s^2 q.k
     float* out;        // (T, C) fp32 or null
-    __nv_bfloat16* out_hi;  // (T, C) bf16 hi/lo split of the result, or null
+    __nv_bfloat16* out_hi;  // (T, C) hi/lo split of the result (same 16-bit format as the inputs), or null
     __nv_bfloat16* out_lo;
 };
 
-template <int CH>
+// F16: every operand pair (q, k, v^T in, P inside, the output pair) has fp16 halves instead of bf16.  The logits'
+// absolute error is what softmax turns into a relative error of P: 2^-17 |q||k| with bf16 pairs (6e-5 through the
+// 64^3 UNet), 2^-22 with fp16 pairs.
+template <int CH, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                   const __grid_constant__ CUtensorMap map_k_hi, const __grid_constant__ CUtensorMap map_k_lo,
@@ -242,8 +256,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc_s = idesc_bf16(BN);
-        constexpr uint32_t idesc_o = idesc_bf16(CH);
+        constexpr uint32_t idesc_s = idesc_16(BN, F16);
+        constexpr uint32_t idesc_o = idesc_16(CH, F16);
         const uint32_t q_base = smem_u32(q_smem);
         const uint32_t p_base = smem_u32(p_smem);
         // S job j: wait for its K tile and for the softmax warps to have drained the S buffer, then 3 x SLABS x 4 UMMAs
@@ -348,7 +362,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 const float p0 = ex2_approx(fmaf(__uint_as_float(v[c]), P.scale_log2, -msc));
                 const float p1 = ex2_approx(fmaf(__uint_as_float(v[c + 1]), P.scale_log2, -msc));
                 l0 += p0, l1 += p1;
-                split2(p0, p1, hi[c / 2], lo[c / 2]);
+                split2<F16>(p0, p1, hi[c / 2], lo[c / 2]);
             }
             const int pb = i % F::PBUF;
             mbar_wait(&p_empty[pb], ((uint32_t)(i / F::PBUF) & 1u) ^ 1u);  // the P V that last read this buffer retired
@@ -387,7 +401,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 if (P.out_hi) {
                     uint32_t oh[16], ol[16];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) split2(f[2 * c], f[2 * c + 1], oh[c], ol[c]);
+                    for (int c = 0; c < 16; ++c) holo_split2(f[2 * c], f[2 * c + 1], F16, oh[c], ol[c]);
                     uint4* hp = reinterpret_cast<uint4*>(P.out_hi + obase + c0);
                     uint4* lp = reinterpret_cast<uint4*>(P.out_lo + obase + c0);
 #pragma unroll
@@ -409,7 +423,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
 
 // V (T, ch) slices of the head-major qkv tensor -> V^T (heads*ch, T) bf16 hi/lo, K-major for the P V product
 __global__ void v_transpose_split_kernel(const float* __restrict__ qkv, int T, int heads, int ch,
-                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int pair_f16) {
     __shared__ float tile[32][33];
     const int C = heads * ch;
     const int c0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
@@ -423,10 +437,7 @@ __global__ void v_transpose_split_kernel(const float* __restrict__ qkv, int T, i
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int c = c0 + i, t = t0 + threadIdx.x;
         if (t < T && c < C) {
-            const float val = tile[threadIdx.x][i];
-            const __nv_bfloat16 h = __float2bfloat16_rn(val);
-            hi[(size_t)c * T + t] = h;
-            lo[(size_t)c * T + t] = __float2bfloat16_rn(val - __bfloat162float(h));
+            holo_split1(tile[threadIdx.x][i], pair_f16 != 0, hi[(size_t)c * T + t], lo[(size_t)c * T + t]);
         }
     }
 }
@@ -462,9 +473,9 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int CH>
+template <int CH, bool F16>
 int launch_flash(const CUtensorMap* maps, const FlashParams& P, cudaStream_t st) {
-    auto k = attn_flash_kernel<CH>;
+    auto k = attn_flash_kernel<CH, F16>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<CH>::SMEM_BYTES),
               "holo_attention_flash");
     dim3 grid((unsigned)((P.T + BM - 1) / BM), (unsigned)P.heads);
@@ -476,18 +487,19 @@ int launch_flash(const CUtensorMap* maps, const FlashParams& P, cudaStream_t st)
 }  // namespace
 
 extern "C" int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi_bf16,
-                                      void* vt_lo_bf16, void* stream) {
+                                      void* vt_lo_bf16, int pair_f16, void* stream) {
     HOLO_CHECK_ARG(qkv_cl && vt_hi_bf16 && vt_lo_bf16 && T > 0 && heads > 0 && ch > 0, "holo_v_transpose_split: bad args");
     dim3 grid(holo_cdiv((long long)heads * ch, 32), holo_cdiv(T, 32));
-    v_transpose_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(qkv_cl, T, heads, ch, (__nv_bfloat16*)vt_hi_bf16,
-                                                                            (__nv_bfloat16*)vt_lo_bf16);
+    v_transpose_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(qkv_cl, T, heads, ch, (uint16_t*)vt_hi_bf16,
+                                                                            (uint16_t*)vt_lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_v_transpose_split");
     return HOLO_OK;
 }
 
 extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
                                     const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
-                                    void* out_lo_bf16, void* stream) {
+                                    void* out_lo, int pair_f16, void* stream) {
+    void* out_lo_bf16 = out_lo;
     HOLO_CHECK_ARG(qkv_hi_bf16 && qkv_lo_bf16 && vt_hi_bf16 && vt_lo_bf16, "holo_attention_flash: null input");
     HOLO_CHECK_ARG(out_cl || out_hi_bf16, "holo_attention_flash: no output requested");
     HOLO_CHECK_ARG((out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr), "holo_attention_flash: hi/lo outputs come together");
@@ -512,5 +524,6 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
     P.scale_log2 = (1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
     P.out = out_cl, P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     cudaStream_t st = (cudaStream_t)stream;
-    return ch == 64 ? launch_flash<64>(maps, P, st) : launch_flash<128>(maps, P, st);
+    if (pair_f16) return ch == 64 ? launch_flash<64, true>(maps, P, st) : launch_flash<128, true>(maps, P, st);
+    return ch == 64 ? launch_flash<64, false>(maps, P, st) : launch_flash<128, false>(maps, P, st);
 }

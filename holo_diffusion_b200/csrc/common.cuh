@@ -1,6 +1,8 @@
 // Shared helpers for the holo_b200 C-ABI library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -43,6 +45,36 @@ static inline int holo_cdiv(long long a, long long b) { return (int)((a + b - 1)
 
 __device__ __forceinline__ float holo_silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float holo_leaky(float x) { return x > 0.0f ? x : 0.2f * x; }
+
+// Operand split x = hi + lo of the tensor-core kernels, two values per 32-bit word.
+//   bf16 pair: fp32's range, hi + lo exact to 2^-17 |x|                      ("3xBF16")
+//   fp16 pair (pair_f16): hi + lo exact to 2^-22 |x| for 6e-5 <= |x| (absolute 3e-8 below), same MMA rate -- what the
+//     convolutions use: through the whole UNet the distance to exact arithmetic drops from 7e-5 to 4e-6, i.e. to
+//     fp32's own.  Range: conversions saturate, |x| <= 131008 is representable (hi and lo both at 65504); a tcgen05
+//     kind::f16 MMA wants A and B in the SAME 16-bit format (bf16 x fp16 raises an illegal-instruction fault), so a
+//     bf16 hi half for range is not an option.
+__device__ __forceinline__ void holo_split2(float a, float b, bool pair_f16, uint32_t& h, uint32_t& l) {
+    if (pair_f16) {
+        const float m = 65504.f;
+        const __half2 hh = __floats2half2_rn(fminf(fmaxf(a, -m), m), fminf(fmaxf(b, -m), m));
+        h = *reinterpret_cast<const uint32_t*>(&hh);
+        const float2 hf = __half22float2(hh);
+        const __half2 lh = __floats2half2_rn(fminf(fmaxf(a - hf.x, -m), m), fminf(fmaxf(b - hf.y, -m), m));
+        l = *reinterpret_cast<const uint32_t*>(&lh);
+    } else {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+        h = *reinterpret_cast<const uint32_t*>(&hb);
+        const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xffff0000u);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(ra, rb);
+        l = *reinterpret_cast<const uint32_t*>(&lb);
+    }
+}
+
+__device__ __forceinline__ void holo_split1(float a, bool pair_f16, uint16_t& h, uint16_t& l) {
+    uint32_t h2, l2;
+    holo_split2(a, 0.f, pair_f16, h2, l2);
+    h = (uint16_t)(h2 & 0xffffu), l = (uint16_t)(l2 & 0xffffu);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

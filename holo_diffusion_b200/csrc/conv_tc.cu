@@ -109,9 +109,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A format [7,10) and B format
+// [10,13) (0 = fp16, 1 = bf16; the hardware faults on a bf16 x fp16 mix), both K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_f16, bool b_f16) {
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -152,6 +154,8 @@ struct TcParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor (no split-K)
+    int fmt;          // 0 = bf16 pairs, HOLO_FMT_F16 = fp16 pairs (all four operand halves)
+    float acc_scale;  // accumulators are multiplied by this before bias / residual (undoes the weights' 2^e scale)
 };
 
 template <int BLOCK_N>
@@ -249,8 +253,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         //   x_lo . w_hi^T           (N = BLOCK_N)    adds lo*hi to columns [0,BN);
         // the epilogue adds the two halves.  14 KB instead of 18 KB of shared-memory operand reads per K step
         // (the kernel is bound by the SMEM operand bandwidth of the SS-mode UMMA at N = 64).
-        constexpr uint32_t idesc1 = make_idesc_bf16(2 * BLOCK_N);
-        constexpr uint32_t idesc2 = make_idesc_bf16(BLOCK_N);
+        const bool f16 = (P.fmt & HOLO_FMT_F16) != 0;   // A and B of one MMA must share the format
+        const uint32_t idesc1 = make_idesc(2 * BLOCK_N, f16, f16);    // x_hi . [w_hi | w_lo]
+        const uint32_t idesc2 = make_idesc(BLOCK_N, f16, f16);        // x_lo . w_hi
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
@@ -325,7 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int n = n0 + c0;
                 float vals[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) vals[j] = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+                for (int j = 0; j < 16; ++j) vals[j] = (__uint_as_float(acc[j]) + __uint_as_float(acc2[j])) * P.acc_scale;
                 if (P.bias && lead) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -353,15 +358,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             op[j4] = make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
                     }
                     if (P.out_hi) {
-                        uint32_t hi[8], lo[8];
+                        uint32_t hi[8], lo[8];   // the result as an operand pair in the format of this call's operands
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            __nv_bfloat16 h0b = __float2bfloat16_rn(vals[2 * j]), h1b = __float2bfloat16_rn(vals[2 * j + 1]);
-                            __nv_bfloat16 l0b = __float2bfloat16_rn(vals[2 * j] - __bfloat162float(h0b));
-                            __nv_bfloat16 l1b = __float2bfloat16_rn(vals[2 * j + 1] - __bfloat162float(h1b));
-                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            holo_split2(vals[2 * j], vals[2 * j + 1], (P.fmt & HOLO_FMT_F16) != 0, hi[j], lo[j]);
                         uint4* hp = reinterpret_cast<uint4*>(P.out_hi + v * P.out_pitch + n);
                         uint4* lp = reinterpret_cast<uint4*>(P.out_lo + v * P.out_pitch + n);
                         hp[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]), hp[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -493,7 +493,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
                         int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
-                        double* stats = nullptr) {
+                        double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -508,6 +508,10 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     else if (W % 4 == 0 && H % 4 == 0 && D % 4 == 0) tw = 4, th = 4, td = 4;
     else tw = 0, th = 0, td = 0;
     const bool stride_ok = stride == 1 || (stride == 2 && ksize == 3 && Din % 2 == 0 && Hin % 2 == 0 && Win % 2 == 0);
+    if (fmt & ~HOLO_FMT_F16) {
+        holo_set_error("%s: unknown operand_fmt bits 0x%x", who, fmt);
+        return HOLO_ERR_ARG;
+    }
     if (!(ksize == 1 || ksize == 3) || !stride_ok || tw == 0 || Cin % SLAB || Cout % 16 || x_pitch % 8 || w_pitch % 8 ||
         out_pitch % 4) {
         holo_set_error("%s: unsupported shape Cin=%d Cout=%d dims=%dx%dx%d k=%d stride=%d", who, Cin, Cout, Din, Hin, Win,
@@ -551,6 +555,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
+    P.fmt = fmt, P.acc_scale = acc_scale;
     cudaStream_t st = (cudaStream_t)stream;
     if (nsplit > 1 && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
@@ -571,13 +576,14 @@ int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int 
 
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
-                              float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, void* stream) {
+                              float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, int operand_fmt,
+                              float acc_scale, void* stream) {
     const int taps = ksize * ksize * ksize;
     // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
     // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
     // (both are bound by the SS-mode UMMA operand fetch at N = 64, not by L2), so it is off by default.
     static const bool no_halo = getenv("HOLO_CONV_HALO") == nullptr;
-    if (!no_halo && !stats_ch && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
+    if (!no_halo && !stats_ch && operand_fmt == 0 && acc_scale == 1.0f && ksize == 3 && stride == 1 && x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16) &&
         (out_hi_bf16 == nullptr) == (out_lo_bf16 == nullptr) && W % 8 == 0 && H % 16 == 0 && D % 2 == 0 &&
         Cout % 64 == 0 && Cin % 64 == 0 && (long long)(W / 8) * (H / 16) * (D / 2) * (Cout / 64) >= 120) {
         int rc = holo_conv3d_tc_halo(x_hi, x_lo, Cin, D, H, W, w_hi, w_lo, bias, residual, Cout, out, out_hi_bf16,
@@ -586,7 +592,7 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
-                        stats_ch);
+                        stats_ch, operand_fmt, acc_scale);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,
@@ -594,11 +600,12 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
 extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
                             const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
                             long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, int out_is_zeroed,
-                            void* stream) {
+                            int operand_fmt, float acc_scale, void* stream) {
     if (M % BLOCK_M) {
         holo_set_error("holo_gemm_tc: M=%d must be a multiple of 128", M);
         return HOLO_ERR_UNSUPPORTED;
     }
     return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
-                        residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream, out_is_zeroed);
+                        residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream, out_is_zeroed, nullptr, operand_fmt,
+                        acc_scale);
 }

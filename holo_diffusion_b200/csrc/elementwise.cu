@@ -217,7 +217,7 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
                                       const double* __restrict__ ch2, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ film, float eps,
                                       float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
-                                      uint16_t* __restrict__ raw_hi, uint16_t* __restrict__ raw_lo) {
+                                      uint16_t* __restrict__ raw_hi, uint16_t* __restrict__ raw_lo, int pair_f16) {
     extern __shared__ float s_ab[];  // a[C], b[C]
     __shared__ double s_acc[64];
     const int C = C1 + C2;
@@ -275,13 +275,7 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
                 // unet.py:222,255): saves the separate split pass re-reading the concat
                 uint32_t h[4], l[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const __nv_bfloat162 hb = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
-                    h[k] = *reinterpret_cast<const uint32_t*>(&hb);
-                    const float ha = __uint_as_float(h[k] << 16), hc = __uint_as_float(h[k] & 0xffff0000u);
-                    const __nv_bfloat162 lb = __floats2bfloat162_rn(r[2 * k] - ha, r[2 * k + 1] - hc);
-                    l[k] = *reinterpret_cast<const uint32_t*>(&lb);
-                }
+                for (int k = 0; k < 4; ++k) holo_split2(r[2 * k], r[2 * k + 1], pair_f16 != 0, h[k], l[k]);
                 *reinterpret_cast<uint4*>(raw_hi + v * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(raw_lo + v * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -297,13 +291,7 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
             if (y_hi) {
                 uint32_t h[4], l[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const __nv_bfloat162 hb = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
-                    h[k] = *reinterpret_cast<const uint32_t*>(&hb);
-                    const float ha = __uint_as_float(h[k] << 16), hc = __uint_as_float(h[k] & 0xffff0000u);
-                    const __nv_bfloat162 lb = __floats2bfloat162_rn(r[2 * k] - ha, r[2 * k + 1] - hc);
-                    l[k] = *reinterpret_cast<const uint32_t*>(&lb);
-                }
+                for (int k = 0; k < 4; ++k) holo_split2(r[2 * k], r[2 * k + 1], pair_f16 != 0, h[k], l[k]);
                 *reinterpret_cast<uint4*>(y_hi + v * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(y_lo + v * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -324,19 +312,11 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
         if (SILU) r.x = holo_silu(r.x), r.y = holo_silu(r.y), r.z = holo_silu(r.z), r.w = holo_silu(r.w);
         if (y) *reinterpret_cast<float4*>(y + v * C + c) = r;
         if (y_hi) {
-            float rr[4] = {r.x, r.y, r.z, r.w};
-            uint16_t hi[4], lo[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                __nv_bfloat16 h = __float2bfloat16_rn(rr[k]);
-                __nv_bfloat16 l = __float2bfloat16_rn(rr[k] - __bfloat162float(h));
-                hi[k] = *reinterpret_cast<uint16_t*>(&h);
-                lo[k] = *reinterpret_cast<uint16_t*>(&l);
-            }
-            *reinterpret_cast<uint2*>(y_hi + v * C + c) =
-                make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
-            *reinterpret_cast<uint2*>(y_lo + v * C + c) =
-                make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+            uint32_t h2[2], l2[2];
+            holo_split2(r.x, r.y, pair_f16 != 0, h2[0], l2[0]);
+            holo_split2(r.z, r.w, pair_f16 != 0, h2[1], l2[1]);
+            *reinterpret_cast<uint2*>(y_hi + v * C + c) = make_uint2(h2[0], h2[1]);
+            *reinterpret_cast<uint2*>(y_lo + v * C + c) = make_uint2(l2[0], l2[1]);
         }
     }
 }
@@ -344,7 +324,7 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
 static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                                  const double* ch1, const double* ch2, const float* gamma, const float* beta,
                                  const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                                 void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream) {
+                                 void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, int pair_f16, void* stream) {
     int C = C1 + C2;
     HOLO_CHECK_ARG(x1 && (acc64 || ch1) && gamma && beta && (y || y_hi_bf16) && V > 0, "holo_gn_apply_fused: bad args");
     HOLO_CHECK_ARG((raw_hi_bf16 == nullptr) == (raw_lo_bf16 == nullptr), "holo_gn_apply_fused: raw hi/lo come together");
@@ -369,31 +349,31 @@ static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C
     if (silu)
         gn_apply_fused_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(
             x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16);
+            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
     else
         gn_apply_fused_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(
             x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16);
+            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_gn_apply_fused");
     return HOLO_OK;
 }
 
 extern "C" int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                                    const float* gamma, const float* beta, const float* film_scale_shift, float eps,
-                                   int silu, float* y, void* y_hi_bf16, void* y_lo_bf16, void* raw_hi_bf16,
-                                   void* raw_lo_bf16, void* stream) {
+                                   int silu, float* y, void* y_hi_bf16, void* y_lo, void* raw_hi_bf16,
+                                   void* raw_lo, int pair_f16, void* stream) {
     HOLO_CHECK_ARG(acc64, "holo_gn_apply_fused: null statistics");
     return gn_apply_fused_launch(x1, C1, x2, C2, V, acc64, nullptr, nullptr, gamma, beta, film_scale_shift, eps, silu, y,
-                                 y_hi_bf16, y_lo_bf16, raw_hi_bf16, raw_lo_bf16, stream);
+                                 y_hi_bf16, y_lo, raw_hi_bf16, raw_lo, pair_f16, stream);
 }
 
 extern "C" int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
                                       const double* ch_stats2, long long V, const float* gamma, const float* beta,
                                       const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                                      void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream) {
+                                      void* y_lo, void* raw_hi_bf16, void* raw_lo, int pair_f16, void* stream) {
     HOLO_CHECK_ARG(ch_stats1, "holo_gn_apply_fused_ch: null statistics");
     return gn_apply_fused_launch(x1, C1, x2, C2, V, nullptr, ch_stats1, ch_stats2, gamma, beta, film_scale_shift, eps,
-                                 silu, y, y_hi_bf16, y_lo_bf16, raw_hi_bf16, raw_lo_bf16, stream);
+                                 silu, y, y_hi_bf16, y_lo, raw_hi_bf16, raw_lo, pair_f16, stream);
 }
 
 extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, long long V, const float* a,
@@ -421,7 +401,7 @@ extern "C" int holo_gn_apply(const float* x1, int C1, const float* x2, int C2, l
 // never written.
 __global__ void split_bf16_kernel(const float* __restrict__ x, int C1, const float* __restrict__ x2, int C2,
                                   long long Vout, int Cpad, int ups, int Din, int Hin, int Win,
-                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int pair_f16) {
     const int C = C1 + C2;
     const int q = Cpad / 4;
     const long long total = Vout * q;
@@ -438,25 +418,18 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int C1, const flo
         float4 r = make_float4(0, 0, 0, 0);
         if (c < C1) r = *reinterpret_cast<const float4*>(x + vs * C1 + c);
         else if (c < C) r = *reinterpret_cast<const float4*>(x2 + vs * C2 + (c - C1));
-        float rr[4] = {r.x, r.y, r.z, r.w};
-        uint16_t h4[4], l4[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat16 h = __float2bfloat16_rn(rr[k]);
-            __nv_bfloat16 l = __float2bfloat16_rn(rr[k] - __bfloat162float(h));
-            h4[k] = *reinterpret_cast<uint16_t*>(&h);
-            l4[k] = *reinterpret_cast<uint16_t*>(&l);
-        }
-        *reinterpret_cast<uint2*>(hi + v * Cpad + c) =
-            make_uint2((uint32_t)h4[0] | ((uint32_t)h4[1] << 16), (uint32_t)h4[2] | ((uint32_t)h4[3] << 16));
-        *reinterpret_cast<uint2*>(lo + v * Cpad + c) =
-            make_uint2((uint32_t)l4[0] | ((uint32_t)l4[1] << 16), (uint32_t)l4[2] | ((uint32_t)l4[3] << 16));
+        uint32_t h2[2], l2[2];
+        holo_split2(r.x, r.y, pair_f16 != 0, h2[0], l2[0]);
+        holo_split2(r.z, r.w, pair_f16 != 0, h2[1], l2[1]);
+        *reinterpret_cast<uint2*>(hi + v * Cpad + c) = make_uint2(h2[0], h2[1]);
+        *reinterpret_cast<uint2*>(lo + v * Cpad + c) = make_uint2(l2[0], l2[1]);
     }
 }
 
 extern "C" int holo_split_bf16(const float* x1, int C1, const float* x2, int C2, long long V, int Cpad, int upsample2x,
-                               int Din, int Hin, int Win, void* hi_bf16, void* lo_bf16, void* stream) {
+                               int Din, int Hin, int Win, void* hi_bf16, void* lo, int pair_f16, void* stream) {
     const int C = C1 + C2;
+    void* lo_bf16 = lo;
     HOLO_CHECK_ARG(x1 && hi_bf16 && lo_bf16 && V > 0 && C1 > 0 && C1 % 4 == 0 && C2 % 4 == 0 && Cpad % 4 == 0 && Cpad >= C,
                    "holo_split_bf16: channel counts must be multiples of 4, Cpad >= C1 + C2");
     HOLO_CHECK_ARG(C2 == 0 || x2, "holo_split_bf16: second source missing");
@@ -468,7 +441,7 @@ extern "C" int holo_split_bf16(const float* x1, int C1, const float* x2, int C2,
     int blocks = holo_cdiv(Vout * (Cpad / 4), 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
     split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, C1, x2, C2, Vout, Cpad, upsample2x, Din, Hin, Win,
-                                                                (uint16_t*)hi_bf16, (uint16_t*)lo_bf16);
+                                                                (uint16_t*)hi_bf16, (uint16_t*)lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_split_bf16");
     return HOLO_OK;
 }

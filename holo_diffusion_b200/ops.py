@@ -30,6 +30,19 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name: str = "tensor"):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _ptr16(t: Optional[torch.Tensor], name: str = "tensor"):
+    """Pointer to one half of a tensor-core operand pair, bf16 or fp16 (the dtype selects the format flag)."""
+    return None if t is None else _ptr(t, t.dtype if t.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16, name)
+
+
+def _pair_f16(*ts) -> int:
+    """1 if the operand halves passed are fp16, 0 if bf16; one call cannot mix them (nor can one UMMA)."""
+    fl = {t.dtype == torch.float16 for t in ts if t is not None}
+    if len(fl) > 1:
+        raise HoloError("the halves of the operand pairs of one call must share a dtype (all bf16 or all fp16)")
+    return 1 if fl == {True} else 0
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -206,15 +219,15 @@ def gn_stats_pp(x1, C1, x2, C2, V, acc, acc_next):
 def gn_apply_fused(x1, C1, x2, C2, V, acc, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None,
                    raw_hi=None, raw_lo=None):
     lib().call("holo_gn_apply_fused", _ptr(x1), C1, _ptr(x2), C2, V, _ptr(acc, torch.float64), _ptr(gamma), _ptr(beta),
-               _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16), _ptr(y_lo, torch.bfloat16),
-               _ptr(raw_hi, torch.bfloat16), _ptr(raw_lo, torch.bfloat16), _stream())
+               _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr16(y_hi), _ptr16(y_lo),
+               _ptr16(raw_hi), _ptr16(raw_lo), _pair_f16(y_hi, y_lo, raw_hi, raw_lo), _stream())
 
 
 def gn_apply_fused_ch(x1, C1, st1, x2, C2, st2, V, gamma, beta, film, eps, silu: bool, y=None, y_hi=None, y_lo=None,
                       raw_hi=None, raw_lo=None):
     lib().call("holo_gn_apply_fused_ch", _ptr(x1), C1, _ptr(st1, torch.float64), _ptr(x2), C2, _ptr(st2, torch.float64), V,
-               _ptr(gamma), _ptr(beta), _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr(y_hi, torch.bfloat16),
-               _ptr(y_lo, torch.bfloat16), _ptr(raw_hi, torch.bfloat16), _ptr(raw_lo, torch.bfloat16), _stream())
+               _ptr(gamma), _ptr(beta), _ptr(film), float(eps), 1 if silu else 0, _ptr(y), _ptr16(y_hi),
+               _ptr16(y_lo), _ptr16(raw_hi), _ptr16(raw_lo), _pair_f16(y_hi, y_lo, raw_hi, raw_lo), _stream())
 
 
 def gn_finalize(acc, gamma, beta, film, C, V, a, b, eps=1e-5):
@@ -228,10 +241,11 @@ def gn_apply(x1, C1, x2, C2, V, a, b, silu: bool, y=None, y_hi=None, y_lo=None):
 
 
 def split_bf16(x, V, C, Cpad, hi, lo, ups_dims=None, x2=None, C2=0):
-    """cat(x (V,C), x2 (V,C2)) fp32 -> hi/lo (Vout,Cpad) bf16; ups_dims=(D,H,W) folds a nearest x2 upsample."""
+    """cat(x (V,C), x2 (V,C2)) fp32 -> hi / lo of shape (Vout,Cpad), both bf16 or both fp16 (by dtype);
+    ups_dims=(D,H,W) folds a nearest x2 upsample."""
     d = ups_dims or (0, 0, 0)
     lib().call("holo_split_bf16", _ptr(x), C, _ptr(x2), C2, V, Cpad, 1 if ups_dims else 0, d[0], d[1], d[2],
-               _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
+               _ptr16(hi), _ptr16(lo), _pair_f16(hi, lo), _stream())
 
 
 def _ptr_off(t, off_elems: int, dtype):
@@ -242,27 +256,36 @@ def _ptr_off(t, off_elems: int, dtype):
 
 
 def gemm_tc(a_hi, a_lo, a_off, a_pitch, M, K, b_hi, b_lo, b_off, b_pitch, N, bias, residual, out_pitch, out, out_off=0,
-            out_hi=None, out_lo=None, out_is_zeroed: bool = False) -> int:
+            out_hi=None, out_lo=None, out_is_zeroed: bool = False, acc_scale: float = 1.0) -> int:
     """out[m][n] (+out_off, row pitch out_pitch) = bias + residual + sum_k a[m][k] b[n][k] on tcgen05 (bf16x3)."""
-    bf = torch.bfloat16
+    f16 = _pair_f16(a_hi, a_lo, b_hi, b_lo, out_hi, out_lo)
+    bf = torch.float16 if f16 else torch.bfloat16
     rc = lib().try_call("holo_gemm_tc", _ptr_off(a_hi, a_off, bf), _ptr_off(a_lo, a_off, bf), a_pitch, M, K,
                         _ptr_off(b_hi, b_off, bf), _ptr_off(b_lo, b_off, bf), b_pitch, N, _ptr(bias),
                         _ptr_off(residual, out_off, torch.float32), out_pitch, _ptr_off(out, out_off, torch.float32),
                         _ptr_off(out_hi, out_off, bf), _ptr_off(out_lo, out_off, bf), 1 if out_is_zeroed else 0,
-                        _stream())
+                        FMT_F16 * f16, float(acc_scale), _stream())
     if rc not in (0, -3):
         raise HoloError(f"holo_gemm_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
 
 
-def softmax_split(S, n_rows, T, scale2, P_hi, P_lo):
-    lib().call("holo_softmax_split", _ptr(S), n_rows, T, float(scale2), _ptr(P_hi, torch.bfloat16),
-               _ptr(P_lo, torch.bfloat16), _stream())
+P_SCALE_F16 = 4096.0   # fp16 probability pairs are written as 4096 P; the P V GEMM takes acc_scale = 1 / 4096
+
+
+def softmax_split(S, n_rows, T, scale2, P_hi, P_lo) -> float:
+    """P = softmax(scale2 * S) as an operand pair; returns the power of two P was multiplied by (1 for bf16 halves,
+    4096 for fp16 halves: pass its reciprocal to the P V GEMM as acc_scale)."""
+    f16 = _pair_f16(P_hi, P_lo)
+    p_scale = P_SCALE_F16 if f16 else 1.0
+    lib().call("holo_softmax_split", _ptr(S), n_rows, T, float(scale2), _ptr16(P_hi), _ptr16(P_lo), f16, p_scale,
+               _stream())
+    return p_scale
 
 
 def transpose_split(src, src_off, src_pitch, rows, cols, hi, lo):
     lib().call("holo_transpose_split_bf16", _ptr_off(src, src_off, torch.float32), src_pitch, rows, cols,
-               _ptr(hi, torch.bfloat16), _ptr(lo, torch.bfloat16), _stream())
+               _ptr16(hi), _ptr16(lo), _pair_f16(hi, lo), _stream())
 
 
 def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, w, bias, residual, Cout, out):
@@ -270,29 +293,35 @@ def conv3d_simt(x1, C1, x2, C2, dims: Tuple[int, int, int], ksize, stride, ups, 
                1 if ups else 0, _ptr(w), _ptr(bias), _ptr(residual), Cout, _ptr(out), _stream())
 
 
+FMT_F16 = 1   # include/holo_b200.h HOLO_FMT_F16
+
+
 def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None,
-              stride: int = 1, stats=None) -> int:
+              stride: int = 1, stats=None, w_scale: float = 1.0) -> int:
     """dims = INPUT volume.  Returns the library status (0 ok, 1 ok but `stats` not produced, -3 unsupported shape);
-    other errors raise.  stats: optional zeroed fp64 (Cout, 2) tensor receiving per-channel (sum, sumsq) of the output."""
-    rc = lib().try_call("holo_conv3d_tc", _ptr(x_hi, torch.bfloat16), _ptr(x_lo, torch.bfloat16), Cin, dims[0],
-                        dims[1], dims[2], ksize, stride, _ptr(w_hi, torch.bfloat16), _ptr(w_lo, torch.bfloat16), _ptr(bias),
-                        _ptr(residual), Cout, _ptr(out), _ptr(out_hi, torch.bfloat16), _ptr(out_lo, torch.bfloat16),
-                        _ptr(stats, torch.float64), _stream())
+    other errors raise.  stats: optional zeroed fp64 (Cout, 2) tensor receiving per-channel (sum, sumsq) of the output.
+    The operand format follows the dtype of the four halves (all bf16 or all fp16); the weight pair holds
+    w_scale * w (a power of two; the kernel multiplies the accumulators by 1 / w_scale)."""
+    fmt = FMT_F16 * _pair_f16(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo)
+    rc = lib().try_call("holo_conv3d_tc", _ptr16(x_hi), _ptr16(x_lo), Cin, dims[0],
+                        dims[1], dims[2], ksize, stride, _ptr16(w_hi), _ptr16(w_lo), _ptr(bias),
+                        _ptr(residual), Cout, _ptr(out), _ptr16(out_hi), _ptr16(out_lo),
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _stream())
     if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
 
 
 def v_transpose_split(qkv, T, heads, ch, vt_hi, vt_lo):
-    lib().call("holo_v_transpose_split", _ptr(qkv), T, heads, ch, _ptr(vt_hi, torch.bfloat16), _ptr(vt_lo, torch.bfloat16),
+    lib().call("holo_v_transpose_split", _ptr(qkv), T, heads, ch, _ptr16(vt_hi), _ptr16(vt_lo), _pair_f16(vt_hi, vt_lo),
                _stream())
 
 
 def attention_flash(qkv_hi, qkv_lo, vt_hi, vt_lo, T, heads, ch, out=None, out_hi=None, out_lo=None) -> int:
     """Fused attention on tcgen05 (holo_attention_flash).  Returns 0, or -3 for a shape the kernel does not take."""
-    bf = torch.bfloat16
-    rc = lib().try_call("holo_attention_flash", _ptr(qkv_hi, bf), _ptr(qkv_lo, bf), _ptr(vt_hi, bf), _ptr(vt_lo, bf), T,
-                        heads, ch, _ptr(out), _ptr(out_hi, bf), _ptr(out_lo, bf), _stream())
+    rc = lib().try_call("holo_attention_flash", _ptr16(qkv_hi), _ptr16(qkv_lo), _ptr16(vt_hi), _ptr16(vt_lo), T,
+                        heads, ch, _ptr(out), _ptr16(out_hi), _ptr16(out_lo),
+                        _pair_f16(qkv_hi, qkv_lo, vt_hi, vt_lo, out_hi, out_lo), _stream())
     if rc not in (0, -3):
         raise HoloError(f"holo_attention_flash failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc

@@ -133,8 +133,9 @@ class _Act:
 class _PackedConv:
     """Weights of one convolution in the kernel layouts, re-packed when the parameter changes."""
 
-    def __init__(self, mod: nn.Module):
+    def __init__(self, mod: nn.Module, pair_dtype=torch.float16):
         self.mod = mod
+        self.pair_dtype = pair_dtype
         self.version = None
         self.w_simt = self.bias = self.w_hi = self.w_lo = None
 
@@ -153,8 +154,16 @@ class _PackedConv:
         self.w_simt = wt.permute(2, 1, 0).contiguous().float()        # [tap][Cin][Cout]
         wk = torch.zeros(cout, taps, self.cin_pad, device=wd.device)   # [Cout][tap][Cin_pad]  (K-major for TMA/UMMA)
         wk[:, :, :cin] = wt.permute(0, 2, 1)
-        self.w_hi = wk.to(torch.bfloat16)
-        self.w_lo = (wk - self.w_hi.float()).to(torch.bfloat16)
+        self.w_scale = 1.0
+        if self.pair_dtype == torch.float16:
+            # fp16 pair of s * w, s = 2^e with s * max|w| in [2^9, 2^10): hi + lo is exact to 2^-22 |w| (fp16 keeps 11
+            # bits per half and the scale keeps lo out of the subnormals); the kernel multiplies by 1 / s in its epilogue
+            amax = float(wk.abs().max())
+            if amax > 0 and math.isfinite(amax):
+                self.w_scale = 2.0 ** (9 - math.floor(math.log2(amax)))
+        ws = wk * self.w_scale
+        self.w_hi = ws.to(self.pair_dtype)
+        self.w_lo = (ws - self.w_hi.float()).to(self.pair_dtype)
         self.bias = self.mod.bias.detach().float().contiguous()
 
 
@@ -171,6 +180,10 @@ class UNetExecutor:
         self.use_tc = use_tensor_cores
         # HOLO_ATTN_FLASH=0 falls back to the three-launch S / softmax / PV pipeline (A/B measurements)
         self.use_flash = os.environ.get("HOLO_ATTN_FLASH", "1") != "0"
+        # number format of the convolutions' operand pairs (x = hi + lo, w = hi + lo): fp16 halves (default; the UNet
+        # lands 4e-6 from exact arithmetic, activations saturate beyond |x| = 131008) or bf16 halves
+        # (HOLO_PAIR_FMT=bf16: fp32's range, 7e-5 from exact)
+        self.pair_dtype = torch.bfloat16 if os.environ.get("HOLO_PAIR_FMT", "f16") == "bf16" else torch.float16
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
@@ -186,7 +199,7 @@ class UNetExecutor:
     def _pc(self, mod) -> _PackedConv:
         pc = self._convs.get(id(mod))
         if pc is None:
-            pc = self._convs[id(mod)] = _PackedConv(mod)
+            pc = self._convs[id(mod)] = _PackedConv(mod, self.pair_dtype)
         pc.refresh()
         return pc
 
@@ -229,13 +242,13 @@ class UNetExecutor:
         y = y_hi = y_lo = None
         r_hi = r_lo = None
         if want_raw:
-            r_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
-            r_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+            r_hi = torch.empty(V, C, device=dev, dtype=self.pair_dtype)
+            r_lo = torch.empty(V, C, device=dev, dtype=self.pair_dtype)
         raw = (r_hi, r_lo) if want_raw else None
         if want_split:
             assert C % 64 == 0
-            y_hi = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
-            y_lo = torch.empty(V, C, device=dev, dtype=torch.bfloat16)
+            y_hi = torch.empty(V, C, device=dev, dtype=self.pair_dtype)
+            y_lo = torch.empty(V, C, device=dev, dtype=self.pair_dtype)
         else:
             y = torch.empty(V, C, device=dev)
         if act.st1 is not None and (act.x2 is None or act.st2 is not None):
@@ -251,12 +264,12 @@ class UNetExecutor:
         return y, y_hi, y_lo, raw
 
     def _split_raw(self, act: _Act, pc: _PackedConv, ups: bool = False):
-        """bf16 hi/lo pair of a raw (un-normalised) activation (skip concat consumed in place), channel-padded,
+        """hi/lo operand pair of a raw (un-normalised) activation (skip concat consumed in place), channel-padded,
         optionally upsampled."""
         dev = act.x1.device
         Vo = act.V * (8 if ups else 1)
-        hi = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
-        lo = torch.empty(Vo, pc.cin_pad, device=dev, dtype=torch.bfloat16)
+        hi = torch.empty(Vo, pc.cin_pad, device=dev, dtype=self.pair_dtype)
+        lo = torch.empty(Vo, pc.cin_pad, device=dev, dtype=self.pair_dtype)
         ops.split_bf16(act.x1, act.V, act.c1, pc.cin_pad, hi, lo, act.dims if ups else None, act.x2, act.c2)
         return hi, lo
 
@@ -269,11 +282,11 @@ class UNetExecutor:
         out = torch.empty(Vo, pc.cout, device=dev)
         o_hi = o_lo = None
         if want_split_out:
-            o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
-            o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=torch.bfloat16)
+            o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
+            o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
         st = self._stats_slice(pc.cout) if want_stats else None
         rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
-                           stride, st)
+                           stride, st, pc.w_scale)
         if rc not in (0, 1):
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
@@ -363,33 +376,34 @@ class UNetExecutor:
         if self.use_flash and ch in (64, 128):
             # fused attention: one launch for all heads, logits never leave the SM; the result comes back already
             # split into the bf16 hi/lo pair the projection conv consumes
-            vt_hi = torch.empty(C, T, device=dev, dtype=torch.bfloat16)
-            vt_lo = torch.empty(C, T, device=dev, dtype=torch.bfloat16)
+            vt_hi = torch.empty(C, T, device=dev, dtype=self.pair_dtype)
+            vt_lo = torch.empty(C, T, device=dev, dtype=self.pair_dtype)
             ops.v_transpose_split(qkv.x1, T, heads, ch, vt_hi, vt_lo)
-            a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
-            a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+            a_hi = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
+            a_lo = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
             rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, ch, None, a_hi, a_lo)
             assert rc == 0
             self.tc_calls += 1
             out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
             return _Act(out.x1, C, act.dims, st1=out.st1)
         S = torch.empty(T, T, device=dev)
-        P_hi = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
-        P_lo = torch.empty(T, T, device=dev, dtype=torch.bfloat16)
-        vt_hi = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
-        vt_lo = torch.empty(ch, T, device=dev, dtype=torch.bfloat16)
+        P_hi = torch.empty(T, T, device=dev, dtype=self.pair_dtype)
+        P_lo = torch.empty(T, T, device=dev, dtype=self.pair_dtype)
+        vt_hi = torch.empty(ch, T, device=dev, dtype=self.pair_dtype)
+        vt_lo = torch.empty(ch, T, device=dev, dtype=self.pair_dtype)
         a = torch.zeros(T, C, device=dev)   # PV GEMMs split K (the keys) across CTAs and accumulate here
         for h in range(heads):
             base = h * 3 * ch
             rc = ops.gemm_tc(q_hi, q_lo, base, 3 * C, T, ch, q_hi, q_lo, base + ch, 3 * C, T, None, None, T, S)
             assert rc == 0
-            ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)   # (q s)(k s) = s^2 q k, s = ch^-1/4
+            ps = ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)   # (q s)(k s) = s^2 q k, s = ch^-1/4
             ops.transpose_split(qkv.x1, base + 2 * ch, 3 * C, T, ch, vt_hi, vt_lo)
-            rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, a, h * ch, out_is_zeroed=True)
+            rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, a, h * ch, out_is_zeroed=True,
+                             acc_scale=1.0 / ps)
             assert rc == 0
             self.tc_calls += 2
-        a_hi = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
-        a_lo = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+        a_hi = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
+        a_lo = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
         ops.split_bf16(a, T, C, C, a_hi, a_lo)
         out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
         return _Act(out.x1, C, act.dims, st1=out.st1)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 111
+#define HOLO_B200_VERSION 112
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -142,21 +142,22 @@ int holo_gn_stats_pp(const float* x1, int C1, const float* x2, int C2, long long
                      void* stream);
 int holo_gn_apply_fused(const float* x1, int C1, const float* x2, int C2, long long V, const double* acc64,
                         const float* gamma, const float* beta, const float* film_scale_shift, float eps, int silu,
-                        float* y, void* y_hi_bf16, void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16,
+                        float* y, void* y_hi, void* y_lo, void* raw_hi, void* raw_lo, int pair_f16,
                         void* stream);
-/* raw_hi/raw_lo (optional, C1 % 8 == C2 % 8 == 0): the UN-normalised cat(x1, x2) as a bf16 hi/lo pair as well -- the
+/* raw_hi/raw_lo (optional, C1 % 8 == C2 % 8 == 0): the UN-normalised cat(x1, x2) as a hi/lo pair as well -- the
  * operand of the ResBlock's 1x1 skip convolution (unet.py:222,255) -- written in the same pass over the tensor.
+ * pair_f16 = 1 writes the pairs (y and raw) as saturating fp16 halves instead of bf16 (holo_conv3d_tc operand_fmt).
  * Same, from the per-channel statistics the producing convolutions left behind (holo_conv3d_tc stats_ch): no
  * statistics pass over the tensor at all.  ch_stats2 belongs to the second source of the concat. */
 int holo_gn_apply_fused_ch(const float* x1, int C1, const double* ch_stats1, const float* x2, int C2,
                            const double* ch_stats2, long long V, const float* gamma, const float* beta,
-                           const float* film_scale_shift, float eps, int silu, float* y, void* y_hi_bf16,
-                           void* y_lo_bf16, void* raw_hi_bf16, void* raw_lo_bf16, void* stream);
-/* fp32 cat(x1 (V,C1), x2 (V,C2)) -> bf16 hi/lo (Vout,Cpad): consumes the skip concat in place, zero-pads channels
+                           const float* film_scale_shift, float eps, int silu, float* y, void* y_hi,
+                           void* y_lo, void* raw_hi, void* raw_lo, int pair_f16, void* stream);
+/* fp32 cat(x1 (V,C1), x2 (V,C2)) -> hi/lo pair (Vout,Cpad): consumes the skip concat in place, zero-pads channels
  * to Cpad; upsample2x folds F.interpolate(nearest, x2) of the (Din,Hin,Win) volume (Upsample.forward,
- * unet.py:94-97), Vout = 8 V. */
+ * unet.py:94-97), Vout = 8 V.  The halves are bf16, or saturating fp16 with pair_f16 = 1. */
 int holo_split_bf16(const float* x1, int C1, const float* x2, int C2, long long V, int Cpad, int upsample2x, int Din,
-                    int Hin, int Win, void* hi_bf16, void* lo_bf16, void* stream);
+                    int Hin, int Win, void* hi, void* lo, int pair_f16, void* stream);
 
 /* Exact-fp32 implicit-GEMM convolution (nn.Conv3d 3^3/1^3, stride 1|2, padding k/2; nn.Conv1d k=1):
  * unet.py:185,211,222,657,792 / Downsample :129-131 / Upsample :89-97 (upsample2x folds F.interpolate nearest x2)
@@ -165,43 +166,56 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
                      int stride, int upsample2x, const float* w_tap_cin_cout, const float* bias,
                      const float* residual, int Cout, float* out, void* stream);
 
-/* tcgen05 (5th-gen tensor core) implicit-GEMM convolution, 3xBF16 split operands, fp32 TMEM accumulation.
- * Same contract as holo_conv3d_simt for ksize 1|3, stride 1|2 (Downsample.op, unet.py:129-131), one source; operands
- * are bf16 hi/lo pairs: x_hi/x_lo (V,Cin) channels-last over the INPUT volume (D,H,W), w_hi/w_lo [Cout][tap][Cin]
- * (K-major).  Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with
- * fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
+/* tcgen05 (5th-gen tensor core) implicit-GEMM convolution, 3-term split operands (hi.hi + hi.lo + lo.hi), fp32 TMEM
+ * accumulation.  Same contract as holo_conv3d_simt for ksize 1|3, stride 1|2 (Downsample.op, unet.py:129-131), one
+ * source; operands are 16-bit hi/lo pairs: x_hi/x_lo (V,Cin) channels-last over the INPUT volume (D,H,W), w_hi/w_lo
+ * [Cout][tap][Cin] (K-major).  operand_fmt selects the number format of all four halves (one kind::f16 UMMA cannot
+ * mix bf16 with fp16): 0 = bf16 pairs (fp32's range, exact to 2^-17: "3xBF16"); HOLO_FMT_F16 = fp16 pairs (exact to
+ * 2^-22; activations saturate beyond |x| = 131008; the weights are the pair of s*w with s a power of two chosen by
+ * the caller so that s*max|w| ~ 2^10, which keeps w_lo out of the subnormals, and acc_scale = 1/s undoes it:
+ * acc_scale multiplies the accumulators before bias and residual; pass 1 otherwise).  fp16 pairs bring the UNet's
+ * distance to exact arithmetic from 7e-5 to 4e-6 -- fp32's own -- at the same MMA count.
+ * out_hi/out_lo (optional): the result as an operand pair in the same format (the attention's q, k).
+ * Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
  * shapes it does not take.  stats_ch (optional, [Cout][2] doubles, pre-zeroed): per-channel (sum, sumsq) of the output
  * for the GroupNorm that consumes it, accumulated in the epilogue; the call returns 1 instead of 0 when it had to
  * split K and therefore did NOT produce them. */
+#define HOLO_FMT_F16 1
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
-                   void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, void* stream);
+                   void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
- * hi/lo pairs, K-major with arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
+ * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with
+ * arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
  * out_is_zeroed = 1 promises a zero-filled fp32 `out`, which lets small grids split K and accumulate with atomics.
  * With holo_softmax_split / holo_transpose_split_bf16 it carries QKVAttentionLegacy (unet.py:438-455) on tensor
  * cores: S = Q K^T, P = softmax(scale2 * S) (fp32, one key row per CTA, emitted as bf16 hi/lo), O = P V. */
 int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
                  const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
-                 long long out_pitch, float* out, void* out_hi_bf16, void* out_lo_bf16, int out_is_zeroed,
-                 void* stream);
-int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_hi_bf16, void* P_lo_bf16,
-                       void* stream);
-int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, int cols, void* hi_bf16,
-                              void* lo_bf16, void* stream);
+                 long long out_pitch, float* out, void* out_hi, void* out_lo, int out_is_zeroed, int operand_fmt,
+                 float acc_scale, void* stream);
+/* P = p_scale * softmax(scale2 * S): with fp16 halves pass p_scale = 4096 (normalised probabilities of long rows sit
+ * in fp16's subnormal range) and give the P V GEMM acc_scale = 1 / 4096; 1 otherwise. */
+int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_hi, void* P_lo, int pair_f16,
+                       float p_scale, void* stream);
+int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, int cols, void* hi, void* lo,
+                              int pair_f16, void* stream);
 
 /* Fused (flash-style) QKVAttentionLegacy.forward -- unet.py:438-455 -- on tcgen05: one launch for all heads, the
- * T x T logits stay in TMEM / shared memory (exact two-pass softmax, 3xBF16 operand splits, fp32 accumulation).
- * qkv_hi/lo (T, heads*3*ch) bf16 hi/lo of the head-major [q|k|v] tensor (the qkv convolution's split output);
- * vt_hi/lo (heads*ch, T) bf16 hi/lo of V^T, produced by holo_v_transpose_split from the fp32 qkv tensor.
- * out_cl (T, heads*ch) fp32 and/or out_hi/lo its bf16 split (what the projection conv consumes); either may be NULL.
+ * T x T logits stay in TMEM / shared memory (exact two-pass softmax, 3-term operand splits, fp32 accumulation).
+ * qkv_hi/lo (T, heads*3*ch) hi/lo pair of the head-major [q|k|v] tensor (the qkv convolution's split output);
+ * vt_hi/lo (heads*ch, T) hi/lo pair of V^T, produced by holo_v_transpose_split from the fp32 qkv tensor.
+ * out_cl (T, heads*ch) fp32 and/or out_hi/lo its split (what the projection conv consumes); either may be NULL.
+ * pair_f16 selects the 16-bit format of EVERY pair (inputs, the probabilities inside, the output pair): 0 = bf16
+ * halves, 1 = fp16 halves (logits exact to 2^-22 instead of 2^-17 -- softmax turns their absolute error into a
+ * relative error of the probabilities).
  * ch in {64, 128}, T % 64 == 0; other shapes return HOLO_ERR_UNSUPPORTED (-3). */
-int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi_bf16, void* vt_lo_bf16,
+int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi, void* vt_lo, int pair_f16,
                            void* stream);
 int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
-                         const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
-                         void* out_lo_bf16, void* stream);
+                         const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi,
+                         void* out_lo, int pair_f16, void* stream);
 
 /* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);

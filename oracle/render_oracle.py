@@ -4,7 +4,8 @@ parity unpinned: pytorch3d 0.7.4 is not available; see ``oracle/__init__.py``.
 
 Every function cites the reference call site (``/root/reference`` relative) that fixes its
 arguments and, where the arithmetic lives in pytorch3d 0.7.4, the pytorch3d file it follows.
-All functions are dtype-generic (fp32 = the reference's arithmetic, fp64 = noise-free twin).
+All functions are dtype- and device-generic (fp32 = the reference's arithmetic, fp64 = noise-free twin; CUDA tensors
+run the same torch ops through cuDNN / cuBLAS -- used by the full-size parity test, never by the product).
 """
 from __future__ import annotations
 
@@ -181,7 +182,7 @@ def harmonic_embedding(v: torch.Tensor, n: int) -> torch.Tensor:
     """pytorch3d HarmonicEmbedding(n, omega_0=1, logspace=True, append_input=True)."""
     if n == 0:
         return v
-    freq = 2.0 ** torch.arange(n, dtype=v.dtype)
+    freq = 2.0 ** torch.arange(n, dtype=v.dtype, device=v.device)
     e = (v[..., None] * freq).reshape(*v.shape[:-1], -1)
     return torch.cat([e.sin(), e.cos(), v], -1)
 
@@ -246,7 +247,7 @@ def implicit_function(params, grid, bundle: Optional[OracleRayBundle], resol: in
     pts = ray_points(bundle) if pts_3d is None else pts_3d
     sp = pts.shape[:-1]
     f = sample_grid(grid, world_to_local(pts.reshape(-1, 3), resol, extent))
-    dirs = bundle.directions if bundle is not None else torch.ones(*sp[:-1], 3, dtype=pts.dtype)
+    dirs = bundle.directions if bundle is not None else torch.ones(*sp[:-1], 3, dtype=pts.dtype, device=pts.device)
     d = F.normalize(dirs, dim=-1)[..., None, :].expand(*sp, 3).reshape(-1, 3)
     dens, rgb, head = render_mlp(params, f, d, return_head=True)
     feats = rgb if head is None else torch.cat([rgb, head], -1)
@@ -289,7 +290,7 @@ def ea_raymarch(dens, feats, lengths, bg=(1.0, 1.0, 1.0), background_opacity=1e1
     w = capped * absorb
     f = (w[..., None] * feats).sum(-2)
     depth = (w * lengths)[..., None].sum(-2)
-    f = f + (1 - mask) * torch.tensor(bg, dtype=f.dtype)
+    f = f + (1 - mask) * torch.tensor(bg, dtype=f.dtype, device=f.device)
     return OracleRenderOut(f, depth, mask, w, lengths=lengths)
 
 
@@ -300,7 +301,7 @@ def sample_pdf(bins, weights, N: int, u: Optional[torch.Tensor] = None, eps: flo
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
     if u is None:
-        u = torch.linspace(0.0, 1.0, N, dtype=weights.dtype).expand(*cdf.shape[:-1], N)
+        u = torch.linspace(0.0, 1.0, N, dtype=weights.dtype, device=weights.device).expand(*cdf.shape[:-1], N)
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp(0)

@@ -21,13 +21,19 @@ GN_EPS = 1e-5
 
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)  # built on the CPU, then moved (nn.py:119-122)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], -1)
 
 
+def _f32(x):
+    """``x.float()`` as the reference writes it (nn.py:25, unet.py:452); an fp64 tensor stays fp64 so that the same
+    code evaluates the noise-free twin from a ``.double()`` state dict."""
+    return x if x.dtype == torch.float64 else x.float()
+
+
 def _gn(sd, pre, x):
-    return F.group_norm(x.float(), GN_GROUPS, sd[pre + ".weight"], sd[pre + ".bias"], GN_EPS)
+    return F.group_norm(_f32(x), GN_GROUPS, sd[pre + ".weight"], sd[pre + ".bias"], GN_EPS)
 
 
 def _conv(sd, pre, x, stride=1, padding=1):
@@ -54,7 +60,7 @@ def _attention(sd, pre, x, n_heads):
     ch = c // n_heads
     q, k, v = qkv.reshape(b * n_heads, 3 * ch, T).split(ch, 1)  # head-major [q_h | k_h | v_h]
     s = 1.0 / math.sqrt(math.sqrt(ch))
-    w = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s).float(), -1)
+    w = torch.softmax(_f32(torch.einsum("bct,bcs->bts", q * s, k * s)), -1)
     a = torch.einsum("bts,bcs->bct", w, v).reshape(b, -1, T)
     h = F.conv1d(a, sd[pre + ".proj_out.weight"], sd[pre + ".proj_out.bias"])
     return (xf + h).reshape(b, c, *sp)
@@ -86,12 +92,13 @@ def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor, 
     if prefix:
         sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     mc = sd["time_embed.0.weight"].shape[1]
-    emb = F.linear(timestep_embedding(t, mc), sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    dt = sd["time_embed.0.weight"].dtype  # fp32 = the reference's arithmetic; fp64 = noise-free twin
+    emb = F.linear(timestep_embedding(t, mc).to(dt), sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     n_in = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("input_blocks."))
     n_out = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("output_blocks."))
     hs = []
-    h = x.float()
+    h = x.to(dt)
     for i in range(n_in):
         h = _run_block(sd, f"input_blocks.{i}", h, emb, n_heads)
         hs.append(h)
