@@ -167,6 +167,7 @@ struct FlashParams {
     float* out;        // (T, C) fp32 or null
     __nv_bfloat16* out_hi;  // (T, C) hi/lo split of the result (same 16-bit format as the inputs), or null
     __nv_bfloat16* out_lo;
+    int q_tile0;            // first 128-query tile of this launch (query-sharded attention: a rank owns a tile range)
 };
 
 // F16: every operand pair (q, k, v^T in, P inside, the output pair) has fp16 halves instead of bf16.  The logits'
@@ -196,7 +197,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int m0 = blockIdx.x * BM;
+    const int m0 = (P.q_tile0 + (int)blockIdx.x) * BM;
     const int head = blockIdx.y;
     const int NT = P.T / BN;        // key tiles per pass
     const int n_jobs = 2 * NT;      // S jobs: pass A (max) then pass B (exp + PV)
@@ -474,11 +475,11 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
 }
 
 template <int CH, bool F16>
-int launch_flash(const CUtensorMap* maps, const FlashParams& P, cudaStream_t st) {
+int launch_flash(const CUtensorMap* maps, const FlashParams& P, int q_tiles, cudaStream_t st) {
     auto k = attn_flash_kernel<CH, F16>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<CH>::SMEM_BYTES),
               "holo_attention_flash");
-    dim3 grid((unsigned)((P.T + BM - 1) / BM), (unsigned)P.heads);
+    dim3 grid((unsigned)q_tiles, (unsigned)P.heads);
     k<<<grid, NTHREADS, FCfg<CH>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
     HOLO_CHECK_LAUNCH("holo_attention_flash");
     return HOLO_OK;
@@ -498,7 +499,8 @@ extern "C" int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int
 
 extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
                                     const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
-                                    void* out_lo, int pair_f16, void* stream) {
+                                    void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count,
+                                    void* stream) {
     void* out_lo_bf16 = out_lo;
     HOLO_CHECK_ARG(qkv_hi_bf16 && qkv_lo_bf16 && vt_hi_bf16 && vt_lo_bf16, "holo_attention_flash: null input");
     HOLO_CHECK_ARG(out_cl || out_hi_bf16, "holo_attention_flash: no output requested");
@@ -507,6 +509,10 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
         holo_set_error("holo_attention_flash: unsupported shape T=%d heads=%d ch=%d (ch 64|128, T %% 64 == 0)", T, heads, ch);
         return HOLO_ERR_UNSUPPORTED;
     }
+    if (q_count <= 0) q_begin = 0, q_count = T;
+    HOLO_CHECK_ARG(q_begin >= 0 && q_begin % BM == 0 && q_begin + q_count <= T && (q_count % BM == 0 || q_begin + q_count == T),
+                   "holo_attention_flash: the query range [%d, %d) must start on a multiple of 128 and end on one or at T",
+                   q_begin, q_begin + q_count);
     const int C = heads * ch;
     CUtensorMap maps[6];
     int e = make_map(&maps[0], qkv_hi_bf16, T, 3LL * C, 3LL * C, BM);
@@ -521,9 +527,12 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
     }
     FlashParams P;
     P.T = T, P.C = C, P.heads = heads;
-    P.scale_log2 = (1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
+    P.scale_log2 = (softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
     P.out = out_cl, P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
+    P.q_tile0 = q_begin / BM;
+    const int q_tiles = (q_count + BM - 1) / BM;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pair_f16) return ch == 64 ? launch_flash<64, true>(maps, P, st) : launch_flash<128, true>(maps, P, st);
-    return ch == 64 ? launch_flash<64, false>(maps, P, st) : launch_flash<128, false>(maps, P, st);
+    if (pair_f16)
+        return ch == 64 ? launch_flash<64, true>(maps, P, q_tiles, st) : launch_flash<128, true>(maps, P, q_tiles, st);
+    return ch == 64 ? launch_flash<64, false>(maps, P, q_tiles, st) : launch_flash<128, false>(maps, P, q_tiles, st);
 }

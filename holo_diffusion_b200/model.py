@@ -90,6 +90,19 @@ class HoloDiffusionModel(nn.Module):
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
+        self._sample_group = None   # set by shard_one_sample()
+
+    def shard_one_sample(self, group=None, attn_min_tokens: int = 1 << 14):
+        """Several GPUs cooperate on ONE grid and ONE view (BASELINE cfg #5): every rank calls
+        forward() with the same inputs; the denoiser's large attention blocks split their queries over the ranks
+        (one all-gather per block, SimpleUnet3D.shard_attention), each rank renders a contiguous block of image rows
+        of the same grid, and the row blocks of features / depths / masks (/ weights / normals) are all-gathered, so
+        every rank returns the full images.  prev_stage is not gathered (None).  Replays no CUDA graph."""
+        import torch.distributed as dist
+        self._sample_group = group if group is not None else dist.group.WORLD
+        if self.net_3d is not None:
+            self.net_3d.shard_attention(self._sample_group, attn_min_tokens)
+        self.use_cuda_graph = False
 
     # ------------------------------------------------------------------ sampling
     def sample_random_voxel_features_progressive(self):
@@ -133,12 +146,33 @@ class HoloDiffusionModel(nn.Module):
         for func in self._implicit_functions:
             func.bind_args(voxel_grid_features=voxel_features, voxel_grid_features_channels_last=grid_cl.view(R, R, R, C))
         ray_bundle = self.raysampler(cam, EvaluationMode.EVALUATION)
-        rendered = self._render(ray_bundle=ray_bundle, chunksize=self.chunk_size_grid,
-                                implicit_functions=list(self._implicit_functions),
-                                evaluation_mode=EvaluationMode.EVALUATION)
+        if self._sample_group is not None:
+            rendered = self._render_row_sharded(ray_bundle)
+        else:
+            rendered = self._render(ray_bundle=ray_bundle, chunksize=self.chunk_size_grid,
+                                    implicit_functions=list(self._implicit_functions),
+                                    evaluation_mode=EvaluationMode.EVALUATION)
         for func in self._implicit_functions:
             func.unbind_args()
         return rendered, ray_bundle, voxel_features
+
+    def _render_row_sharded(self, ray_bundle: ImplicitronRayBundle) -> RendererOutput:
+        """Render this rank's block of image rows, then all-gather the image-shaped outputs (shard_one_sample)."""
+        import torch.distributed as dist
+        from .sharding import gather_rows, row_shard
+        world, rank = dist.get_world_size(self._sample_group), dist.get_rank(self._sample_group)
+        H = ray_bundle.lengths.shape[1]
+        h0, h1, _ = row_shard(H, world, rank)
+        sub = ImplicitronRayBundle(ray_bundle.origins[:, h0:h1].contiguous(), ray_bundle.directions[:, h0:h1].contiguous(),
+                                   ray_bundle.lengths[:, h0:h1].contiguous(), ray_bundle.xys[:, h0:h1].contiguous())
+        out = self._render(ray_bundle=sub, chunksize=self.chunk_size_grid,
+                           implicit_functions=list(self._implicit_functions), evaluation_mode=EvaluationMode.EVALUATION)
+
+        def g(t):
+            return None if t is None else gather_rows(t.contiguous(), H, rank, world, self._sample_group)
+
+        return RendererOutput(features=g(out.features), depths=g(out.depths), masks=g(out.masks), prev_stage=None,
+                              normals=g(out.normals), points=None, weights=g(out.weights), aux={})
 
     # ------------------------------------------------------------------ GenericModel._render (chunked rendering)
     def _render(self, *, ray_bundle: ImplicitronRayBundle, chunksize: int, **kwargs) -> RendererOutput:

@@ -133,9 +133,10 @@ class _Act:
 class _PackedConv:
     """Weights of one convolution in the kernel layouts, re-packed when the parameter changes."""
 
-    def __init__(self, mod: nn.Module, pair_dtype=torch.float16):
+    def __init__(self, mod: nn.Module, pair_dtype=torch.float16, remap=None):
         self.mod = mod
         self.pair_dtype = pair_dtype
+        self.remap = remap   # optional (w (Cout, Cin, taps), bias) -> (w', bias'): zero-padded attention heads
         self.version = None
         self.w_simt = self.bias = self.w_hi = self.w_lo = None
 
@@ -149,6 +150,10 @@ class _PackedConv:
         cout, cin = wd.shape[0], wd.shape[1]
         taps = wd.numel() // (cout * cin)
         wt = wd.reshape(cout, cin, taps)
+        bias = self.mod.bias.detach().float()
+        if self.remap is not None:
+            wt, bias = self.remap(wt, bias)
+            cout, cin = wt.shape[0], wt.shape[1]
         self.cout, self.cin, self.taps = cout, cin, taps
         self.cin_pad = (cin + 63) // 64 * 64                          # the tcgen05 kernel walks K in 64-channel slabs
         self.w_simt = wt.permute(2, 1, 0).contiguous().float()        # [tap][Cin][Cout]
@@ -164,7 +169,31 @@ class _PackedConv:
         ws = wk * self.w_scale
         self.w_hi = ws.to(self.pair_dtype)
         self.w_lo = (ws - self.w_hi.float()).to(self.pair_dtype)
-        self.bias = self.mod.bias.detach().float().contiguous()
+        self.bias = bias.contiguous()
+
+
+def _pad_qkv_heads(heads: int, ch: int, chp: int):
+    """qkv conv (heads*3*ch outputs, head-major [q|k|v], unet.py:445-447) -> heads*3*chp outputs with every q / k / v
+    block zero-padded from ch to chp channels: q.k is unchanged by zero channels, and the padded v channels come out
+    as zero attention outputs that the padded projection ignores."""
+    def remap(w, b):
+        cin, taps = w.shape[1], w.shape[2]
+        wp = w.new_zeros(heads, 3, chp, cin, taps)
+        wp[:, :, :ch] = w.reshape(heads, 3, ch, cin, taps)
+        bp = b.new_zeros(heads, 3, chp)
+        bp[:, :, :ch] = b.reshape(heads, 3, ch)
+        return wp.reshape(heads * 3 * chp, cin, taps), bp.reshape(-1)
+    return remap
+
+
+def _pad_proj_heads(heads: int, ch: int, chp: int):
+    """proj_out conv (heads*ch inputs) -> heads*chp inputs; the weights of the padded input channels are zero."""
+    def remap(w, b):
+        cout, taps = w.shape[0], w.shape[2]
+        wp = w.new_zeros(cout, heads, chp, taps)
+        wp[:, :, :ch] = w.reshape(cout, heads, ch, taps)
+        return wp.reshape(cout, heads * chp, taps), b
+    return remap
 
 
 def _tile_ok(dims) -> bool:
@@ -187,7 +216,13 @@ class UNetExecutor:
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
-        self._convs: Dict[int, _PackedConv] = {}
+        self._convs: Dict[Tuple[int, str], _PackedConv] = {}
+        # query-sharded attention over a process group (cfg #5: one sample on several GPUs): every
+        # rank runs the whole network on the same input, but an attention block with at least `attn_shard_min_tokens`
+        # tokens computes only its share of the query tiles (all ranks hold all keys / values) and the operand pair of
+        # the result is all-gathered before the projection.  Set by shard_attention().
+        self.attn_group = None
+        self.attn_shard_min_tokens = 1 << 14
         self._film_version = None
         self._film_w = self._film_b = None
         self._film_slices: Dict[int, Tuple[int, int]] = {}
@@ -196,12 +231,19 @@ class UNetExecutor:
         self._acc = None
 
     # -- weights -------------------------------------------------------------------------------------------
-    def _pc(self, mod) -> _PackedConv:
-        pc = self._convs.get(id(mod))
+    def _pc(self, mod, kind: str = "", remap=None) -> _PackedConv:
+        pc = self._convs.get((id(mod), kind))
         if pc is None:
-            pc = self._convs[id(mod)] = _PackedConv(mod, self.pair_dtype)
+            pc = self._convs[(id(mod), kind)] = _PackedConv(mod, self.pair_dtype, remap)
         pc.refresh()
         return pc
+
+    def shard_attention(self, group=None, min_tokens: int = 1 << 14):
+        """Split the queries of large attention blocks over the ranks of `group` (default: the world group)."""
+        import torch.distributed as dist
+        self.attn_group = group if group is not None else dist.group.WORLD
+        self.attn_shard_min_tokens = min_tokens
+        self._graph = None
 
     def _res_blocks(self):
         return [m for m in self.p.modules() if isinstance(m, _ResParams)]
@@ -360,8 +402,17 @@ class UNetExecutor:
         T, C = act.V, act.C
         heads = blk.heads
         ch = C // heads
-        pcq, pcp = self._pc(blk.qkv), self._pc(blk.proj_out)
-        tc = self.use_tc and T % 128 == 0 and ch % 64 == 0 and C % 64 == 0
+        # heads narrower than 64 channels (ch = 32 at the 64-channel levels when attention runs at every resolution,
+        # cfg #5) take the fused kernel zero-padded to 64: the qkv / proj weights are re-packed, nothing else changes
+        chp = 64 if (ch < 64 and self.use_flash) else ch
+        tc = self.use_tc and T % 128 == 0 and chp % 64 == 0 and C % 64 == 0
+        if tc and chp != ch:
+            pcq = self._pc(blk.qkv, "pad", _pad_qkv_heads(heads, ch, chp))
+            pcp = self._pc(blk.proj_out, "pad", _pad_proj_heads(heads, ch, chp))
+        else:
+            chp = ch
+            pcq, pcp = self._pc(blk.qkv), self._pc(blk.proj_out)
+        Cp = heads * chp
         flat = _Act(act.x1, C, (1, 1, T), st1=act.st1)
         if not tc:
             y, _, _, _ = self._gn(flat, blk.norm, None, False, False)
@@ -373,19 +424,25 @@ class UNetExecutor:
         gdims = (T // 32, 4, 8)  # GEMM view of the token axis for the TMA box
         _, y_hi, y_lo, _ = self._gn(flat, blk.norm, None, False, True)
         qkv, (q_hi, q_lo) = self._conv_tc(pcq, y_hi, y_lo, gdims, want_split_out=True, want_stats=False)
-        if self.use_flash and ch in (64, 128):
+        if self.use_flash and chp in (64, 128):
             # fused attention: one launch for all heads, logits never leave the SM; the result comes back already
-            # split into the bf16 hi/lo pair the projection conv consumes
-            vt_hi = torch.empty(C, T, device=dev, dtype=self.pair_dtype)
-            vt_lo = torch.empty(C, T, device=dev, dtype=self.pair_dtype)
-            ops.v_transpose_split(qkv.x1, T, heads, ch, vt_hi, vt_lo)
-            a_hi = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
-            a_lo = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
-            rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, ch, None, a_hi, a_lo)
-            assert rc == 0
+            # split into the hi/lo pair the projection conv consumes
+            vt_hi = torch.empty(Cp, T, device=dev, dtype=self.pair_dtype)
+            vt_lo = torch.empty(Cp, T, device=dev, dtype=self.pair_dtype)
+            ops.v_transpose_split(qkv.x1, T, heads, chp, vt_hi, vt_lo)
+            scale = 1.0 / math.sqrt(ch)   # the TRUE head width ((q s).(k s), s = ch^-1/4, unet.py:448-449)
+            world, rank = self._attn_world(T)
+            if world == 1:
+                a_hi = torch.empty(T, Cp, device=dev, dtype=self.pair_dtype)
+                a_lo = torch.empty(T, Cp, device=dev, dtype=self.pair_dtype)
+                rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, a_hi, a_lo, scale)
+                assert rc == 0
+            else:
+                a_hi, a_lo = self._attn_sharded(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, scale, world, rank)
             self.tc_calls += 1
             out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
             return _Act(out.x1, C, act.dims, st1=out.st1)
+        assert chp == ch
         S = torch.empty(T, T, device=dev)
         P_hi = torch.empty(T, T, device=dev, dtype=self.pair_dtype)
         P_lo = torch.empty(T, T, device=dev, dtype=self.pair_dtype)
@@ -407,6 +464,31 @@ class UNetExecutor:
         ops.split_bf16(a, T, C, C, a_hi, a_lo)
         out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
         return _Act(out.x1, C, act.dims, st1=out.st1)
+
+    def _attn_world(self, T: int) -> Tuple[int, int]:
+        if self.attn_group is None or T < self.attn_shard_min_tokens:
+            return 1, 0
+        import torch.distributed as dist
+        world = dist.get_world_size(self.attn_group)
+        return (world, dist.get_rank(self.attn_group)) if T // 128 >= world else (1, 0)
+
+    def _attn_sharded(self, q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, scale, world, rank):
+        """This rank's query tiles of the fused attention, then ONE all-gather of the (hi | lo) operand pair: rows
+        [q0, q0 + qn) of a (world * chunk, 2, Cp) buffer are written in place by the kernel (it addresses rows by
+        their absolute query index), the gather fills in the other ranks' rows."""
+        import torch.distributed as dist
+        from .sharding import query_shard
+        q0, qn, chunk = query_shard(T, world, rank)
+        Cp = heads * chp
+        buf = torch.empty(2, world * chunk, Cp, device=q_hi.device, dtype=self.pair_dtype)
+        if qn > 0:
+            rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, buf[0], buf[1], scale, q0, qn)
+            assert rc == 0
+        in_place = dist.get_backend(self.attn_group) == "nccl"   # NCCL gathers in place when the input is the rank's
+        for half in (0, 1):                                      # slice of the output; gloo (CPU tests) wants a copy
+            mine = buf[half, rank * chunk:(rank + 1) * chunk]
+            dist.all_gather_into_tensor(buf[half], mine if in_place else mine.clone(), group=self.attn_group)
+        return buf[0, :T], buf[1, :T]
 
     def _run(self, seq: nn.Sequential, act: _Act, film_all) -> _Act:
         for layer in seq:
@@ -505,7 +587,7 @@ class UNetExecutor:
         outs = []
         x = x.contiguous().float()
         t = t.to(device=x.device, dtype=torch.int64).contiguous()
-        if self.use_cuda_graph and N == 1 and not torch.cuda.is_current_stream_capturing():
+        if self.use_cuda_graph and N == 1 and self.attn_group is None and not torch.cuda.is_current_stream_capturing():
             return self._graph_forward(x, t)
         for n in range(N):
             x_cl = ops.transpose2d(x[n].reshape(-1), C, V).view(V, C)
@@ -551,6 +633,11 @@ class SimpleUnet3D(Unet3DBase):
         # replay each single-sample evaluation as one CUDA graph (~280 launches): the DDPM / DDIM loops call the
         # denoiser 1000x back to back and are otherwise bound by the host-side launch rate
         self._exec.use_cuda_graph = use_cuda_graph
+
+    def shard_attention(self, group=None, min_tokens: int = 1 << 14):
+        """Several GPUs on ONE sample (BASELINE cfg #5): every rank evaluates the network on the same input, attention
+        blocks with >= min_tokens tokens split their queries over the ranks of `group` (one all-gather per block)."""
+        self._exec.shard_attention(group, min_tokens)
 
     def forward(self, x, timesteps, cond_features=None):
         if cond_features is not None:

@@ -209,13 +209,17 @@ int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, i
  * out_cl (T, heads*ch) fp32 and/or out_hi/lo its split (what the projection conv consumes); either may be NULL.
  * pair_f16 selects the 16-bit format of EVERY pair (inputs, the probabilities inside, the output pair): 0 = bf16
  * halves, 1 = fp16 halves (logits exact to 2^-22 instead of 2^-17 -- softmax turns their absolute error into a
- * relative error of the probabilities).
+ * relative error of the probabilities).  softmax_scale: logits are softmax_scale * q.k; <= 0 selects the reference's
+ * ch^-1/2 (heads narrower than 64 channels run zero-padded to 64 and pass their true ch^-1/2 here).
+ * q_begin / q_count: only queries [q_begin, q_begin + q_count) are computed and written (rows of the full-size
+ * outputs) -- the query-sharded multi-GPU form, every rank holding all keys / values; q_begin % 128 == 0, the range
+ * ends on a multiple of 128 or at T; q_count <= 0 = all queries.
  * ch in {64, 128}, T % 64 == 0; other shapes return HOLO_ERR_UNSUPPORTED (-3). */
 int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi, void* vt_lo, int pair_f16,
                            void* stream);
 int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
                          const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi,
-                         void* out_lo, int pair_f16, void* stream);
+                         void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count, void* stream);
 
 /* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);

@@ -168,3 +168,29 @@ def test_diffusion_tables_match_oracle():
         assert np.array_equal(v, tab[k]), k
     with pytest.raises(NotImplementedError):
         hd.ImplicitronGaussianDiffusion(model_mean_type="EPSILON")
+
+
+def test_attention_head_padding_is_exact():
+    """Heads narrower than 64 channels run on the fused kernel zero-padded to 64 (unet.py executor): the re-packed
+    qkv / proj weights with the TRUE ch^-1/2 softmax scale give the reference attention block exactly."""
+    import math
+    import torch.nn.functional as F
+    from holo_diffusion_b200.unet import _pad_proj_heads, _pad_qkv_heads
+    g = torch.Generator().manual_seed(5)
+    heads, ch, chp, T = 2, 32, 64, 96
+    C = heads * ch
+    x = torch.randn(1, C, T, generator=g, dtype=torch.float64)
+    wq, bq = torch.randn(3 * C, C, 1, generator=g, dtype=torch.float64) / 8, torch.randn(3 * C, generator=g, dtype=torch.float64)
+    wp, bp = torch.randn(C, C, 1, generator=g, dtype=torch.float64) / 8, torch.randn(C, generator=g, dtype=torch.float64)
+
+    def attn(qkv, n_ch, scale2):   # QKVAttentionLegacy.forward, unet.py:438-455, with an explicit logit scale
+        q, k, v = qkv.reshape(heads, 3 * n_ch, T).split(n_ch, 1)
+        w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) * scale2, -1)
+        return torch.einsum("bts,bcs->bct", w, v).reshape(1, -1, T)
+
+    ref = F.conv1d(attn(F.conv1d(x, wq, bq), ch, 1 / math.sqrt(ch)), wp, bp)
+    wq2, bq2 = _pad_qkv_heads(heads, ch, chp)(wq, bq)
+    wp2, bp2 = _pad_proj_heads(heads, ch, chp)(wp, bp)
+    assert wq2.shape == (heads * 3 * chp, C, 1) and wp2.shape == (C, heads * chp, 1)
+    got = F.conv1d(attn(F.conv1d(x, wq2, bq2), chp, 1 / math.sqrt(ch)), wp2, bp2)
+    assert torch.allclose(got, ref, rtol=0, atol=1e-12)

@@ -479,3 +479,64 @@ def test_conv_tc_rejects_unsupported():
     z = torch.zeros(64, 32, device="cuda", dtype=torch.bfloat16)
     o = torch.zeros(64, 32, device="cuda")
     assert ops.conv3d_tc(z, z, 32, (4, 4, 4), 3, z, z, None, None, 32, o) == -3  # Cin not a multiple of 64
+
+
+def test_attention_flash_query_range_and_scale():
+    """Query-range launches (the multi-GPU query shards) write exactly the rows of the full launch, bit for bit, and
+    leave the others alone; an explicit softmax scale replaces ch^-1/2."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    T, heads, ch = 640, 2, 64
+    C = heads * ch
+    x = torch.randn(T, 3 * C, generator=g).cuda()
+    hi = torch.empty(T, 3 * C, device="cuda", dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(x, T, 3 * C, 3 * C, hi, lo)
+    vt_hi = torch.empty(C, T, device="cuda", dtype=torch.float16)
+    vt_lo = torch.empty_like(vt_hi)
+    ops.v_transpose_split(x, T, heads, ch, vt_hi, vt_lo)
+    full = torch.empty(T, C, device="cuda")
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, full) == 0
+    part = torch.full((T, C), 7.0, device="cuda")
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, part, q_begin=0, q_count=384) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(part[:384], full[:384]) and bool((part[384:] == 7.0).all())
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, part, q_begin=384, q_count=256) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(part, full)
+    with pytest.raises(ops.HoloError):
+        ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, part, q_begin=64, q_count=128)
+    # explicit scale: softmax(0.05 q.k)
+    q, k, v = x.cpu().double().t().reshape(heads, 3 * ch, T).split(ch, 1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) * 0.05, -1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(C, T).t()
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, part, softmax_scale=0.05) == 0
+    torch.cuda.synchronize()
+    assert rel_err(part, ref) < 1e-5
+
+
+def test_unet_attention_at_every_level_16():
+    """BASELINE cfg #5's architecture (attention at all UNet levels) on a 16^3 grid: the 64-channel levels have
+    32-channel heads (T = 4096 and 512), which run on the fused kernel zero-padded to 64 channels."""
+    kw = dict(model_channels=64, num_res_blocks=2, channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(1, 2, 4, 8, 16),
+              num_heads=2)
+    sd = uo.make_unet_state_dict(16, 16, attention_resolutions=(1, 2, 4, 8, 16), seed=2)
+    net = _build(16, 16, True, **kw)
+    net._net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = torch.tanh(torch.randn(1, 16, 16, 16, 16, generator=torch.Generator().manual_seed(0)))
+    tt = torch.full((1,), 0, dtype=torch.long)
+    ref = uo.unet_forward(sd, x, tt)
+    calls = []
+    from holo_diffusion_b200 import ops
+    orig = ops.attention_flash
+    ops.attention_flash = lambda *a, **k: (calls.append((a[4], a[6])), orig(*a, **k))[1]
+    try:
+        out = net(x.cuda(), tt.cuda())
+    finally:
+        ops.attention_flash = orig
+    torch.cuda.synchronize()
+    assert (4096, 64) in calls and (512, 64) in calls, calls   # (T, padded head width) of the fused launches
+    e = rel_err(out, ref)
+    print(f"unet 16^3, attention at every level: vs fp32 oracle {e:.2e}")
+    assert e < 2e-5
