@@ -52,7 +52,14 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(a, n_gpus):
+def workload_config(a, n_gpus, host: bool = False):
+    if host:   # the reference arm: the oracle port on the host cores, same workload
+        return {
+            "workload": f"cfg#2: tanh(UNet(g,t=0)) + {a.passes}-pass EA render of one view per step; "
+                        f"grid {a.resol}^3 x {a.channels}ch, base UNet args (configs/base.yaml:93-98), image {a.image}^2, "
+                        f"{a.pts}{'+' + str(a.fine) if a.passes > 1 else ''} pts/ray",
+            "passes": a.passes, "global_batch_views_per_step": 1, "parallelism": "host cores (torch CPU threads), rank 0 only",
+            "l2": "n/a (host)", "launch": "torch CPU eager; each step is a bounded sample scaled to the full view"}
     return {
         "workload": f"cfg#2: tanh(UNet(g,t=0)) + {a.passes}-pass EA render of one view per step; "
                     f"grid {a.resol}^3 x {a.channels}ch, base UNet args (configs/base.yaml:93-98), image {a.image}^2, "
@@ -124,7 +131,7 @@ def run_reference(a):
     sample = _cpu_sample_text(a, det)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "views/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus, host=True),
            "cpu_baseline": {"value": v, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "detail": det}
@@ -370,10 +377,20 @@ def run_ours(a):
             d[2] += 1
         kind = "tc" if "tc" in by else "simt"
         fl, ms, n = by[kind]
+        # DRAM traffic of the dominant kernel: measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum, average
+        # per launch over one step of this same workload) and committed under profiles/ -- never measured in here
+        traffic = traffic_src = None
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+        if tfiles and a.resol == 64 and a.channels == 32:
+            tj = json.load(open(tfiles[-1]))
+            traffic = tj["bytes_per_launch"].get("conv_tc_kernel" if kind == "tc" else "conv_simt_kernel")
+            traffic_src = "profiles/" + os.path.basename(tfiles[-1])
         ach = fl / (ms / 1e3) / 1e12
         roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3d, 3-term fp16-pair split)" if kind == "tc" else "conv_simt_kernel (fp32 CUDA cores)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "launches_per_step": n // 3, "avg_launch_us": ms * 1e3 / n,
+                "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write, ncu)", "traffic_source": traffic_src,
+                "launches_per_step": n // 3, "avg_launch_us": ms * 1e3 / n,
                 "algorithmic_flops_per_launch_avg": fl / n,
                 "executed_tensor_tflops": ach * 3 if kind == "tc" else None,
                 "executed_frac": ach * 3 / peak_tf if kind == "tc" else None,
