@@ -30,19 +30,29 @@ def launches(path, out):
         return "torch/other" if "at::" in n or not m else m.group(1)
     sn = [short(n) for n in names]
     rend = [i for i, n in enumerate(sn) if n.startswith("render_")]
-    a, b = rend[-2] + 1, rend[-1] + 1
+    note = ""
+    if len(rend) >= 2:
+        a, b = rend[-2] + 1, rend[-1] + 1
+        idx = list(range(a, b))
+    else:
+        # the capture ended inside the second step: take the FIRST step (a warm-up step: cold caches, one-time weight
+        # packing by torch kernels interleaved -- those are left out), from the first own kernel to the render kernel
+        a = next(i for i, n in enumerate(sn) if n != "torch/other")
+        b = rend[0] + 1
+        idx = [i for i in range(a, b) if sn[i] != "torch/other"]
+        note = " [FIRST (warm-up) step of a truncated capture: use for DRAM bytes, not for time shares]"
     agg, cnt, byt = collections.OrderedDict(), collections.Counter(), collections.Counter()
-    for i in range(a, b):
+    for i in idx:
         agg[sn[i]] = agg.get(sn[i], 0) + t[i]; cnt[sn[i]] += 1; byt[sn[i]] += dram[i]
     tot = sum(agg.values())
     with open(out, "w") as f:
-        f.write(f"# one bench step (eager launches under ncu, cold-cache serialized): {b - a} launches, {tot/1e6:.3f} ms\n")
+        f.write(f"# one bench step (eager launches under ncu, cold-cache serialized): {len(idx)} launches, {tot/1e6:.3f} ms{note}\n")
         f.write("# compare SHARES, not absolutes (B200_PROFILING.md)" + ("; dram = dram__bytes_read.sum + dram__bytes_write.sum per launch (average)" if have_dram else "") + "\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1]):
             extra = f"  dram {byt[k] / cnt[k] / 1e6:8.2f} MB/launch" if have_dram else ""
             f.write(f"{k:30s} n={cnt[k]:4d} {v/1e6:8.3f} ms {100*v/tot:5.1f}%{extra}\n")
         f.write("\n# conv_tc / halo launches in step order: grid, us\n")
-        f.write(" ".join(f"{data[i]['grid'].replace(' ','')}:{t[i]/1e3:.1f}" for i in range(a, b) if "conv_tc" in names[i]) + "\n")
+        f.write(" ".join(f"{data[i]['grid'].replace(' ','')}:{t[i]/1e3:.1f}" for i in idx if "conv_tc" in names[i]) + "\n")
     if have_dram:
         json.dump({"what": "ncu dram__bytes_read.sum + dram__bytes_write.sum, average bytes per launch over one bench step",
                    "source": os.path.basename(out),
