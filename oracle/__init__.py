@@ -19,11 +19,18 @@ Pinning status
 * UNet / diffusion: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified
   reference modules from ``/root/reference`` (pure torch, importable) and the oracle is
   checked against their outputs; the vectors are committed under ``tests/golden``.
-* Renderer: **parity unpinned**.  Its arithmetic lives in the un-vendored dependency
-  ``pytorch3d==0.7.4`` (reference ``environment.yaml:139``), absent from this image and
-  from ``/root/reference``; the reference's own tests only check for NaNs
-  (``holo_diffusion/tests/test_voxel_grid_implicit_function.py:55,77,93,117``).  The
-  restatement follows the published pytorch3d 0.7.4 algorithm and the reference call sites
-  cited per function.  An optional ``importorskip("pytorch3d")`` tier checks it against the
-  real thing wherever pytorch3d is installed.
+* Renderer, in-tree logic: PINNED against the reference's own code.  ``tests/golden/
+  make_render_intree_golden.py`` imports ``MLPWithInputSkips`` / ``RenderMLP`` / ``HoloVoxelGridImplicitFunction`` /
+  ``HoloMultiPassEmissionAbsorptionRenderer`` from ``/root/reference`` and executes them UNMODIFIED against the small
+  pytorch3d stand-in under ``oracle/pt3d_stub`` (layer / activation placement, skip concat, output slicing, direction
+  handling, normals through autograd, the multi-pass recursion incl. training-mode noise, state-dict key names);
+  vectors in ``tests/golden/render_intree_ref.npz``, checked by ``tests/test_cpu_oracle_and_host.py``.
+* Renderer, pytorch3d leaves: **parity unpinned**.  The arithmetic of the harmonic embedding, ray points, volume
+  locator + grid sampling, emission-absorption ray marcher, ray-point refiner / ``sample_pdf``, ray sampler and
+  cameras lives in the un-vendored dependency ``pytorch3d==0.7.4`` (reference ``environment.yaml:139``), absent from
+  this image and from ``/root/reference`` (the stand-in implements those leaves WITH this oracle, so it cannot pin
+  them); the reference's own tests only check for NaNs
+  (``holo_diffusion/tests/test_voxel_grid_implicit_function.py:55,77,93,117``).  The restatement follows the published
+  pytorch3d 0.7.4 algorithm and the reference call sites cited per function.  An optional
+  ``importorskip("pytorch3d")`` tier checks it against the real thing wherever pytorch3d is installed.
 """

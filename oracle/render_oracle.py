@@ -1,6 +1,9 @@
 """CPU restatement of the HoloDiffusion volumetric renderer (TEST INFRASTRUCTURE ONLY).
 
-parity unpinned: pytorch3d 0.7.4 is not available; see ``oracle/__init__.py``.
+Pinning: the in-tree logic (RenderMLP / MLPWithInputSkips, HoloVoxelGridImplicitFunction.forward, the multi-pass
+recursion) is pinned against the reference's own code run on ``oracle/pt3d_stub`` (tests/golden/render_intree_ref.npz);
+the pytorch3d leaves (ray sampler, cameras, grid sampling, ray marcher, refiner, harmonic embedding) are
+**parity unpinned**: pytorch3d 0.7.4 is not available; see ``oracle/__init__.py``.
 
 Every function cites the reference call site (``/root/reference`` relative) that fixes its
 arguments and, where the arithmetic lives in pytorch3d 0.7.4, the pytorch3d file it follows.
