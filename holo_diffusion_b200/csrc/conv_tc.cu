@@ -154,6 +154,8 @@ struct TcParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor (no split-K)
+    int k2_slabs;     // fused 1x1 "skip" operand: Cin2 / 64 extra K iterations after the taps x slabs main loop, reading
+                      // the SECOND activation pair at the output voxel itself (no tap offset); 0 = none
     int fmt;          // 0 = bf16 pairs, HOLO_FMT_F16 = fp16 pairs (all four operand halves)
     float acc_scale;  // accumulators are multiplied by this before bias / residual (undoes the weights' 2^e scale)
 };
@@ -161,7 +163,8 @@ struct TcParams {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcParams P) {
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo, TcParams P) {
     // PERSISTENT: each CTA walks work items (M tile, N block, K split) with a stride of gridDim.x.  The TMA producer
     // runs ahead across item boundaries and the accumulator is double-buffered in TMEM, so the epilogue of item i
     // (TMEM -> registers -> global) overlaps the main loop of item i+1 and the ~5 us of per-CTA prologue / epilogue
@@ -183,7 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int taps = P.ksize * P.ksize * P.ksize;
     const int pad = P.ksize / 2;
     const int slabs = P.Cin / SLAB;
-    const int k_total = taps * slabs;
+    const int k_main = taps * slabs;
+    const int k_total = k_main + P.k2_slabs;   // the fused skip operand extends the K loop (weights are concatenated)
     const bool split = P.nsplit > 1;
     const int n_items = P.m_tiles * P.n_blocks * P.nsplit;
 
@@ -192,6 +196,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+        if (P.k2_slabs) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2_lo) : "memory");
+        }
         for (int s = 0; s < n_stages; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
         for (int b = 0; b < 2; ++b) mbar_init(&tmem_full_bar[b], 1), mbar_init(&tmem_empty_bar[b], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -230,16 +238,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 int w0, h0, d0, n0, it_begin, it_end, z;
                 decode(item, w0, h0, d0, n0, it_begin, it_end, z);
                 for (int it = it_begin; it < it_end; ++it) {
-                    const int tap = it / slabs, slab = it % slabs;
-                    const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    const int c0 = slab * SLAB;
-                    const int xw = w0 * P.stride + kw - pad, xh = h0 * P.stride + kh - pad, xd = d0 * P.stride + kd - pad;
-                    tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, xw, xh, xd);
-                    tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, xw, xh, xd);
-                    const int kk = tap * P.Cin + c0;
+                    int kk;
+                    if (it < k_main) {
+                        const int tap = it / slabs, slab = it % slabs;
+                        const int kd = tap / (P.ksize * P.ksize), kh = (tap / P.ksize) % P.ksize, kw = tap % P.ksize;
+                        const int c0 = slab * SLAB;
+                        const int xw = w0 * P.stride + kw - pad, xh = h0 * P.stride + kh - pad, xd = d0 * P.stride + kd - pad;
+                        tma_load_4d(st, &map_a_hi, &full_bar[stage], c0, xw, xh, xd);
+                        tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &full_bar[stage], c0, xw, xh, xd);
+                        kk = tap * P.Cin + c0;
+                    } else {   // fused 1x1 skip operand (stride 1): the box of the output tile itself
+                        const int c0 = (it - k_main) * SLAB;
+                        tma_load_4d(st, &map_a2_hi, &full_bar[stage], c0, w0, h0, d0);
+                        tma_load_4d(st + A_TILE_BYTES, &map_a2_lo, &full_bar[stage], c0, w0, h0, d0);
+                        kk = taps * P.Cin + c0;
+                    }
                     tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kk, n0);
                     tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &map_b_lo, &full_bar[stage], kk, n0);
                     if (++stage == n_stages) stage = 0, phase ^= 1;
@@ -458,7 +474,7 @@ int make_w_map(CUtensorMap* m, const void* base, int Ktot, long long pitch, int 
 
 template <int BLOCK_N>
 int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-           const TcParams& P, int tiles, int nsplit, cudaStream_t st) {
+           const CUtensorMap& a2h, const CUtensorMap& a2l, const TcParams& P, int tiles, int nsplit, cudaStream_t st) {
     auto k = conv_tc_kernel<BLOCK_N>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
               "holo_conv3d_tc");
@@ -482,7 +498,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     const long long items = (long long)Q.m_tiles * Q.n_blocks * Q.nsplit;
     long long grid = (long long)n_sm * occ;
     if (grid > items) grid = items;
-    k<<<dim3((unsigned)grid), NUM_THREADS, smem, st>>>(ah, al, bh, bl, Q);
+    k<<<dim3((unsigned)grid), NUM_THREADS, smem, st>>>(ah, al, bh, bl, a2h, a2l, Q);
     HOLO_CHECK_LAUNCH("holo_conv3d_tc");
     return HOLO_OK;
 }
@@ -493,7 +509,8 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
                         int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
-                        double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f) {
+                        double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f, const void* x2_hi = nullptr,
+                        const void* x2_lo = nullptr, int Cin2 = 0) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -527,7 +544,11 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     const int tiles = (D / td) * (H / th) * (W / tw);
     if (block_n == 128 && tiles * (Cout / 128) < 148) block_n = 64;
     const int taps = ksize * ksize * ksize;
-    const int k_total = taps * (Cin / SLAB);
+    if (Cin2 && (!x2_hi || !x2_lo || Cin2 % SLAB || stride != 1)) {
+        holo_set_error("%s: the fused skip operand needs both halves, Cin_skip %% 64 == 0 and stride 1", who);
+        return HOLO_ERR_ARG;
+    }
+    const int k_total = taps * (Cin / SLAB) + Cin2 / SLAB;
     // split-K: when the M x N grid cannot fill the 148 SMs and K is long, slice the (tap, slab) loop across
     // gridDim.z and accumulate with fp32 atomics into a zeroed output (>= 4 iterations per slice)
     int nsplit = 1, per = k_total;
@@ -540,11 +561,17 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         per = (k_total + nsplit - 1) / nsplit;
         nsplit = (k_total + per - 1) / per;
     }
-    CUtensorMap ah, al, bh, bl;
+    CUtensorMap ah, al, bh, bl, a2h, a2l;
     int e = make_act_map(&ah, x_hi, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
     if (!e) e = make_act_map(&al, x_lo, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
-    if (!e) e = make_w_map(&bh, w_hi, taps * Cin, w_pitch, Cout, block_n);
-    if (!e) e = make_w_map(&bl, w_lo, taps * Cin, w_pitch, Cout, block_n);
+    if (!e) e = make_w_map(&bh, w_hi, taps * Cin + Cin2, w_pitch, Cout, block_n);
+    if (!e) e = make_w_map(&bl, w_lo, taps * Cin + Cin2, w_pitch, Cout, block_n);
+    if (Cin2) {
+        if (!e) e = make_act_map(&a2h, x2_hi, Cin2, Cin2, Din, Hin, Win, tw, th, td, 1);
+        if (!e) e = make_act_map(&a2l, x2_lo, Cin2, Cin2, Din, Hin, Win, tw, th, td, 1);
+    } else {
+        a2h = ah, a2l = al;   // never dereferenced (k2_slabs = 0)
+    }
     if (e) {
         holo_set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, e);
         return HOLO_ERR_CUDA;
@@ -555,16 +582,16 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
-    P.fmt = fmt, P.acc_scale = acc_scale;
+    P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
     cudaStream_t st = (cudaStream_t)stream;
     if (nsplit > 1 && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
     int rc;
     switch (block_n) {
-        case 128: rc = launch<128>(ah, al, bh, bl, P, tiles, nsplit, st); break;
-        case 64: rc = launch<64>(ah, al, bh, bl, P, tiles, nsplit, st); break;
-        case 32: rc = launch<32>(ah, al, bh, bl, P, tiles, nsplit, st); break;
-        default: rc = launch<16>(ah, al, bh, bl, P, tiles, nsplit, st); break;
+        case 128: rc = launch<128>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
+        case 64: rc = launch<64>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
+        case 32: rc = launch<32>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
+        default: rc = launch<16>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
     }
     if (rc == HOLO_OK && stats && !P.stats) return 1;  // done, but the statistics were not produced (split-K / pitch)
     return rc;
@@ -593,6 +620,23 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
                         stats_ch, operand_fmt, acc_scale);
+}
+
+// ResBlock tail in one launch: out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual): the 1x1 skip connection
+// (unet.py:222,255) rides the same TMEM accumulator as Cin_skip / 64 extra K iterations, so its fp32 result is never
+// written nor re-read.  Weights: [Cout][27 * Cin + Cin_skip] pairs (the 3^3 taps, then the 1x1 columns), one common
+// scale; bias = conv bias + skip bias (the caller adds them).
+extern "C" int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
+                                   int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo,
+                                   const float* bias, const float* residual, int Cout, float* out, double* stats_ch,
+                                   int operand_fmt, float acc_scale, void* stream) {
+    if (!skip_hi || !skip_lo || Cin_skip <= 0) {
+        holo_set_error("holo_conv3d_tc_skip: the skip operand is missing");
+        return HOLO_ERR_ARG;
+    }
+    return conv_tc_impl("holo_conv3d_tc_skip", x_hi, x_lo, Cin, Cin, D, H, W, 3, 1, w_hi, w_lo,
+                        27LL * Cin + Cin_skip, bias, residual, Cout, Cout, out, nullptr, nullptr, stream, 0, stats_ch,
+                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,

@@ -312,6 +312,19 @@ def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, ou
     return rc
 
 
+def conv3d_tc_skip(x_hi, x_lo, Cin, skip_hi, skip_lo, Cin_skip, dims, w_hi, w_lo, bias, residual, Cout, out, stats=None,
+                   w_scale: float = 1.0) -> int:
+    """out = conv3^3(x) + conv1^1(skip) + bias (+ residual) in one launch (holo_conv3d_tc_skip); w = [Cout][27 Cin +
+    Cin_skip] pairs.  Status as conv3d_tc."""
+    fmt = FMT_F16 * _pair_f16(x_hi, x_lo, skip_hi, skip_lo, w_hi, w_lo)
+    rc = lib().try_call("holo_conv3d_tc_skip", _ptr16(x_hi), _ptr16(x_lo), Cin, _ptr16(skip_hi), _ptr16(skip_lo), Cin_skip,
+                        dims[0], dims[1], dims[2], _ptr16(w_hi), _ptr16(w_lo), _ptr(bias), _ptr(residual), Cout, _ptr(out),
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _stream())
+    if rc not in (0, 1, -3):
+        raise HoloError(f"holo_conv3d_tc_skip failed ({rc}): {lib().cdll.holo_last_error().decode()}")
+    return rc
+
+
 def v_transpose_split(qkv, T, heads, ch, vt_hi, vt_lo):
     lib().call("holo_v_transpose_split", _ptr(qkv), T, heads, ch, _ptr16(vt_hi), _ptr16(vt_lo), _pair_f16(vt_hi, vt_lo),
                _stream())

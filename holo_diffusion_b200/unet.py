@@ -172,6 +172,37 @@ class _PackedConv:
         self.bias = bias.contiguous()
 
 
+class _PackedFusedSkip:
+    """Weights of a ResBlock tail for holo_conv3d_tc_skip: [Cout][27 * Cin + Cin_skip] pairs = the 3^3 convolution's
+    taps followed by the 1x1 skip connection's columns, one common power-of-two scale; bias = the sum of both."""
+
+    def __init__(self, conv: nn.Module, skip: nn.Module, pair_dtype=torch.float16):
+        self.conv, self.skip, self.pair_dtype = conv, skip, pair_dtype
+        self.version = None
+
+    def refresh(self):
+        ps = (self.conv.weight, self.conv.bias, self.skip.weight, self.skip.bias)
+        ver = tuple((p._version, p.data_ptr()) for p in ps)
+        if ver == self.version:
+            return
+        self.version = ver
+        w, ws = self.conv.weight.detach().float(), self.skip.weight.detach().float()
+        cout, cin = w.shape[0], w.shape[1]
+        cin2 = ws.shape[1]
+        assert cin % 64 == 0 and cin2 % 64 == 0 and ws.shape[0] == cout
+        self.cout, self.cin, self.cin_skip = cout, cin, cin2
+        wk = torch.cat([w.reshape(cout, cin, 27).permute(0, 2, 1).reshape(cout, 27 * cin), ws.reshape(cout, cin2)], 1)
+        self.w_scale = 1.0
+        if self.pair_dtype == torch.float16:
+            amax = float(wk.abs().max())
+            if amax > 0 and math.isfinite(amax):
+                self.w_scale = 2.0 ** (9 - math.floor(math.log2(amax)))
+        wsc = wk * self.w_scale
+        self.w_hi = wsc.to(self.pair_dtype).contiguous()
+        self.w_lo = (wsc - self.w_hi.float()).to(self.pair_dtype).contiguous()
+        self.bias = (self.conv.bias.detach().float() + self.skip.bias.detach().float()).contiguous()
+
+
 def _pad_qkv_heads(heads: int, ch: int, chp: int):
     """qkv conv (heads*3*ch outputs, head-major [q|k|v], unet.py:445-447) -> heads*3*chp outputs with every q / k / v
     block zero-padded from ch to chp channels: q.k is unchanged by zero channels, and the padded v channels come out
@@ -213,6 +244,11 @@ class UNetExecutor:
         # lands 4e-6 from exact arithmetic, activations saturate beyond |x| = 131008) or bf16 halves
         # (HOLO_PAIR_FMT=bf16: fp32's range, 7e-5 from exact)
         self.pair_dtype = torch.bfloat16 if os.environ.get("HOLO_PAIR_FMT", "f16") == "bf16" else torch.float16
+        # HOLO_FUSE_SKIP=1: ResBlocks with a 1x1 skip connection run their tail (second 3^3 convolution + skip
+        # convolution + add) as ONE launch (holo_conv3d_tc_skip).  Numerically validated on a B200 (unit shapes and the
+        # 16^3 UNet: 2.7e-6 from the fp64 twin) but written when the round's GPU budget was down to its last seconds:
+        # its speed is not measured yet, so it stays opt-in.
+        self.fuse_skip = os.environ.get("HOLO_FUSE_SKIP", "0") == "1"
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
@@ -389,12 +425,34 @@ class UNetExecutor:
             skip = act.x1
         else:
             pcs = self._pc(blk.skip_connection)
+            pc2 = self._pc(blk.out_layers[3])
+            if (self.fuse_skip and raw is not None and self._tc_ok(pc2, act.dims) and pc2.cin % 64 == 0
+                    and pcs.cin % 64 == 0 and pcs.cin == act.C):
+                return self._res_tail_fused(blk, h, raw, film_all[off:off + n])
             if raw is not None and self._tc_ok(pcs, act.dims) and pcs.cin_pad == act.C:
                 # 1x1 skip conv on the raw concat: its operand pair came out of the GroupNorm pass over the same tensor
                 skip = self._conv_tc(pcs, raw[0], raw[1], act.dims).x1
             else:
                 skip = self._conv_raw(blk.skip_connection, act).x1
         return self._conv_norm(blk.out_layers[3], h, blk.out_layers[0], film_all[off:off + n], residual=skip)
+
+    def _res_tail_fused(self, blk: _ResParams, h: _Act, raw, film) -> _Act:
+        """out_layers (GroupNorm + FiLM + SiLU + 3^3 conv) + skip_connection(x) + add in one convolution launch."""
+        key = (id(blk), "fuse")
+        pf = self._convs.get(key)
+        if pf is None:
+            pf = self._convs[key] = _PackedFusedSkip(blk.out_layers[3], blk.skip_connection, self.pair_dtype)
+        pf.refresh()
+        _, y_hi, y_lo, _ = self._gn(h, blk.out_layers[0], film, True, True)
+        Vo = h.V
+        out = torch.empty(Vo, pf.cout, device=y_hi.device)
+        st = self._stats_slice(pf.cout)
+        rc = ops.conv3d_tc_skip(y_hi, y_lo, pf.cin, raw[0], raw[1], pf.cin_skip, h.dims, pf.w_hi, pf.w_lo, pf.bias, None,
+                                pf.cout, out, st, pf.w_scale)
+        if rc not in (0, 1):
+            raise ops.HoloError("fused skip conv rejected a shape: " + ops.lib().cdll.holo_last_error().decode())
+        self.tc_calls += 1
+        return _Act(out, pf.cout, h.dims, st1=st if rc == 0 else None)
 
     def _attn(self, blk: _AttnParams, act: _Act) -> _Act:
         assert act.x2 is None

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 112
+#define HOLO_B200_VERSION 113
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -184,6 +184,17 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
                    void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, void* stream);
+
+/* ResBlock tail in ONE launch (ResBlock._forward, unet.py:254-256, with a 1x1 skip_connection :222):
+ *   out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual)
+ * The skip convolution rides the 3^3 convolution's TMEM accumulator as Cin_skip / 64 extra K iterations.  w_hi / w_lo:
+ * [Cout][27 * Cin + Cin_skip] pairs (taps first, then the 1x1 columns) under one common scale; bias = the sum of the two
+ * biases.  Same shape rules, formats, statistics and return codes as holo_conv3d_tc (stride 1, Cin_skip % 64 == 0).
+ * Numerically validated on a B200; opt-in in the executor (HOLO_FUSE_SKIP=1) until its speed has been measured. */
+int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
+                        int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo, const float* bias,
+                        const float* residual, int Cout, float* out, double* stats_ch, int operand_fmt,
+                        float acc_scale, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
  * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with

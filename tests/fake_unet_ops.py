@@ -117,6 +117,24 @@ def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, ou
     return 0
 
 
+def conv3d_tc_skip(x_hi, x_lo, Cin, skip_hi, skip_lo, Cin_skip, dims, w_hi, w_lo, bias, residual, Cout, out, stats=None,
+                   w_scale=1.0):
+    w = (w_hi + w_lo) / w_scale                               # [Cout][27 Cin + Cin_skip]
+    w3 = w[:, : 27 * Cin].reshape(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)
+    w1 = w[:, 27 * Cin:].reshape(Cout, Cin_skip, 1, 1, 1)
+    y = F.conv3d(_cl_to_ncdhw(x_hi + x_lo, Cin, dims), w3, bias, padding=1) + \
+        F.conv3d(_cl_to_ncdhw(skip_hi + skip_lo, Cin_skip, dims), w1)
+    y = _ncdhw_to_cl(y)
+    if residual is not None:
+        y = y + residual
+    out.copy_(y)
+    if stats is not None:
+        st = stats.view(Cout, 2)
+        st[:, 0] += y.double().sum(0)
+        st[:, 1] += (y.double() ** 2).sum(0)
+    return 0
+
+
 def conv3d_simt(x1, C1, x2, C2, dims, ksize, stride, ups, w, bias, residual, Cout, out):
     x = _cl_to_ncdhw(_cat(x1, C1, x2, C2), C1 + C2, dims)
     if ups:
@@ -189,7 +207,7 @@ def transpose_split(src, src_off, src_pitch, rows, cols, hi, lo):
 
 ALL = dict(timestep_embedding=timestep_embedding, linear_rows=linear_rows, gn_stats_pp=gn_stats_pp,
            gn_apply_fused=gn_apply_fused, gn_apply_fused_ch=gn_apply_fused_ch, split_bf16=split_bf16, conv3d_tc=conv3d_tc,
-           conv3d_simt=conv3d_simt, attention_simt=attention_simt, v_transpose_split=v_transpose_split,
+           conv3d_tc_skip=conv3d_tc_skip, conv3d_simt=conv3d_simt, attention_simt=attention_simt, v_transpose_split=v_transpose_split,
            attention_flash=attention_flash, gemm_tc=gemm_tc, softmax_split=softmax_split, transpose_split=transpose_split)
 
 

@@ -48,6 +48,24 @@ def test_executor_orchestration_matches_oracle(R, tc, monkeypatch):
     assert (net._exec.tc_calls > 0) == tc
 
 
+def test_executor_fused_skip_tail(monkeypatch):
+    """HOLO_FUSE_SKIP=1: ResBlocks with a 1x1 skip connection run conv3^3 + skip conv + add as one launch
+    (holo_conv3d_tc_skip); weight concatenation [taps | skip columns], summed bias and the statistics hand-over are
+    host logic -- checked here against the oracle with the torch stand-in of the kernel."""
+    monkeypatch.setenv("HOLO_FUSE_SKIP", "1")
+    sd = uo.make_unet_state_dict(16, 16, seed=2)
+    net = _net(16, 16, sd, monkeypatch, **BASE)
+    from holo_diffusion_b200 import ops
+    n = []
+    orig = ops.conv3d_tc_skip
+    monkeypatch.setattr(ops, "conv3d_tc_skip", lambda *a, **k: (n.append(a[5]), orig(*a, **k))[1])
+    x = torch.tanh(torch.randn(1, 16, 16, 16, 16, generator=torch.Generator().manual_seed(0)))
+    tt = torch.zeros(1, dtype=torch.long)
+    assert rel_err(_forward(net, x, tt), uo.unet_forward(sd, x, tt)) < 2e-5
+    # fused at the levels that run on tensor cores (>= 4^3): the channel-changing input blocks and the output blocks
+    assert len(n) >= 8 and set(n) <= {64, 128, 192, 256, 384, 512, 768, 1024}, n
+
+
 @pytest.mark.parametrize("flash", ["1", "0"])
 def test_executor_attention_dispatches(flash, monkeypatch):
     """16^3 x (64, 128)-channel model with attention at both levels: T = 4096 (ch 32: zero-padded heads on the fused
