@@ -168,6 +168,13 @@ struct FlashParams {
     __nv_bfloat16* out_hi;  // (T, C) hi/lo split of the result (same 16-bit format as the inputs), or null
     __nv_bfloat16* out_lo;
     int q_tile0;            // first 128-query tile of this launch (query-sharded attention: a rank owns a tile range)
+    // split-KV (gridDim.z > 1): CTA z handles key tiles [z * kt_per_split, ...) with its OWN stabiliser m_z and writes
+    // the un-normalised O_z (part_o: [z][T][C] fp32) and (m_z * scale_log2, rowsum_z) (part_ml: [z][heads][T] float2);
+    // flash_combine_kernel merges: O = sum_z 2^(m_z - M) O_z / sum_z 2^(m_z - M) l_z.  Fills the 148 SMs when
+    // (T / 128) x heads is small (64 CTAs at T = 4096, 8 at T = 512).
+    int kt_per_split;
+    float* part_o;
+    float2* part_ml;
 };
 
 // F16: every operand pair (q, k, v^T in, P inside, the output pair) has fp16 halves instead of bf16.  The logits'
@@ -199,7 +206,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m0 = (P.q_tile0 + (int)blockIdx.x) * BM;
     const int head = blockIdx.y;
-    const int NT = P.T / BN;        // key tiles per pass
+    const int kt0 = (int)blockIdx.z * P.kt_per_split;                     // first key tile of this CTA's share
+    const int NT = min(P.T / BN - kt0, P.kt_per_split);                   // key tiles per pass (all of them unsplit)
     const int n_jobs = 2 * NT;      // S jobs: pass A (max) then pass B (exp + PV)
     const int col_q = head * 3 * CH, col_k = col_q + CH;
 
@@ -240,7 +248,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 const int stage = j % F::STAGES;
                 const uint32_t phase = (uint32_t)(j / F::STAGES) & 1u;
                 const bool with_v = j >= NT;
-                const int n0 = (with_v ? j - NT : j) * BN;
+                const int n0 = (kt0 + (with_v ? j - NT : j)) * BN;
                 mbar_wait(&kv_empty[stage], phase ^ 1u);
                 uint8_t* st = kv_smem + stage * F::STAGE_BYTES;
                 mbar_expect_tx(&kv_full[stage], (uint32_t)(F::K_BYTES + (with_v ? F::V_BYTES : 0)));
@@ -383,10 +391,28 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         tc_fence_after();
         xch[half * BM + row] = l0 + l1;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = 1.0f / (xch[row] + xch[BM + row]);
+        const float lsum = xch[row] + xch[BM + row];
         const int t = m0 + row;
         const bool ok = t < P.T;
         const size_t obase = (size_t)t * P.C + (size_t)head * CH;
+        if (gridDim.z > 1) {
+            // split-KV: this CTA's share of the keys only -- leave O un-normalised for flash_combine_kernel
+            if (ok && half == 0) P.part_ml[((size_t)blockIdx.z * P.heads + head) * P.T + t] = make_float2(msc, lsum);
+            float* po = P.part_o + (size_t)blockIdx.z * P.T * P.C + obase;
+#pragma unroll 1
+            for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
+                tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
+                if (ok) {
+                    float4* op = reinterpret_cast<float4*>(po + c0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        op[c4] = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                             __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+                }
+            }
+            tc_fence_before();
+        } else {
+        const float inv = 1.0f / lsum;
 #pragma unroll 1
         for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
             tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
@@ -414,11 +440,54 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// Merge of the split-KV partials: thread = 8 channels of one query row.
+__global__ void flash_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int splits,
+                                     int T, int heads, int ch, int q_begin, int q_count, float* __restrict__ out,
+                                     uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int pair_f16) {
+    const int C = heads * ch;
+    const int c8 = C / 8;
+    const long long total = (long long)q_count * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = q_begin + (int)(i / c8);
+        const int c = (int)(i % c8) * 8;
+        const int head = c / ch;
+        float M = -INFINITY;
+        for (int z = 0; z < splits; ++z) M = fmaxf(M, part_ml[((size_t)z * heads + head) * T + t].x);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float l = 0.f;
+        for (int z = 0; z < splits; ++z) {
+            const float2 ml = part_ml[((size_t)z * heads + head) * T + t];
+            const float w = exp2f(ml.x - M);
+            l = fmaf(w, ml.y, l);
+            const float4* po = reinterpret_cast<const float4*>(part_o + ((size_t)z * T + t) * C + c);
+            const float4 a = po[0], b = po[1];
+            acc[0] = fmaf(w, a.x, acc[0]), acc[1] = fmaf(w, a.y, acc[1]), acc[2] = fmaf(w, a.z, acc[2]), acc[3] = fmaf(w, a.w, acc[3]);
+            acc[4] = fmaf(w, b.x, acc[4]), acc[5] = fmaf(w, b.y, acc[5]), acc[6] = fmaf(w, b.z, acc[6]), acc[7] = fmaf(w, b.w, acc[7]);
+        }
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= inv;
+        const size_t o = (size_t)t * C + c;
+        if (out) {
+            *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(out + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (out_hi) {
+            uint32_t h[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) holo_split2(acc[2 * k], acc[2 * k + 1], pair_f16 != 0, h[k], lo[k]);
+            *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
@@ -475,11 +544,11 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
 }
 
 template <int CH, bool F16>
-int launch_flash(const CUtensorMap* maps, const FlashParams& P, int q_tiles, cudaStream_t st) {
+int launch_flash(const CUtensorMap* maps, const FlashParams& P, int q_tiles, int splits, cudaStream_t st) {
     auto k = attn_flash_kernel<CH, F16>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<CH>::SMEM_BYTES),
               "holo_attention_flash");
-    dim3 grid((unsigned)q_tiles, (unsigned)P.heads);
+    dim3 grid((unsigned)q_tiles, (unsigned)P.heads, (unsigned)splits);
     k<<<grid, NTHREADS, FCfg<CH>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
     HOLO_CHECK_LAUNCH("holo_attention_flash");
     return HOLO_OK;
@@ -500,7 +569,7 @@ extern "C" int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int
 extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
                                     const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi_bf16,
                                     void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count,
-                                    void* stream) {
+                                    int kv_splits, void* workspace, void* stream) {
     void* out_lo_bf16 = out_lo;
     HOLO_CHECK_ARG(qkv_hi_bf16 && qkv_lo_bf16 && vt_hi_bf16 && vt_lo_bf16, "holo_attention_flash: null input");
     HOLO_CHECK_ARG(out_cl || out_hi_bf16, "holo_attention_flash: no output requested");
@@ -531,8 +600,37 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
     P.out = out_cl, P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     P.q_tile0 = q_begin / BM;
     const int q_tiles = (q_count + BM - 1) / BM;
+    // split-KV: kv_splits CTAs share the key tiles of one (query tile, head); needs the caller's workspace
+    const int nt_all = T / BN;
+    int splits = kv_splits < 1 ? 1 : (kv_splits > nt_all ? nt_all : kv_splits);
+    P.kt_per_split = (nt_all + splits - 1) / splits;
+    splits = (nt_all + P.kt_per_split - 1) / P.kt_per_split;
+    P.part_o = nullptr, P.part_ml = nullptr;
+    if (splits > 1) {
+        HOLO_CHECK_ARG(workspace, "holo_attention_flash: kv_splits > 1 needs a workspace of "
+                                  "holo_attention_flash_workspace_bytes(T, heads, ch, kv_splits)");
+        P.part_o = reinterpret_cast<float*>(workspace);
+        P.part_ml = reinterpret_cast<float2*>(P.part_o + (size_t)splits * T * C);
+    }
     cudaStream_t st = (cudaStream_t)stream;
+    int rc;
     if (pair_f16)
-        return ch == 64 ? launch_flash<64, true>(maps, P, q_tiles, st) : launch_flash<128, true>(maps, P, q_tiles, st);
-    return ch == 64 ? launch_flash<64, false>(maps, P, q_tiles, st) : launch_flash<128, false>(maps, P, q_tiles, st);
+        rc = ch == 64 ? launch_flash<64, true>(maps, P, q_tiles, splits, st) : launch_flash<128, true>(maps, P, q_tiles, splits, st);
+    else
+        rc = ch == 64 ? launch_flash<64, false>(maps, P, q_tiles, splits, st)
+                      : launch_flash<128, false>(maps, P, q_tiles, splits, st);
+    if (rc != HOLO_OK || splits == 1) return rc;
+    const long long total = (long long)q_count * (C / 8);
+    int blocks = holo_cdiv(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    flash_combine_kernel<<<blocks, 256, 0, st>>>(P.part_o, P.part_ml, splits, T, heads, ch, q_begin, q_count, out_cl,
+                                                 (uint16_t*)out_hi_bf16, (uint16_t*)out_lo_bf16, pair_f16);
+    HOLO_CHECK_LAUNCH("holo_attention_flash (combine)");
+    return HOLO_OK;
+}
+
+extern "C" long long holo_attention_flash_workspace_bytes(int T, int heads, int ch, int kv_splits) {
+    if (kv_splits <= 1) return 0;
+    const long long C = (long long)heads * ch;
+    return (long long)kv_splits * T * C * 4 + (long long)kv_splits * heads * T * 8;
 }

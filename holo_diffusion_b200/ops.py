@@ -330,14 +330,21 @@ def v_transpose_split(qkv, T, heads, ch, vt_hi, vt_lo):
                _stream())
 
 
+def attention_flash_workspace(T, heads, ch, kv_splits: int, device) -> Optional[torch.Tensor]:
+    n = lib().cdll.holo_attention_flash_workspace_bytes(T, heads, ch, kv_splits)
+    return torch.empty(n, dtype=torch.uint8, device=device) if n > 0 else None
+
+
 def attention_flash(qkv_hi, qkv_lo, vt_hi, vt_lo, T, heads, ch, out=None, out_hi=None, out_lo=None,
-                    softmax_scale: float = 0.0, q_begin: int = 0, q_count: int = 0) -> int:
+                    softmax_scale: float = 0.0, q_begin: int = 0, q_count: int = 0, kv_splits: int = 1,
+                    workspace=None) -> int:
     """Fused attention on tcgen05 (holo_attention_flash).  Returns 0, or -3 for a shape the kernel does not take.
-    softmax_scale 0 = ch^-1/2; (q_begin, q_count) restricts the launch to a query range (0, 0 = all)."""
+    softmax_scale 0 = ch^-1/2; (q_begin, q_count) restricts the launch to a query range (0, 0 = all); kv_splits > 1
+    shares the keys of a query tile between that many CTAs (workspace from attention_flash_workspace)."""
     rc = lib().try_call("holo_attention_flash", _ptr16(qkv_hi), _ptr16(qkv_lo), _ptr16(vt_hi), _ptr16(vt_lo), T,
                         heads, ch, _ptr(out), _ptr16(out_hi), _ptr16(out_lo),
                         _pair_f16(qkv_hi, qkv_lo, vt_hi, vt_lo, out_hi, out_lo), float(softmax_scale), int(q_begin),
-                        int(q_count), _stream())
+                        int(q_count), int(kv_splits), _ptr(workspace, torch.uint8), _stream())
     if rc not in (0, -3):
         raise HoloError(f"holo_attention_flash failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc

@@ -227,6 +227,15 @@ def _pad_proj_heads(heads: int, ch: int, chp: int):
     return remap
 
 
+def kv_split_for(T: int, heads: int, mode: str, n_sm: int = 148) -> int:
+    """Number of CTAs that share the key tiles of one (128-query tile, head) of the fused attention: "1" = off,
+    "<n>" = fixed, "auto" = as many as keep the grid within the SM count, with at least 2 of the T / 64 key tiles each."""
+    if mode != "auto":
+        return max(1, int(mode))
+    ctas = ((T + 127) // 128) * heads
+    return max(1, min((T // 64) // 2, n_sm // ctas))
+
+
 def _tile_ok(dims) -> bool:
     D, H, W = dims  # the TMA box is 8 (w) x 4 (h) x 4 (d) voxels, or 4 x 4 x 4 for the coarsest levels
     return W % 4 == 0 and H % 4 == 0 and D % 4 == 0
@@ -249,6 +258,10 @@ class UNetExecutor:
         # 16^3 UNet: 2.7e-6 from the fp64 twin) but written when the round's GPU budget was down to its last seconds:
         # its speed is not measured yet, so it stays opt-in.
         self.fuse_skip = os.environ.get("HOLO_FUSE_SKIP", "0") == "1"
+        # HOLO_ATTN_KV_SPLIT=auto | <n>: split the keys of every (query tile, head) of the fused attention over n CTAs
+        # (auto: fill ~148 SMs, >= 2 key tiles per CTA) + a merge kernel.  Opt-in: written after the round's GPU budget
+        # was spent, NOT yet run on a B200 (the merge arithmetic and the dispatch are covered on the CPU).
+        self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "1")
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
@@ -493,7 +506,10 @@ class UNetExecutor:
             if world == 1:
                 a_hi = torch.empty(T, Cp, device=dev, dtype=self.pair_dtype)
                 a_lo = torch.empty(T, Cp, device=dev, dtype=self.pair_dtype)
-                rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, a_hi, a_lo, scale)
+                splits = kv_split_for(T, heads, self.attn_kv_split)
+                ws = ops.attention_flash_workspace(T, heads, chp, splits, dev) if splits > 1 else None
+                rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, a_hi, a_lo, scale,
+                                         kv_splits=splits, workspace=ws)
                 assert rc == 0
             else:
                 a_hi, a_lo = self._attn_sharded(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, scale, world, rank)

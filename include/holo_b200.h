@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 113
+#define HOLO_B200_VERSION 114
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -225,12 +225,17 @@ int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, i
  * q_begin / q_count: only queries [q_begin, q_begin + q_count) are computed and written (rows of the full-size
  * outputs) -- the query-sharded multi-GPU form, every rank holding all keys / values; q_begin % 128 == 0, the range
  * ends on a multiple of 128 or at T; q_count <= 0 = all queries.
+ * kv_splits > 1 (opt-in): that many CTAs share the key tiles of one (query tile, head), each with its own softmax
+ * stabiliser, and a small merge kernel combines the partial results -- fills the 148 SMs when (T / 128) x heads is
+ * small (64 CTAs at T = 4096).  Needs `workspace` of holo_attention_flash_workspace_bytes() bytes (device memory).
  * ch in {64, 128}, T % 64 == 0; other shapes return HOLO_ERR_UNSUPPORTED (-3). */
 int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi, void* vt_lo, int pair_f16,
                            void* stream);
 int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
                          const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi,
-                         void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count, void* stream);
+                         void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count, int kv_splits,
+                         void* workspace, void* stream);
+long long holo_attention_flash_workspace_bytes(int T, int heads, int ch, int kv_splits);
 
 /* QKVAttentionLegacy.forward -- unet.py:438-455.  qkv_cl (T, heads*3*ch) head-major [q|k|v]; out_cl (T, heads*ch). */
 int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* out_cl, void* stream);

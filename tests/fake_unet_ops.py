@@ -159,8 +159,12 @@ def v_transpose_split(qkv, T, heads, ch, vt_hi, vt_lo):
     vt_lo.zero_()
 
 
+def attention_flash_workspace(T, heads, ch, kv_splits, device):
+    return None
+
+
 def attention_flash(qkv_hi, qkv_lo, vt_hi, vt_lo, T, heads, ch, out=None, out_hi=None, out_lo=None, softmax_scale=0.0,
-                    q_begin=0, q_count=0):
+                    q_begin=0, q_count=0, kv_splits=1, workspace=None):
     if q_count <= 0:
         q_begin, q_count = 0, T
     qkv = (qkv_hi + qkv_lo).reshape(T, heads, 3, ch)
@@ -208,7 +212,7 @@ def transpose_split(src, src_off, src_pitch, rows, cols, hi, lo):
 ALL = dict(timestep_embedding=timestep_embedding, linear_rows=linear_rows, gn_stats_pp=gn_stats_pp,
            gn_apply_fused=gn_apply_fused, gn_apply_fused_ch=gn_apply_fused_ch, split_bf16=split_bf16, conv3d_tc=conv3d_tc,
            conv3d_tc_skip=conv3d_tc_skip, conv3d_simt=conv3d_simt, attention_simt=attention_simt, v_transpose_split=v_transpose_split,
-           attention_flash=attention_flash, gemm_tc=gemm_tc, softmax_split=softmax_split, transpose_split=transpose_split)
+           attention_flash=attention_flash, attention_flash_workspace=attention_flash_workspace, gemm_tc=gemm_tc, softmax_split=softmax_split, transpose_split=transpose_split)
 
 
 def install(ops_module, setattr_fn=setattr):

@@ -286,3 +286,32 @@ def test_intree_golden_is_reproducible_from_the_reference():
             assert np.allclose(a, b_, rtol=0, atol=1e-6), k
         else:
             assert (a == b_).all(), k
+
+
+def test_split_kv_merge_arithmetic_and_dispatch():
+    """Split-KV fused attention (holo_attention_flash kv_splits > 1): each share of the keys is reduced against its OWN
+    stabiliser m_z; the merge O = sum_z 2^(m_z - M) O_z / sum_z 2^(m_z - M) l_z (flash_combine_kernel) must reproduce
+    the un-split softmax for ANY stabilisers.  Restated here in torch; plus the executor's choice of the split count."""
+    import math
+    from holo_diffusion_b200.unet import kv_split_for
+    g = torch.Generator().manual_seed(9)
+    T, ch, splits = 256, 16, 4
+    q, k, v = (torch.randn(T, ch, generator=g, dtype=torch.float64) for _ in range(3))
+    scale_log2 = (1 / math.sqrt(ch)) * math.log2(math.e)
+    s = q @ k.t()
+    ref = torch.softmax(s / math.sqrt(ch), -1) @ v
+    per = T // splits
+    parts = []
+    for z in range(splits):
+        sz = s[:, z * per:(z + 1) * per]
+        m = sz.max(-1, keepdim=True).values + torch.rand(T, 1, generator=g, dtype=torch.float64)   # an inexact stabiliser
+        p = torch.exp2(sz * scale_log2 - m * scale_log2)
+        parts.append((m * scale_log2, p.sum(-1, keepdim=True), p @ v[z * per:(z + 1) * per]))
+    M = torch.stack([m for m, _, _ in parts]).max(0).values
+    num = sum(torch.exp2(m - M) * o for m, _, o in parts)
+    den = sum(torch.exp2(m - M) * l for m, l, _ in parts)
+    assert torch.allclose(num / den, ref, rtol=0, atol=1e-12)
+    assert kv_split_for(4096, 2, "1") == 1 and kv_split_for(4096, 2, "3") == 3
+    assert kv_split_for(4096, 2, "auto") == 2        # 64 CTAs -> 128
+    assert kv_split_for(512, 2, "auto") == 4         # 8 CTAs, 8 key tiles -> 2 tiles per CTA
+    assert kv_split_for(64, 1, "auto") == 1 and kv_split_for(32768, 2, "auto") == 1

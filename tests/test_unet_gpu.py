@@ -608,3 +608,35 @@ def test_unet_fused_skip_tail(monkeypatch):
     e64 = rel_err(out, uo.unet_forward({k: v.double() for k, v in sd.items()}, x.double(), tt))
     print(f"unet 16^3 fused skip tails: vs fp64 twin {e64:.2e}")
     assert e64 < 2e-5
+
+
+@_UNVALIDATED
+@pytest.mark.parametrize("T,heads,ch,splits", [(4096, 2, 64, 2), (512, 2, 128, 4), (1024, 1, 64, 3), (192, 1, 64, 2)])
+def test_attention_flash_split_kv(T, heads, ch, splits):
+    """kv_splits > 1: the keys of a query tile shared between CTAs + flash_combine_kernel, against the un-split launch
+    and the fp64 einsum (uneven shares: 16 key tiles over 3, 3 over 2)."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    C = heads * ch
+    qkv = torch.randn(1, heads * 3 * ch, T, generator=g) * 1.5
+    q, k, v = qkv.reshape(heads, 3 * ch, T).double().split(ch, 1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) / math.sqrt(ch), -1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(C, T).t()
+    x = qkv[0].t().contiguous().cuda()
+    hi = torch.empty(T, 3 * C, device="cuda", dtype=torch.float16)
+    lo = torch.empty_like(hi)
+    ops.split_bf16(x, T, 3 * C, 3 * C, hi, lo)
+    vt_hi = torch.empty(C, T, device="cuda", dtype=torch.float16)
+    vt_lo = torch.empty_like(vt_hi)
+    ops.v_transpose_split(x, T, heads, ch, vt_hi, vt_lo)
+    one = torch.empty(T, C, device="cuda")
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, one) == 0
+    ws = ops.attention_flash_workspace(T, heads, ch, splits, "cuda")
+    out = torch.full((T, C), float("nan"), device="cuda")
+    o_hi = torch.empty(T, C, device="cuda", dtype=torch.float16)
+    o_lo = torch.empty_like(o_hi)
+    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, out, o_hi, o_lo, kv_splits=splits, workspace=ws) == 0
+    torch.cuda.synchronize()
+    print(f"split-KV T={T} ch={ch} x{splits}: vs un-split {rel_err(out, one):.2e}, vs fp64 {rel_err(out, ref):.2e}")
+    assert rel_err(out, one) < 2e-6 and rel_err(out, ref) < 4e-5
+    assert rel_err(o_hi.float() + o_lo.float(), out) < 5e-7
