@@ -1,10 +1,10 @@
 """Where does the denoiser's distance to the reference come from?  Runs the base-args UNet on a synthetic grid
 through our kernels and through the oracle restatement (torch ops on the same GPU, fp32 with TF32 off, or fp64 with
 --f64) and prints the relative error after every block (input_blocks.i / middle_block / output_blocks.i / out).
-Diagnostic tool (uses oracle/): never part of the product path or of bench.py.
+Test-side diagnostic (it executes oracle/, so it lives under tests/): never part of the product path or of bench.py.
 
-  python tools/unet_error_trace.py --resol 64 --channels 32 [--f64] [--no-tc]
-  HOLO_PAIR_FMT=bf16 python tools/unet_error_trace.py ...      # bf16 operand pairs
+  python tests/diagnostics/unet_error_trace.py --resol 64 --channels 32 [--f64] [--no-tc]
+  HOLO_PAIR_FMT=bf16 python tests/diagnostics/unet_error_trace.py ...      # bf16 operand pairs
 """
 import argparse
 import os
@@ -12,7 +12,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
