@@ -196,12 +196,12 @@ int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void*
                         const float* residual, int Cout, float* out, double* stats_ch, int operand_fmt,
                         float acc_scale, void* stream);
 
-/* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are bf16
+/* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are 16-bit
  * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with
  * arbitrary row pitches (elements).  M % 128 == 0, K % 64 == 0, N % 16 == 0.
  * out_is_zeroed = 1 promises a zero-filled fp32 `out`, which lets small grids split K and accumulate with atomics.
  * With holo_softmax_split / holo_transpose_split_bf16 it carries QKVAttentionLegacy (unet.py:438-455) on tensor
- * cores: S = Q K^T, P = softmax(scale2 * S) (fp32, one key row per CTA, emitted as bf16 hi/lo), O = P V. */
+ * cores: S = Q K^T, P = softmax(scale2 * S) (fp32, one key row per CTA, emitted as a hi/lo pair), O = P V. */
 int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
                  const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
                  long long out_pitch, float* out, void* out_hi, void* out_lo, int out_is_zeroed, int operand_fmt,
@@ -231,8 +231,8 @@ int holo_transpose_split_bf16(const float* src, long long src_pitch, int rows, i
  * ch in {64, 128}, T % 64 == 0; other shapes return HOLO_ERR_UNSUPPORTED (-3). */
 int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi, void* vt_lo, int pair_f16,
                            void* stream);
-int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_bf16, const void* vt_hi_bf16,
-                         const void* vt_lo_bf16, int T, int heads, int ch, float* out_cl, void* out_hi,
+int holo_attention_flash(const void* qkv_hi, const void* qkv_lo, const void* vt_hi,
+                         const void* vt_lo, int T, int heads, int ch, float* out_cl, void* out_hi,
                          void* out_lo, int pair_f16, float softmax_scale, int q_begin, int q_count, int kv_splits,
                          void* workspace, void* stream);
 long long holo_attention_flash_workspace_bytes(int T, int heads, int ch, int kv_splits);
