@@ -230,8 +230,9 @@ def test_conv_tc(Cin, Cout, dims, k, fmt):
     torch.cuda.synchronize()
     assert rc == 0
     tol = 2e-5 if Cin * k ** 3 < 8192 else 4e-5   # 3xBF16 error grows ~sqrt(K); the bar is 1e-4
-    if mixed and Cin * k ** 3 < 8192:
-        tol /= 2   # long K: both formats are dominated by the tensor core's truncating fp32 accumulation (error ~ K)
+    if mixed and Cin * k ** 3 <= 1728:
+        tol = 5e-6   # measured 2.1e-7 (K = 64) ... 2.1e-6 (K = 1728); beyond that both formats are dominated by the
+        #              tensor core's truncating fp32 accumulation (error ~ K: 7.5e-6 at K = 5184) and share the bound
     err = rel_err(_from_cl(out, Cout, dims), ref)
     print(f"conv_tc {fmt} Cin={Cin} Cout={Cout} k={k}: rel err {err:.2e}")
     assert err < tol
@@ -389,7 +390,9 @@ def test_attention_flash(T, heads, ch, amp, fmt):
     torch.cuda.synchronize()
     err = rel_err(out.t().cpu()[None], ref)
     print(f"attention flash {fmt} T={T} ch={ch} amp={amp}: rel err {err:.2e}")
-    assert err < (5e-5 if fmt == "bf16" else (1e-5 if T < 4096 else 2.5e-5))
+    # T = 4096: 2.4e-5 measured with either format -- the P V product's 256 accumulation steps in TMEM (truncating
+    # fp32 adds, error ~ K) dominate there; below that fp16 pairs are 4-14x closer than bf16 pairs
+    assert err < (5e-5 if fmt == "bf16" else (1e-5 if T < 4096 else 4e-5))
     assert rel_err(o_hi.float() + o_lo.float(), out) < (2e-5 if fmt == "bf16" else 5e-7)
     # repeatable bit for bit (no atomics, fixed summation order)
     out2 = torch.empty_like(out)
