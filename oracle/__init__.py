@@ -31,6 +31,8 @@ Pinning status
   this image and from ``/root/reference`` (the stand-in implements those leaves WITH this oracle, so it cannot pin
   them); the reference's own tests only check for NaNs
   (``holo_diffusion/tests/test_voxel_grid_implicit_function.py:55,77,93,117``).  The restatement follows the published
-  pytorch3d 0.7.4 algorithm and the reference call sites cited per function.  An optional
-  ``importorskip("pytorch3d")`` tier checks it against the real thing wherever pytorch3d is installed.
+  pytorch3d 0.7.4 algorithm and the reference call sites cited per function.  Independent anchors (not pytorch3d, but
+  not this restatement either) hold the leaves in place: ``so3_exp_map`` against scipy, the trilinear sampler on linear
+  fields, the ray marcher against the closed forms of volume rendering, ``sample_pdf`` against numpy's ``interp`` of the
+  same CDF, look-at / ray geometry invariants (``tests/test_cpu_oracle_and_host.py::test_leaf_*``).
 """

@@ -315,3 +315,100 @@ def test_split_kv_merge_arithmetic_and_dispatch():
     assert kv_split_for(4096, 2, "auto") == 2        # 64 CTAs -> 128
     assert kv_split_for(512, 2, "auto") == 4         # 8 CTAs, 8 key tiles -> 2 tiles per CTA
     assert kv_split_for(64, 1, "auto") == 1 and kv_split_for(32768, 2, "auto") == 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# independent anchors for the pytorch3d LEAVES of the renderer oracle (unpinned against pytorch3d itself): closed forms
+# of volume rendering, independent implementations (scipy / numpy), geometric invariants
+# ------------------------------------------------------------------------------------------------------------
+def test_leaf_so3_exp_map_matches_scipy():
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(16, 3, generator=g, dtype=torch.float64) * 1.3
+    got = ro.so3_exp_map(v)
+    ref = torch.from_numpy(Rotation.from_rotvec(v.numpy()).as_matrix())
+    assert torch.allclose(got, ref, atol=1e-12)
+
+
+def test_leaf_camera_and_ray_geometry():
+    """look-at cameras of the turntable: orthonormal R, centre at the orbit radius, the central pixel's ray goes
+    through the scene centre, depths span [radius - extent, radius + extent], unit directions."""
+    cams = ro.simple_360_cameras(8, dtype=torch.float64)
+    R = cams.R
+    eye = torch.eye(3, dtype=torch.float64)
+    assert torch.allclose(R @ R.transpose(1, 2), eye.expand_as(R), atol=1e-12)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(8, dtype=torch.float64), atol=1e-12)
+    C = cams.centre()
+    assert torch.allclose(C.norm(dim=-1), torch.full((8,), 10.0, dtype=torch.float64), atol=1e-9)
+    for pose in (0, 3, 6):
+        b = ro.sample_rays(cams[pose], 5, 5, 9)                      # odd size: pixel (2, 2) sits at NDC (0, 0)
+        o, d, z = b.origins[0, 2, 2], b.directions[0, 2, 2], b.lengths[0, 2, 2]
+        assert torch.allclose(b.xys[0, 2, 2], torch.zeros(2, dtype=b.xys.dtype), atol=1e-7)
+        assert abs(float(d.norm()) - 1.0) < 1e-6
+        t_centre = 0.5 * (z[0] + z[-1])                              # depth of the scene centre along the ray
+        assert float((o + t_centre * d).norm()) < 1e-4               # ... where the ray meets the origin
+        assert abs(float(z[0]) - 6.0) < 1e-4 and abs(float(z[-1]) - 14.0) < 1e-4
+        assert torch.allclose(z[1:] - z[:-1], torch.full((8,), 1.0, dtype=z.dtype), atol=1e-5)   # linspace
+
+
+def test_leaf_trilinear_sampling_reproduces_linear_fields():
+    """Volume convention: world (x, y, z) <-> grid axes (W, H, D), voxel centres at (i - (R-1)/2) * extent / R; trilinear
+    interpolation is exact on a linear field; outside the volume the value is 0 (zeros padding)."""
+    R, ext = 8, 8.0
+    vs = ext / R
+    c = (torch.arange(R, dtype=torch.float64) - (R - 1) / 2) * vs
+    zz, yy, xx = torch.meshgrid(c, c, c, indexing="ij")                  # (D, H, W)
+    coef = torch.tensor([[0.3, -1.1, 0.7, 0.2], [1.5, 0.4, -0.6, -0.9]], dtype=torch.float64)
+    grid = torch.stack([k[0] * xx + k[1] * yy + k[2] * zz + k[3] for k in coef])[None]   # (1, 2, D, H, W)
+    g = torch.Generator().manual_seed(4)
+    p = (torch.rand(200, 3, generator=g, dtype=torch.float64) - 0.5) * (R - 1) * vs     # inside the centre lattice
+    got = ro.sample_grid(grid, ro.world_to_local(p, R, ext))
+    ref = p @ coef[:, :3].t() + coef[:, 3]
+    assert torch.allclose(got, ref, atol=1e-10)
+    far = torch.tensor([[10.0, 0.0, 0.0], [0.0, -9.0, 0.0]], dtype=torch.float64)
+    assert float(ro.sample_grid(grid, ro.world_to_local(far, R, ext)).abs().max()) == 0.0
+
+
+def test_leaf_emission_absorption_closed_forms():
+    """NeRF volume rendering: constant density sigma over uniform steps delta gives w_i = (1 - e^{-sigma delta})
+    e^{-sigma delta i}, the last interval is opaque (delta = 1e10) so the weights sum to 1; empty space returns the
+    background colour, zero depth and zero mask."""
+    S, sigma, delta = 12, 0.8, 0.5
+    z = 2.0 + delta * torch.arange(S, dtype=torch.float64)[None]
+    dens = torch.full((1, S, 1), sigma, dtype=torch.float64)
+    col = torch.tensor([0.2, 0.5, 0.9], dtype=torch.float64).expand(1, S, 3)
+    o = ro.ea_raymarch(dens, col, z, bg=(1.0, 1.0, 1.0))
+    i = torch.arange(S, dtype=torch.float64)
+    w = (1 - math.exp(-sigma * delta)) * torch.exp(-sigma * delta * i)
+    w[-1] = math.exp(-sigma * delta * (S - 1))                           # opaque last interval
+    assert torch.allclose(o.weights[0], w, atol=1e-12) and abs(float(o.weights.sum()) - 1.0) < 1e-12
+    assert torch.allclose(o.features[0], col[0, 0], atol=1e-12) and abs(float(o.masks) - 1.0) < 1e-12
+    assert abs(float(o.depths) - float((w * z[0]).sum())) < 1e-12
+    e = ro.ea_raymarch(torch.zeros(1, S, 1, dtype=torch.float64), col, z, bg=(0.1, 0.2, 0.3))
+    assert torch.allclose(e.features[0], torch.tensor([0.1, 0.2, 0.3], dtype=torch.float64), atol=1e-12)
+    assert float(e.masks) == 0.0 and float(e.depths) == 0.0 and float(e.weights.abs().max()) == 0.0
+    neg = ro.ea_raymarch(torch.full((1, S, 1), -3.0, dtype=torch.float64), col, z)   # density_relu
+    assert float(neg.masks) == 0.0
+
+
+def test_leaf_sample_pdf_is_the_piecewise_linear_inverse_cdf():
+    """sample_pdf (deterministic u) against numpy's interp of the same piecewise-linear CDF -- an independent
+    implementation; the refiner then merges and sorts."""
+    g = torch.Generator().manual_seed(6)
+    n, S, N = 7, 10, 16
+    bins = torch.sort(torch.rand(n, S, generator=g, dtype=torch.float64) * 4 + 2, -1)[0]
+    w = torch.rand(n, S - 1, generator=g, dtype=torch.float64) + 0.05
+    got = ro.sample_pdf(bins, w, N)
+    wn = (w + 1e-5).numpy()
+    cdf = np.concatenate([np.zeros((n, 1)), np.cumsum(wn / wn.sum(-1, keepdims=True), -1)], -1)
+    u = np.linspace(0.0, 1.0, N)
+    ref = np.stack([np.interp(u, cdf[r], bins[r].numpy()) for r in range(n)])
+    assert np.allclose(got.numpy(), ref, atol=1e-9)
+    # refiner: mids of the depths as bins, the inner weights, sorted union with the input samples
+    z = bins
+    wz = torch.rand(n, S, generator=g, dtype=torch.float64)
+    zz = ro.refine_lengths(z, wz, N)
+    assert zz.shape == (n, S + N) and bool((zz[:, 1:] >= zz[:, :-1]).all())
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    new = ro.sample_pdf(mids, wz[:, 1:-1], N)
+    assert torch.allclose(torch.sort(torch.cat([z, new], -1), -1)[0], zz)
