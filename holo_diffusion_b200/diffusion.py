@@ -9,7 +9,7 @@ reference does) and kept resident on the device as fp32 tables; each step is one
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict
 
 import numpy as np
 import torch

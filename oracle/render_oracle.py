@@ -13,8 +13,8 @@ run the same torch ops through cuDNN / cuBLAS -- used by the full-size parity te
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F

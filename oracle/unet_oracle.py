@@ -10,7 +10,7 @@ this oracle and the CUDA path.  Follows ``holo_diffusion/guided_diffusion/unet.p
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Sequence
 
 import torch
 import torch.nn.functional as F
