@@ -16,6 +16,8 @@ LIB = os.path.join(HERE, "libholo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("HOLO_PTXAS_V") else "-O3"]
+if os.environ.get("HOLO_BUILD_PDL") == "1":   # opt-in: programmatic dependent launch (csrc/common.cuh), run with HOLO_PDL=1
+    FLAGS.append("-DHOLO_ENABLE_PDL")
 
 
 def _newer(src: str, dst: str, deps) -> bool:

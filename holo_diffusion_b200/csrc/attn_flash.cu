@@ -234,6 +234,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    holo_pdl_trigger();   // opt-in PDL build only (common.cuh)
+    holo_pdl_wait();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -549,7 +551,8 @@ int launch_flash(const CUtensorMap* maps, const FlashParams& P, int q_tiles, int
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<CH>::SMEM_BYTES),
               "holo_attention_flash");
     dim3 grid((unsigned)q_tiles, (unsigned)P.heads, (unsigned)splits);
-    k<<<grid, NTHREADS, FCfg<CH>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
+    holo_launch(k, grid, dim3(NTHREADS), (size_t)FCfg<CH>::SMEM_BYTES, st, maps[0], maps[1], maps[2], maps[3], maps[4],
+                maps[5], P);
     HOLO_CHECK_LAUNCH("holo_attention_flash");
     return HOLO_OK;
 }

@@ -43,6 +43,48 @@ void holo_set_error(const char* fmt, ...);
 
 static inline int holo_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL).  OPT-IN BUILD: compiled only with -DHOLO_ENABLE_PDL (HOLO_BUILD_PDL=1 python
+// holo_diffusion_b200/build.py) and then switched on at run time with HOLO_PDL=1; the default build contains none of
+// it (the helpers below are empty and holo_launch is a plain <<<>>> launch).  A kernel launched through holo_launch
+// may start while its predecessor in the stream is still running; it therefore executes holo_pdl_wait() -- which
+// returns when every prerequisite grid has completed and flushed its memory -- before its first dependent global
+// access (reads AND writes: the caching allocator recycles buffers), and only its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) and its scheduling overlap the predecessor's tail.  That is aimed at the ~45
+// launches per step of the coarse UNet levels, which keep 16-64 CTAs on 148 SMs for 10-25 us each.  Written after
+// the round's GPU budget was spent: NOT yet run on a GPU.
+#ifdef HOLO_ENABLE_PDL
+#include <cstdlib>
+#include <utility>
+__device__ __forceinline__ void holo_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void holo_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void holo_pdl_wait() {}
+__device__ __forceinline__ void holo_pdl_trigger() {}
+#endif
+
+// Launch of a kernel that contains holo_pdl_wait().  Errors surface through cudaGetLastError (HOLO_CHECK_LAUNCH).
+template <typename... KArgs, typename... Args>
+static inline void holo_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                               Args&&... args) {
+#ifdef HOLO_ENABLE_PDL
+    static const bool on = [] {
+        const char* e = getenv("HOLO_PDL");
+        return e && e[0] == '1';
+    }();
+    if (on) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        return;
+    }
+#endif
+    kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float holo_silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float holo_leaky(float x) { return x > 0.0f ? x : 0.2f * x; }
 

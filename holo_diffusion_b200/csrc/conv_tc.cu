@@ -213,6 +213,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    holo_pdl_trigger();   // (opt-in PDL build) the next kernel may be scheduled; it waits for this grid to complete
+    holo_pdl_wait();      // everything above overlapped the predecessor's tail; no dependent access before this line
 
     // work item -> (M tile, N block, K slice); M tiles fastest so that concurrently running CTAs share weights in L2
     auto decode = [&](int item, int& w0, int& h0, int& d0, int& n0, int& it_begin, int& it_end, int& z) {
@@ -498,7 +500,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     const long long items = (long long)Q.m_tiles * Q.n_blocks * Q.nsplit;
     long long grid = (long long)n_sm * occ;
     if (grid > items) grid = items;
-    k<<<dim3((unsigned)grid), NUM_THREADS, smem, st>>>(ah, al, bh, bl, a2h, a2l, Q);
+    holo_launch(k, dim3((unsigned)grid), dim3(NUM_THREADS), (size_t)smem, st, ah, al, bh, bl, a2h, a2l, Q);
     HOLO_CHECK_LAUNCH("holo_conv3d_tc");
     return HOLO_OK;
 }

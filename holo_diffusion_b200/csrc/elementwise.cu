@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
                                                         int C2, long long V, int vox_per_block,
                                                         double* __restrict__ acc, double* __restrict__ acc_zero) {
     extern __shared__ float sh[];  // [vstep][2C] per-thread partials, then [2C] totals
+    holo_pdl_trigger();   // opt-in PDL build only (common.cuh): no dependent access before the wait
+    holo_pdl_wait();
     // ping-pong accumulators: while this GroupNorm accumulates into `acc`, block 0 clears the buffer the NEXT one
     // will use (its previous reader, the preceding fused apply, has completed in stream order)
     if (acc_zero && blockIdx.x == 0)
@@ -109,7 +111,8 @@ static int gn_stats_launch(const float* x1, int C1, const float* x2, int C2, lon
     int blocks = holo_cdiv(V, vpb);
     const int vstep = threads / (C / 4);
     size_t smem = (size_t)(vstep > 1 ? vstep : 1) * 2 * C * sizeof(float);
-    gn_stats_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(x1, C1, x2, C2, V, (int)vpb, acc64, acc_zero);
+    holo_launch(gn_stats_kernel, dim3(blocks), dim3(threads), (size_t)smem, (cudaStream_t)stream, x1, C1, x2, C2, V,
+                (int)vpb, acc64, acc_zero);
     HOLO_CHECK_LAUNCH("holo_gn_stats");
     return HOLO_OK;
 }
@@ -222,6 +225,8 @@ __global__ void gn_apply_fused_kernel(const float* __restrict__ x1, int C1, cons
     __shared__ double s_acc[64];
     const int C = C1 + C2;
     const int cpg = C / 32;
+    holo_pdl_trigger();   // opt-in PDL build only (common.cuh): the statistics below come from the predecessor
+    holo_pdl_wait();
     if (threadIdx.x < 64) {
         double t = 0;
         if (acc) {  // group statistics from holo_gn_stats (8 replicas)
@@ -347,13 +352,13 @@ static int gn_apply_fused_launch(const float* x1, int C1, const float* x2, int C
     }
     size_t smem = 2 * (size_t)C * sizeof(float);
     if (silu)
-        gn_apply_fused_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(
-            x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
+        holo_launch(gn_apply_fused_kernel<true>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream, x1, C1, x2, C2, V,
+                    acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16,
+                    (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
     else
-        gn_apply_fused_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(
-            x1, C1, x2, C2, V, acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16,
-            (uint16_t*)y_lo_bf16, (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
+        holo_launch(gn_apply_fused_kernel<false>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream, x1, C1, x2, C2, V,
+                    acc64, ch1, ch2, gamma, beta, film_scale_shift, eps, y, (uint16_t*)y_hi_bf16, (uint16_t*)y_lo_bf16,
+                    (uint16_t*)raw_hi_bf16, (uint16_t*)raw_lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_gn_apply_fused");
     return HOLO_OK;
 }
@@ -405,6 +410,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int C1, const flo
     const int C = C1 + C2;
     const int q = Cpad / 4;
     const long long total = Vout * q;
+    holo_pdl_trigger();   // opt-in PDL build only (common.cuh)
+    holo_pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long v = i / q;
@@ -440,8 +447,8 @@ extern "C" int holo_split_bf16(const float* x1, int C1, const float* x2, int C2,
     }
     int blocks = holo_cdiv(Vout * (Cpad / 4), 256 * 4);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, C1, x2, C2, Vout, Cpad, upsample2x, Din, Hin, Win,
-                                                                (uint16_t*)hi_bf16, (uint16_t*)lo_bf16, pair_f16);
+    holo_launch(split_bf16_kernel, dim3(blocks), dim3(256), (size_t)0, (cudaStream_t)stream, x1, C1, x2, C2, Vout, Cpad,
+                upsample2x, Din, Hin, Win, (uint16_t*)hi_bf16, (uint16_t*)lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_split_bf16");
     return HOLO_OK;
 }
