@@ -325,10 +325,10 @@ def run_ours(a):
     clocks = Clocks(local) if (rank == 0 and not a.no_clocks) else None
     if a.e2e_first:
         ms_e2e, _, _ = timed(step_e2e, a.steps, max(a.warmup, 3))
-        ms_dev, _, clk = timed(step_device, a.steps, 2, clocks)
+        ms_dev, _, clk = timed(step_device, a.steps, 3, clocks)
     else:
         ms_dev, _, clk = timed(step_device, a.steps, max(a.warmup, 3), clocks)
-        ms_e2e, _, _ = timed(step_e2e, a.steps, 2)
+        ms_e2e, _, _ = timed(step_e2e, a.steps, 3)
     launches = launches_per_step * a.steps
     views = a.steps * world
     value = views / (ms_dev / 1e3)
