@@ -563,6 +563,19 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         per = (k_total + nsplit - 1) / nsplit;
         nsplit = (k_total + per - 1) / per;
     }
+    // Accuracy knob (opt-in, HOLO_CONV_MAX_CHAIN=<n>): the tensor core adds every K = 16 step into the fp32 TMEM
+    // accumulator with truncation, an error that grows linearly with the chain length.  Capping
+    // the (tap, slab) iterations per accumulator at n and summing the chains with fp32 atomics (round-to-nearest) --
+    // the split-K path above, forced -- shortens the chains at the price of the atomics, a memset and the epilogue
+    // statistics (the GroupNorm then runs its own statistics pass).
+    static const int max_chain = [] {
+        const char* e = getenv("HOLO_CONV_MAX_CHAIN");
+        return e ? atoi(e) : 0;
+    }();
+    if (max_chain > 0 && per > max_chain && out && !out_hi_bf16 && (out_pitch == Cout || out_is_zeroed)) {
+        per = max_chain;
+        nsplit = (k_total + per - 1) / per;
+    }
     CUtensorMap ah, al, bh, bl, a2h, a2l;
     int e = make_act_map(&ah, x_hi, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
     if (!e) e = make_act_map(&al, x_lo, Cin, x_pitch, Din, Hin, Win, tw, th, td, stride);
