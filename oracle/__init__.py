@@ -25,6 +25,10 @@ Pinning status
   pytorch3d stand-in under ``oracle/pt3d_stub`` (layer / activation placement, skip concat, output slicing, direction
   handling, normals through autograd, the multi-pass recursion incl. training-mode noise, state-dict key names);
   vectors in ``tests/golden/render_intree_ref.npz``, checked by ``tests/test_cpu_oracle_and_host.py``.
+* Wrappers, in-tree logic: PINNED the same way (``tests/golden/make_wrappers_intree_golden.py`` ->
+  ``wrappers_intree_ref.{npz,json}``): the reference ``SimpleUnet3D`` (keys, shapes, initialisation, ``cond_features``),
+  ``ImplicitronGaussianDiffusion`` defaults (schedule tables), and ``get_simple_360_camera_trajectory`` (its source
+  executed as is: angle conversion and the order R = R_plane @ R_lookat).
 * Renderer, pytorch3d leaves: **parity unpinned**.  The arithmetic of the harmonic embedding, ray points, volume
   locator + grid sampling, emission-absorption ray marcher, ray-point refiner / ``sample_pdf``, ray sampler and
   cameras lives in the un-vendored dependency ``pytorch3d==0.7.4`` (reference ``environment.yaml:139``), absent from

@@ -412,3 +412,97 @@ def test_leaf_sample_pdf_is_the_piecewise_linear_inverse_cdf():
     mids = 0.5 * (z[:, 1:] + z[:, :-1])
     new = ro.sample_pdf(mids, wz[:, 1:-1], N)
     assert torch.allclose(torch.sort(torch.cat([z, new], -1), -1)[0], zz)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's in-tree WRAPPERS (SimpleUnet3D, ImplicitronGaussianDiffusion, the turntable cameras), executed
+# unmodified against oracle/pt3d_stub by tests/golden/make_wrappers_intree_golden.py
+# ------------------------------------------------------------------------------------------------------------
+def _wrappers():
+    return np.load(os.path.join(GOLD, "wrappers_intree_ref.npz")), json.load(open(os.path.join(GOLD, "wrappers_intree_ref.json")))
+
+
+def test_simple_unet3d_matches_reference_wrapper():
+    """State-dict keys / shapes and the initialisation facts of the reference SimpleUnet3D (diffusion_utils.py:41-80):
+    Xavier-uniform Conv3d / Linear weights with zero biases, Conv1d qkv left at PyTorch's default (non-zero bias),
+    proj_out zeroed; and forward(x, t, cond_features) = UNet(cat(x, cond))."""
+    from holo_diffusion_b200.unet import SimpleUnet3D
+    g, facts = _wrappers()
+    torch.manual_seed(0)
+    net = SimpleUnet3D(image_size=16, in_channels=16, out_channels=16, model_channels=64, num_res_blocks=2,
+                       channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(4, 8), num_heads=2)
+    ours = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert ours == facts["unet_keys"]                                   # same names, same order, same shapes
+    init = facts["unet_init"]
+    mods = dict(net._net.named_modules())
+    for name in init["zero_bias"]:
+        assert float(mods[name].bias.detach().abs().max()) == 0.0, name
+    for name in init["nonzero_bias"]:
+        assert float(mods[name].bias.detach().abs().max()) > 0.0, name   # the Conv1d qkv layers keep their default init
+    for name in init["zero_weight"]:
+        assert float(mods[name].weight.detach().abs().max()) == 0.0, name  # zero_module(proj_out), unet.py:392
+    for name in init["within_xavier_bound"]:
+        w = mods[name].weight.detach()
+        rf = int(np.prod(w.shape[2:])) if w.dim() > 2 else 1
+        bound = math.sqrt(6.0 / ((w.shape[0] + w.shape[1]) * rf))
+        assert 0.5 * bound < float(w.abs().max()) <= bound * (1 + 1e-6), name
+    assert sorted(init["zero_bias"] + init["nonzero_bias"]) == sorted(
+        n for n, m in mods.items() if isinstance(m, (torch.nn.Conv3d, torch.nn.Linear, torch.nn.Conv1d)))
+    # cond_features: concatenated after x on the channel axis (oracle = the pinned UNet restatement)
+    fix = uo.make_unet_state_dict(8, 8, 32, 1, (1, 2), (2,), seed=5)
+    x, c = torch.from_numpy(g["unet/x"]), torch.from_numpy(g["unet/cond"])
+    y = uo.unet_forward(fix, torch.cat([x, c], 1), torch.full((1,), 37, dtype=torch.long), n_heads=1)
+    assert torch.allclose(y, torch.from_numpy(g["unet/y"]), rtol=0, atol=1e-5)
+
+
+def test_diffusion_wrapper_defaults_match_reference():
+    """ImplicitronGaussianDiffusion() with its DEFAULTS (diffusion_utils.py:89-112): linear betas 1e-4 .. 0.02, 1000
+    steps, START_X / FIXED_SMALL, no timestep rescaling -- the tables of the product's wrapper and of the oracle."""
+    from holo_diffusion_b200.diffusion import ImplicitronGaussianDiffusion
+    g, facts = _wrappers()
+    assert facts["diffusion"] == {"num_timesteps": 1000, "model_mean_type": "START_X", "model_var_type": "FIXED_SMALL",
+                                  "rescale_timesteps": False}
+    d = ImplicitronGaussianDiffusion()
+    assert d.num_timesteps == 1000
+    for k, v in d.tables64.items():
+        if "diffusion/" + k in g.files:
+            assert np.allclose(v, g["diffusion/" + k], rtol=1e-14, atol=0), k
+    t = do.schedule_tables()
+    for k in ("posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped", "sqrt_alphas_cumprod"):
+        assert np.allclose(np.asarray(t[k], dtype=np.float64), g["diffusion/" + k], rtol=1e-14, atol=0), k
+
+
+def test_turntable_cameras_match_reference_function():
+    """get_simple_360_camera_trajectory (flyaround.py:301-350), its own source executed on the stand-in leaves: the
+    azimuth / elevation conversion, R = R_plane @ R_lookat (NOT the other order), T unchanged, (n, 1) focal length."""
+    import holo_diffusion_b200 as hd
+    g, _ = _wrappers()
+    for n, max_angle in ((8, 2 * math.pi), (5, math.pi)):
+        tag = f"cams{n}"
+        oc = ro.simple_360_cameras(n, max_angle=max_angle)
+        assert torch.allclose(oc.R, torch.from_numpy(g[tag + "/R"]), atol=1e-6)
+        assert torch.allclose(oc.T, torch.from_numpy(g[tag + "/T"]), atol=1e-6)
+        pc = hd.get_simple_360_camera_trajectory(max_angle, n, -math.pi / 6, 10.0, ro.CANONICAL_CO3D_UP_AXIS, 3.2)
+        assert torch.allclose(pc.R, torch.from_numpy(g[tag + "/R"]), atol=1e-6)
+        assert torch.allclose(pc.T, torch.from_numpy(g[tag + "/T"]), atol=1e-6)
+        assert tuple(g[tag + "/focal"].shape) == (n, 1)      # one focal length for both axes; ours stores it per axis
+        assert torch.allclose(pc.focal_length, torch.from_numpy(g[tag + "/focal"]).expand(n, pc.focal_length.shape[1]))
+        assert float(pc.principal_point.abs().max()) == 0.0 and float(np.abs(g[tag + "/pp"]).max()) == 0.0
+        # the other multiplication order is a different set of cameras: the vectors do discriminate
+        Rp = ro.so3_exp_map(torch.cross(torch.tensor((0.0, -1.0, 0.0)), torch.tensor(ro.CANONICAL_CO3D_UP_AXIS), dim=-1)[None])[0]
+        R_look = torch.linalg.solve(Rp[None].expand(n, 3, 3), oc.R)
+        assert float((torch.bmm(R_look, Rp[None].expand(n, 3, 3)) - oc.R).abs().max()) > 1e-2
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/holo_diffusion"), reason="needs the reference checkout")
+def test_wrappers_golden_is_reproducible_from_the_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_wrappers_intree_golden",
+                                                  os.path.join(GOLD, "make_wrappers_intree_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    arrays, facts = m.generate()
+    g, f = _wrappers()
+    assert facts == f and sorted(arrays.keys()) == sorted(g.files)
+    for k in g.files:
+        assert np.allclose(np.asarray(arrays[k]), g[k], rtol=0, atol=1e-6), k
