@@ -88,7 +88,36 @@ def generate():
         tag = f"cams{n_poses}"
         arrays[tag + "/R"], arrays[tag + "/T"] = cams.R.numpy(), cams.T.numpy()
         arrays[tag + "/focal"], arrays[tag + "/pp"] = cams.focal_length.numpy(), cams.principal_point.numpy()
+    # ---- call signatures of the plug-in surface, read from the reference SOURCE (SURVEY.md section 8b)
+    facts["signatures"] = {}
+    for rel, cls, fn_name in (("holo_diffusion/holo_diffusion_model.py", "HoloDiffusionModel", "forward"),
+                              ("holo_diffusion/holo_voxel_grid_implicit_function.py", "HoloVoxelGridImplicitFunction", "forward"),
+                              ("holo_diffusion/holo_voxel_grid_implicit_function.py", "RenderMLP", "forward"),
+                              ("holo_diffusion/holo_multipass_ea.py", "HoloMultiPassEmissionAbsorptionRenderer", "_run_raymarcher"),
+                              ("holo_diffusion/utils/diffusion_utils.py", "Unet3DBase", "forward"),
+                              ("holo_diffusion/utils/diffusion_utils.py", "SimpleUnet3D", "forward"),
+                              ("holo_diffusion/utils/render_utils/flyaround.py", None, "get_simple_360_camera_trajectory")):
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        body = tree.body if cls is None else next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+        f = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == fn_name)
+        facts["signatures"][(cls + "." if cls else "") + fn_name] = signature_of(f.args)
     return arrays, facts
+
+
+def signature_of(a: ast.arguments):
+    """[(name, kind, default-source-or-None)] with kinds as in inspect.Parameter."""
+    out = []
+    pos = a.posonlyargs + a.args
+    d0 = len(pos) - len(a.defaults)
+    for i, arg in enumerate(pos):
+        out.append([arg.arg, "POSITIONAL_OR_KEYWORD", ast.unparse(a.defaults[i - d0]) if i >= d0 else None])
+    if a.vararg:
+        out.append([a.vararg.arg, "VAR_POSITIONAL", None])
+    for arg, d in zip(a.kwonlyargs, a.kw_defaults):
+        out.append([arg.arg, "KEYWORD_ONLY", ast.unparse(d) if d is not None else None])
+    if a.kwarg:
+        out.append([a.kwarg.arg, "VAR_KEYWORD", None])
+    return out
 
 
 if __name__ == "__main__":

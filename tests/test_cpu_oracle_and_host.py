@@ -506,3 +506,47 @@ def test_wrappers_golden_is_reproducible_from_the_reference():
     assert facts == f and sorted(arrays.keys()) == sorted(g.files)
     for k in g.files:
         assert np.allclose(np.asarray(arrays[k]), g[k], rtol=0, atol=1e-6), k
+
+
+def test_plugin_signatures_match_reference_source():
+    """The call signatures of the plug-in surface, read from the reference SOURCE by
+    tests/golden/make_wrappers_intree_golden.py: same parameter names, order and kinds (keyword-only forward()s), same
+    defaults where the reference states one; extra parameters of ours must be optional and keyword-only."""
+    import inspect
+
+    import holo_diffusion_b200 as hd
+    from holo_diffusion_b200 import renderer as rd
+    from holo_diffusion_b200 import unet as un
+    _, facts = _wrappers()
+    ours = {"HoloDiffusionModel.forward": hd.HoloDiffusionModel.forward,
+            "HoloVoxelGridImplicitFunction.forward": hd.HoloVoxelGridImplicitFunction.forward,
+            "RenderMLP.forward": rd.RenderMLP.forward,
+            "HoloMultiPassEmissionAbsorptionRenderer._run_raymarcher": hd.HoloMultiPassEmissionAbsorptionRenderer._run_raymarcher,
+            "Unet3DBase.forward": un.Unet3DBase.forward, "SimpleUnet3D.forward": un.SimpleUnet3D.forward,
+            "get_simple_360_camera_trajectory": hd.get_simple_360_camera_trajectory}
+    assert sorted(ours) == sorted(facts["signatures"])
+    for name, fn in ours.items():
+        fn = inspect.unwrap(fn)                       # forward() is wrapped by torch.no_grad()
+        params = inspect.signature(fn).parameters
+        ref = [(n, k) for n, k, _ in facts["signatures"][name]]
+        got = [(p.name, p.kind.name) for p in params.values() if p.name in dict(ref)]
+        assert got == ref, (name, got, ref)
+        # anything extra must be optional and keyword-only (an extension the reference's callers never see)
+        for p in params.values():
+            if p.name not in dict(ref):
+                assert p.kind.name == "KEYWORD_ONLY" and p.default is not inspect.Parameter.empty, (name, p.name)
+        for n, _, default in facts["signatures"][name]:
+            p = inspect.signature(fn).parameters.get(n)
+            if default is None or p is None:
+                continue
+            if default == "None":
+                assert p.default is None, (name, n)
+            elif default == "EvaluationMode.EVALUATION":
+                assert p.default == hd.EvaluationMode.EVALUATION, (name, n)
+            else:
+                assert p.default == eval(default), (name, n)
+    # the call generate_samples.py makes (flyaround.py:247-253): a FrameData unpacked into keywords, image_rgb = None
+    sig = inspect.signature(inspect.unwrap(hd.HoloDiffusionModel.forward))
+    sig.bind(None, frame_number=None, sequence_category=None, image_rgb=None, camera=object(), fg_probability=None,
+             mask_crop=None, depth_map=None, sequence_name=None, frame_timestamp=None,
+             evaluation_mode=hd.EvaluationMode.EVALUATION, voxel_features=None)
