@@ -264,5 +264,6 @@ class HoloDiffusionModel(nn.Module):
         preds["implicitron_render"] = ImplicitronRender(image_render=preds["images_render"],
                                                         depth_render=preds["depths_render"],
                                                         mask_render=preds["masks_render"])
-        preds["objective"] = None
+        # no "objective" key: the reference adds it only when _get_objective() returns one (holo_diffusion_model.py:
+        # 529-537), which it does not in evaluation without target images
         return preds

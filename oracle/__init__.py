@@ -28,7 +28,9 @@ Pinning status
 * Wrappers, in-tree logic: PINNED the same way (``tests/golden/make_wrappers_intree_golden.py`` ->
   ``wrappers_intree_ref.{npz,json}``): the reference ``SimpleUnet3D`` (keys, shapes, initialisation, ``cond_features``),
   ``ImplicitronGaussianDiffusion`` defaults (schedule tables), and ``get_simple_360_camera_trajectory`` (its source
-  executed as is: angle conversion and the order R = R_plane @ R_lookat).
+  executed as is: angle conversion and the order R = R_plane @ R_lookat), the plug-in call signatures (read with
+  ``ast``), and ``HoloDiffusionModel.forward`` (its source executed on a stand-in ``self`` wired to this oracle:
+  ``tests/golden/make_model_forward_intree_golden.py``).
 * Renderer, pytorch3d leaves: **parity unpinned**.  The arithmetic of the harmonic embedding, ray points, volume
   locator + grid sampling, emission-absorption ray marcher, ray-point refiner / ``sample_pdf``, ray sampler and
   cameras lives in the un-vendored dependency ``pytorch3d==0.7.4`` (reference ``environment.yaml:139``), absent from
