@@ -16,8 +16,15 @@ LIB = os.path.join(HERE, "libholo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("HOLO_PTXAS_V") else "-O3"]
-if os.environ.get("HOLO_BUILD_PDL") == "1":   # opt-in: programmatic dependent launch (csrc/common.cuh), run with HOLO_PDL=1
+# Opt-in builds of code that has not run on a GPU yet (the default build keeps the validated device code):
+#   HOLO_BUILD_PDL=1           programmatic dependent launch (csrc/common.cuh), switched on at run time with HOLO_PDL=1
+#   HOLO_BUILD_SPLIT_KV=1      split-KV fused attention (csrc/attn_flash.cu), used with HOLO_ATTN_KV_SPLIT=auto|<n>
+#   HOLO_BUILD_EXPERIMENTAL=1  both
+_exp = os.environ.get("HOLO_BUILD_EXPERIMENTAL") == "1"
+if _exp or os.environ.get("HOLO_BUILD_PDL") == "1":
     FLAGS.append("-DHOLO_ENABLE_PDL")
+if _exp or os.environ.get("HOLO_BUILD_SPLIT_KV") == "1":
+    FLAGS.append("-DHOLO_ENABLE_SPLIT_KV")
 
 
 def _newer(src: str, dst: str, deps) -> bool:

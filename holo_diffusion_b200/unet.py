@@ -259,8 +259,10 @@ class UNetExecutor:
         # its speed is not measured yet, so it stays opt-in.
         self.fuse_skip = os.environ.get("HOLO_FUSE_SKIP", "0") == "1"
         # HOLO_ATTN_KV_SPLIT=auto | <n>: split the keys of every (query tile, head) of the fused attention over n CTAs
-        # (auto: fill ~148 SMs, >= 2 key tiles per CTA) + a merge kernel.  Opt-in: written after the round's GPU budget
-        # was spent, NOT yet run on a B200 (the merge arithmetic and the dispatch are covered on the CPU).
+        # (auto: fill ~148 SMs, >= 2 key tiles per CTA) + a merge kernel.  Opt-in AND an opt-in build
+        # (HOLO_BUILD_SPLIT_KV=1 python holo_diffusion_b200/build.py): written after the round's GPU budget was spent,
+        # NOT yet run on a B200 (the merge arithmetic and the dispatch are covered on the CPU); the default library
+        # keeps the validated attention kernel bit for bit and answers kv_splits > 1 with "unsupported".
         self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "1")
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None

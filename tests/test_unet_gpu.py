@@ -638,7 +638,10 @@ def test_attention_flash_split_kv(T, heads, ch, splits):
     out = torch.full((T, C), float("nan"), device="cuda")
     o_hi = torch.empty(T, C, device="cuda", dtype=torch.float16)
     o_lo = torch.empty_like(o_hi)
-    assert ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, out, o_hi, o_lo, kv_splits=splits, workspace=ws) == 0
+    rc = ops.attention_flash(hi, lo, vt_hi, vt_lo, T, heads, ch, out, o_hi, o_lo, kv_splits=splits, workspace=ws)
+    if rc == -3:
+        pytest.skip("split-KV is compiled only into the experimental build (HOLO_BUILD_SPLIT_KV=1 python holo_diffusion_b200/build.py)")
+    assert rc == 0
     torch.cuda.synchronize()
     print(f"split-KV T={T} ch={ch} x{splits}: vs un-split {rel_err(out, one):.2e}, vs fp64 {rel_err(out, ref):.2e}")
     assert rel_err(out, one) < 2e-6 and rel_err(out, ref) < 4e-5
