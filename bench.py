@@ -383,9 +383,12 @@ def run_ours(a):
         import glob
         tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
         if tfiles and a.resol == 64 and a.channels == 32:
-            tj = json.load(open(tfiles[-1]))
-            traffic = tj["bytes_per_launch"].get("conv_tc_kernel" if kind == "tc" else "conv_simt_kernel")
-            traffic_src = "profiles/" + os.path.basename(tfiles[-1])
+            try:
+                tj = json.load(open(tfiles[-1]))
+                traffic = tj["bytes_per_launch"].get("conv_tc_kernel" if kind == "tc" else "conv_simt_kernel")
+                traffic_src = "profiles/" + os.path.basename(tfiles[-1])
+            except Exception:  # noqa: BLE001  (a malformed profile file must not cost the bench line)
+                traffic = traffic_src = None
         ach = fl / (ms / 1e3) / 1e12
         roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv3d, 3-term fp16-pair split)" if kind == "tc" else "conv_simt_kernel (fp32 CUDA cores)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
