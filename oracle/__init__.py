@@ -41,4 +41,6 @@ Pinning status
   not this restatement either) hold the leaves in place: ``so3_exp_map`` against scipy, the trilinear sampler on linear
   fields, the ray marcher against the closed forms of volume rendering, ``sample_pdf`` against numpy's ``interp`` of the
   same CDF, look-at / ray geometry invariants (``tests/test_cpu_oracle_and_host.py::test_leaf_*``).
+  ``tests/test_pytorch3d_optional.py`` compares every leaf with the real pytorch3d wherever it is installed (it skips
+  -- and has never run -- in this image).
 """
