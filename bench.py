@@ -282,16 +282,15 @@ def run_ours(a):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if clocks:   # the sampler starts (and settles) BEFORE the barrier: no rank may enter step 0 late, or the
+            clocks.start()   # others wait for it inside the first gather and the max-over-ranks time absorbs the delay
+            time.sleep(0.25)
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         counter["n"] = 0
         t0 = time.perf_counter()
-        if clocks:
-            clocks.start()
-            time.sleep(0.25)
-            t0 = time.perf_counter()
         for s, e in ev:
             flush.zero_()  # L2 flush, outside the event bracket
             s.record()

@@ -172,11 +172,9 @@ struct FlashParams {
     // the un-normalised O_z (part_o: [z][T][C] fp32) and (m_z * scale_log2, rowsum_z) (part_ml: [z][heads][T] float2);
     // flash_combine_kernel merges: O = sum_z 2^(m_z - M) O_z / sum_z 2^(m_z - M) l_z.  Fills the 148 SMs when
     // (T / 128) x heads is small (64 CTAs at T = 4096, 8 at T = 512).
-#ifdef HOLO_ENABLE_SPLIT_KV
     int kt_per_split;
     float* part_o;
     float2* part_ml;
-#endif
 };
 
 // F16: every operand pair (q, k, v^T in, P inside, the output pair) has fp16 halves instead of bf16.  The logits'
@@ -210,13 +208,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     const int head = blockIdx.y;
     // split-KV is an OPT-IN BUILD (-DHOLO_ENABLE_SPLIT_KV, HOLO_BUILD_EXPERIMENTAL=1): it has not run on a GPU yet, and
     // the default build keeps the device code that has (identical SASS to the validated revision)
-#ifdef HOLO_ENABLE_SPLIT_KV
     const int kt0 = (int)blockIdx.z * P.kt_per_split;                     // first key tile of this CTA's share
     const int NT = min(P.T / BN - kt0, P.kt_per_split);                   // key tiles per pass (all of them unsplit)
-#else
-    constexpr int kt0 = 0;
-    const int NT = P.T / BN;        // key tiles per pass
-#endif
     const int n_jobs = 2 * NT;      // S jobs: pass A (max) then pass B (exp + PV)
     const int col_q = head * 3 * CH, col_k = col_q + CH;
 
@@ -402,15 +395,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         tc_fence_after();
         xch[half * BM + row] = l0 + l1;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-#ifdef HOLO_ENABLE_SPLIT_KV
         const float lsum = xch[row] + xch[BM + row];
-#else
-        const float inv = 1.0f / (xch[row] + xch[BM + row]);
-#endif
         const int t = m0 + row;
         const bool ok = t < P.T;
         const size_t obase = (size_t)t * P.C + (size_t)head * CH;
-#ifdef HOLO_ENABLE_SPLIT_KV
         if (gridDim.z > 1) {
             // split-KV: this CTA's share of the keys only -- leave O un-normalised for flash_combine_kernel
             if (ok && half == 0) P.part_ml[((size_t)blockIdx.z * P.heads + head) * P.T + t] = make_float2(msc, lsum);
@@ -428,11 +416,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             }
             tc_fence_before();
         } else
-#endif
         {
-#ifdef HOLO_ENABLE_SPLIT_KV
         const float inv = 1.0f / lsum;
-#endif
 #pragma unroll 1
         for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
             tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
@@ -469,7 +454,6 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     }
 }
 
-#ifdef HOLO_ENABLE_SPLIT_KV
 // Merge of the split-KV partials: thread = 8 channels of one query row.
 __global__ void flash_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int splits,
                                      int T, int heads, int ch, int q_begin, int q_count, float* __restrict__ out,
@@ -511,7 +495,6 @@ __global__ void flash_combine_kernel(const float* __restrict__ part_o, const flo
         }
     }
 }
-#endif  // HOLO_ENABLE_SPLIT_KV
 
 // V (T, ch) slices of the head-major qkv tensor -> V^T (heads*ch, T) bf16 hi/lo, K-major for the P V product
 __global__ void v_transpose_split_kernel(const float* __restrict__ qkv, int T, int heads, int ch,
@@ -626,7 +609,6 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
     // split-KV: kv_splits CTAs share the key tiles of one (query tile, head); needs the caller's workspace
     const int nt_all = T / BN;
     int splits = kv_splits < 1 ? 1 : (kv_splits > nt_all ? nt_all : kv_splits);
-#ifdef HOLO_ENABLE_SPLIT_KV
     P.kt_per_split = (nt_all + splits - 1) / splits;
     splits = (nt_all + P.kt_per_split - 1) / P.kt_per_split;
     P.part_o = nullptr, P.part_ml = nullptr;
@@ -636,14 +618,6 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
         P.part_o = reinterpret_cast<float*>(workspace);
         P.part_ml = reinterpret_cast<float2*>(P.part_o + (size_t)splits * T * C);
     }
-#else
-    if (splits > 1) {
-        holo_set_error("holo_attention_flash: kv_splits > 1 needs the experimental build (HOLO_BUILD_SPLIT_KV=1 python "
-                       "holo_diffusion_b200/build.py)");
-        return HOLO_ERR_UNSUPPORTED;
-    }
-    (void)workspace;
-#endif
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (pair_f16)
@@ -652,14 +626,12 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
         rc = ch == 64 ? launch_flash<64, false>(maps, P, q_tiles, splits, st)
                       : launch_flash<128, false>(maps, P, q_tiles, splits, st);
     if (rc != HOLO_OK || splits == 1) return rc;
-#ifdef HOLO_ENABLE_SPLIT_KV
     const long long total = (long long)q_count * (C / 8);
     int blocks = holo_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     flash_combine_kernel<<<blocks, 256, 0, st>>>(P.part_o, P.part_ml, splits, T, heads, ch, q_begin, q_count, out_cl,
                                                  (uint16_t*)out_hi_bf16, (uint16_t*)out_lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_attention_flash (combine)");
-#endif
     return HOLO_OK;
 }
 

@@ -43,30 +43,22 @@ void holo_set_error(const char* fmt, ...);
 
 static inline int holo_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// Programmatic dependent launch (PDL).  OPT-IN BUILD: compiled only with -DHOLO_ENABLE_PDL (HOLO_BUILD_PDL=1 python
-// holo_diffusion_b200/build.py) and then switched on at run time with HOLO_PDL=1; the default build contains none of
-// it (the helpers below are empty and holo_launch is a plain <<<>>> launch).  A kernel launched through holo_launch
-// may start while its predecessor in the stream is still running; it therefore executes holo_pdl_wait() -- which
-// returns when every prerequisite grid has completed and flushed its memory -- before its first dependent global
-// access (reads AND writes: the caching allocator recycles buffers), and only its prologue (barrier init, TMEM
-// allocation, tensor-map prefetch) and its scheduling overlap the predecessor's tail.  That is aimed at the ~45
-// launches per step of the coarse UNet levels, which keep 16-64 CTAs on 148 SMs for 10-25 us each.  Written after
-// the round's GPU budget was spent: NOT yet run on a GPU.
-#ifdef HOLO_ENABLE_PDL
+// Programmatic dependent launch (PDL), switched on at run time with HOLO_PDL=1.  A kernel launched through
+// holo_launch may start while its predecessor in the stream is still running; it therefore executes holo_pdl_wait()
+// -- which returns when every prerequisite grid has completed and flushed its memory -- before its first dependent
+// global access (reads AND writes: the caching allocator recycles buffers), and only its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) and its scheduling overlap the predecessor's tail.  Aimed at the launches of the
+// coarse UNet levels, which keep 16-64 CTAs on 148 SMs for 10-25 us each.  Without the launch attribute both
+// griddepcontrol instructions are no-ops.
 #include <cstdlib>
 #include <utility>
 __device__ __forceinline__ void holo_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void holo_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-#else
-__device__ __forceinline__ void holo_pdl_wait() {}
-__device__ __forceinline__ void holo_pdl_trigger() {}
-#endif
 
 // Launch of a kernel that contains holo_pdl_wait().  Errors surface through cudaGetLastError (HOLO_CHECK_LAUNCH).
 template <typename... KArgs, typename... Args>
 static inline void holo_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                Args&&... args) {
-#ifdef HOLO_ENABLE_PDL
     static const bool on = [] {
         const char* e = getenv("HOLO_PDL");
         return e && e[0] == '1';
@@ -81,7 +73,6 @@ static inline void holo_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
         (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
         return;
     }
-#endif
     kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
 }
 
