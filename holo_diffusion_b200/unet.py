@@ -253,17 +253,13 @@ class UNetExecutor:
         # lands 4e-6 from exact arithmetic, activations saturate beyond |x| = 131008) or bf16 halves
         # (HOLO_PAIR_FMT=bf16: fp32's range, 7e-5 from exact)
         self.pair_dtype = torch.bfloat16 if os.environ.get("HOLO_PAIR_FMT", "f16") == "bf16" else torch.float16
-        # HOLO_FUSE_SKIP=1: ResBlocks with a 1x1 skip connection run their tail (second 3^3 convolution + skip
-        # convolution + add) as ONE launch (holo_conv3d_tc_skip).  Numerically validated on a B200 (unit shapes and the
-        # 16^3 UNet: 2.7e-6 from the fp64 twin) but written when the round's GPU budget was down to its last seconds:
-        # its speed is not measured yet, so it stays opt-in.
-        self.fuse_skip = os.environ.get("HOLO_FUSE_SKIP", "0") == "1"
-        # HOLO_ATTN_KV_SPLIT=auto | <n>: split the keys of every (query tile, head) of the fused attention over n CTAs
-        # (auto: fill ~148 SMs, >= 2 key tiles per CTA) + a merge kernel.  Opt-in AND an opt-in build
-        # (HOLO_BUILD_SPLIT_KV=1 python holo_diffusion_b200/build.py): written after the round's GPU budget was spent,
-        # NOT yet run on a B200 (the merge arithmetic and the dispatch are covered on the CPU); the default library
-        # keeps the validated attention kernel bit for bit and answers kv_splits > 1 with "unsupported".
-        self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "1")
+        # ResBlocks with a 1x1 skip connection run their tail (second 3^3 convolution + skip convolution + add) as ONE
+        # launch (holo_conv3d_tc_skip): -0.15 ms per 64^3 step on B200 (profiles/r02a).  HOLO_FUSE_SKIP=0 = separate launches
+        self.fuse_skip = os.environ.get("HOLO_FUSE_SKIP", "1") == "1"
+        # HOLO_ATTN_KV_SPLIT=auto | <n>: the keys of every (query tile, head) of the fused attention are shared between
+        # n CTAs (auto: fill ~148 SMs, >= 2 key tiles per CTA) and merged by flash_combine_kernel: -0.23 ms per 64^3
+        # step (profiles/r02a); "1" = one CTA per (query tile, head)
+        self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "auto")
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
