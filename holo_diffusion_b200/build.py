@@ -16,6 +16,7 @@ LIB = os.path.join(HERE, "libholo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("HOLO_PTXAS_V") else "-O3"]
+FLAGS += os.environ.get("HOLO_NVCC_FLAGS", "").split()   # tuning experiments (-DHOLO_CONV_LDW=32 ...); part of the stamp
 
 def _hash(paths) -> str:
     import hashlib

@@ -134,8 +134,7 @@ class AdaptiveRaySampler:
         if mask is not None:
             raise NotImplementedError("mask_sample ray sampling (training) is not part of the built path")
         dev = cameras.device
-        if dev.type != "cuda":
-            raise ops.HoloError("AdaptiveRaySampler: cameras must live on the CUDA device")
+        ops.require_cuda(dev, "AdaptiveRaySampler (cameras)")
         H, W, S = self.image_height, self.image_width, self.n_pts_per_ray_evaluation
         xy = self.xy_grid(dev)
         o, d, l = ops.raygen(cameras.R, cameras.T, cameras.focal_length, cameras.principal_point, xy, S,

@@ -24,6 +24,9 @@
 
 namespace {
 
+#ifndef HOLO_CONV_LDW
+#define HOLO_CONV_LDW 16
+#endif
 constexpr int TILE_W = 8, TILE_H = 4, TILE_D = 4;
 constexpr int BLOCK_M = TILE_W * TILE_H * TILE_D;  // 128
 constexpr int SLAB = 64;                           // bf16 channels per K slab = 128 bytes = one swizzle row
@@ -139,12 +142,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Two TMEM loads (the [hi.hi + lo.hi] and [hi.lo] halves of W accumulator columns) and ONE wait in a single asm
+// statement: the loads overlap each other, and no consumer of the registers can be scheduled before the wait.
+__device__ __forceinline__ void tmem_ld_pair16(uint32_t ta, uint32_t tb, uint32_t (&a)[16], uint32_t (&b)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+          "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(b[0]), "=r"(b[1]),
+          "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]),
+          "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+        : "r"(ta), "r"(tb)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_pair32(uint32_t ta, uint32_t tb, uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+          "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+          "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+          "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]), "=r"(b[0]), "=r"(b[1]),
+          "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]),
+          "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]),
+          "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]),
+          "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(ta), "r"(tb)
+        : "memory");
+}
+
 struct TcParams {
     int Cin, D, H, W, ksize, Cout;   // D, H, W = OUTPUT volume
     int tw, th, td;                  // voxel box of one M tile: 8x4x4 (128 rows) or 4x4x4 (64 rows, upper half idle)
     int stride;                      // 1 | 2 (input coordinate = out * stride + tap - pad)
     int iters_per_split;             // split-K: gridDim.z slices of the (tap, slab) loop; atomics into a zeroed out
     int m_tiles, n_blocks, nsplit;   // work-item grid walked by the persistent CTAs
+    int chunk;                       // (tap, slab) iterations per TMEM accumulation chain (see "chunked accumulation")
     int stages;                      // pipeline depth actually used (<= Cfg::STAGES); short K loops take fewer stages
                                      // and less shared memory so that several CTAs share an SM
     long long out_pitch;  // elements between consecutive output rows (= Cout for dense tensors)
@@ -274,36 +311,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const bool f16 = (P.fmt & HOLO_FMT_F16) != 0;   // A and B of one MMA must share the format
         const uint32_t idesc1 = make_idesc(2 * BLOCK_N, f16, f16);    // x_hi . [w_hi | w_lo]
         const uint32_t idesc2 = make_idesc(BLOCK_N, f16, f16);        // x_lo . w_hi
+        // CHUNKED ACCUMULATION: the tensor core adds every K = 16 step into the fp32 TMEM accumulator with truncation, a
+        // bias that grows linearly with the length of the chain.  The (tap, slab) loop of an
+        // item is therefore cut into chains of P.chunk iterations; each chain starts from zero in the other TMEM
+        // buffer and the epilogue warps sum the chains in registers (round-to-nearest) while the next chain runs.
         int stage = 0;
         uint32_t phase = 0;
-        int local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        int cl = 0;   // chains issued by this CTA so far (TMEM buffer = cl & 1)
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int w0, h0, d0, n0, it_begin, it_end, z;
             decode(item, w0, h0, d0, n0, it_begin, it_end, z);
-            const int buf = local & 1;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::TMEM_COLS);
-            mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue drained this accumulator
-            tc_fence_after();
-            for (int it = it_begin; it < it_end; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+            for (int cb = it_begin; cb < it_end; cb += P.chunk, ++cl) {
+                const int ce = min(it_end, cb + P.chunk);
+                const int buf = cl & 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::TMEM_COLS);
+                mbar_wait(&tmem_empty_bar[buf], ((cl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;  // b_lo follows at + B_TILE_BYTES
+                for (int it = cb; it < ce; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;  // b_lo follows at + B_TILE_BYTES
 #pragma unroll
-                    for (int k = 0; k < SLAB / 16; ++k) {
-                        const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                        const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
-                        const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko);
-                        umma_bf16(d_tmem, dah, dbh, idesc1, (it > it_begin) || (k != 0));
-                        umma_bf16(d_tmem, dal, dbh, idesc2, 1);
+                        for (int k = 0; k < SLAB / 16; ++k) {
+                            const uint32_t ko = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                            const uint64_t dah = make_kmajor_sw128_desc(a_hi + ko), dal = make_kmajor_sw128_desc(a_lo + ko);
+                            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ko);
+                            umma_bf16(d_tmem, dah, dbh, idesc1, (it > cb) || (k != 0));
+                            umma_bf16(d_tmem, dal, dbh, idesc2, 1);
+                        }
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        if (it == ce - 1) umma_commit(&tmem_full_bar[buf]);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (it == it_end - 1) umma_commit(&tmem_full_bar[buf]);
+                    __syncwarp();
+                    if (++stage == n_stages) stage = 0, phase ^= 1;
                 }
-                __syncwarp();
-                if (++stage == n_stages) stage = 0, phase ^= 1;
             }
         }
     } else {
@@ -325,30 +369,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             asm volatile("bar.sync 1, 128;" ::: "memory");
         };
         if (do_stats) flush_stats();  // clears the partials
-        int local = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++local) {
+        int cl = 0;
+        float accv[BLOCK_N];   // sum of the finished chains of the current item (used when an item has several)
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int w0, h0, d0, n0, it_begin, it_end, z;
             decode(item, w0, h0, d0, n0, it_begin, it_end, z);
             if (do_stats && n0 != stat_n0) {
                 if (stat_n0 >= 0) flush_stats();
                 stat_n0 = n0;
             }
-            const int buf = local & 1;
-            const uint32_t t_base = tmem_base + (uint32_t)(buf * C::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
             const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
             const size_t v = row_ok ? ((size_t)d * P.H + h) * P.W + w : 0;
             const bool lead = z == 0;
-            mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
+            const int n_chains = (it_end - it_begin + P.chunk - 1) / P.chunk;
+            // ---- every chain: TMEM -> registers (summed, round-to-nearest), hand the buffer straight back so that the
+            // MMA warp never waits for the global-memory part of the epilogue
+            for (int ch = 0; ch < n_chains; ++ch, ++cl) {
+                const int buf = cl & 1;
+                const uint32_t t_base = tmem_base + (uint32_t)(buf * C::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
+                mbar_wait(&tmem_full_bar[buf], (cl >> 1) & 1);
+                tc_fence_after();
+                // pairs of 16-column loads with one wait each (LDW = 32 halves the round trips again where the register
+                // budget allows: BLOCK_N <= 64)
+                constexpr int LDW = (BLOCK_N == 32 || BLOCK_N == 64) ? HOLO_CONV_LDW : 16;
+#pragma unroll
+                for (int c0 = 0; c0 < BLOCK_N; c0 += LDW) {
+                    uint32_t acc[LDW], acc2[LDW];
+                    if constexpr (LDW == 32) tmem_ld_pair32(t_base + (uint32_t)c0, t_base + (uint32_t)(BLOCK_N + c0), acc, acc2);
+                    else tmem_ld_pair16(t_base + (uint32_t)c0, t_base + (uint32_t)(BLOCK_N + c0), acc, acc2);
+#pragma unroll
+                    for (int j = 0; j < LDW; ++j) {
+                        const float s2 = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+                        accv[c0 + j] = ch == 0 ? s2 : accv[c0 + j] + s2;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            }
+            // ---- scale, bias, residual, outputs, statistics
+#pragma unroll
             for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                uint32_t acc[16], acc2[16];
-                tmem_ld16(t_base + (uint32_t)c0, acc);
-                tmem_ld16(t_base + (uint32_t)(BLOCK_N + c0), acc2);
                 const int n = n0 + c0;
                 float vals[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) vals[j] = (__uint_as_float(acc[j]) + __uint_as_float(acc2[j])) * P.acc_scale;
+                for (int j = 0; j < 16; ++j) vals[j] = accv[c0 + j] * P.acc_scale;
                 if (P.bias && lead) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -414,10 +479,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
             }
-            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld16): hand the buffer back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
         if (do_stats) flush_stats();
     }
@@ -495,6 +556,10 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     int occ_smem = (227 * 1024) / (smem + 1024);
     int occ_tmem = 512 / (2 * Cfg<BLOCK_N>::TMEM_COLS);
     int occ = occ_smem < occ_tmem ? occ_smem : occ_tmem;
+    int occ_api = 0;   // registers bound the residency too (the epilogue keeps BLOCK_N partial sums per thread)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_api, k, NUM_THREADS, (size_t)smem) == cudaSuccess && occ_api > 0 &&
+        occ_api < occ)
+        occ = occ_api;
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
     const long long items = (long long)Q.m_tiles * Q.n_blocks * Q.nsplit;
@@ -598,6 +663,19 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
     P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
+    // chunked accumulation (see the MMA issuer): chains of ~HOLO_CONV_CHUNK (tap, slab) iterations, 0 = one chain per item
+    // (default 9 = three chains for a 27-tap x 1-slab item), balanced so that no short tail chain is left: every chain
+    // boundary costs ~0.3 us of tensor-pipe time (the TMEM -> register flush shares the TMEM port, profiles/r02b)
+    static const int chunk_env = [] {
+        const char* e = getenv("HOLO_CONV_CHUNK");
+        return e ? atoi(e) : 9;
+    }();
+    if (chunk_env > 0 && per > chunk_env) {
+        const int n_chains = (per + chunk_env - 1) / chunk_env;
+        P.chunk = (per + n_chains - 1) / n_chains;
+    } else {
+        P.chunk = 1 << 30;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (nsplit > 1 && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);

@@ -22,7 +22,7 @@ from . import ops
 from .cameras import AdaptiveRaySampler, ImplicitronRayBundle, PerspectiveCameras
 from .diffusion import ImplicitronGaussianDiffusion
 from .renderer import (EvaluationMode, HoloMultiPassEmissionAbsorptionRenderer, HoloVoxelGridImplicitFunction,
-                       ImplicitFunctionWrapper, RendererOutput)
+                       ImplicitFunctionWrapper, RendererOutput, coerce_mode, impl_of)
 from .unet import SimpleUnet3D
 
 
@@ -46,6 +46,18 @@ def _cat_render_outputs(outs: List[Optional[RendererOutput]], B: int, spatial) -
                           masks=cat([o.masks for o in outs]), normals=cat([o.normals for o in outs]),
                           points=cat([o.points for o in outs]), weights=cat([o.weights for o in outs]), aux=aux,
                           prev_stage=_cat_render_outputs([o.prev_stage for o in outs], B, spatial))
+
+
+def _clone_render_output(o: Optional[RendererOutput]) -> Optional[RendererOutput]:
+    if o is None:
+        return None
+
+    def c(t):
+        return t.clone() if torch.is_tensor(t) else t
+
+    return RendererOutput(features=c(o.features), depths=c(o.depths), masks=c(o.masks), normals=c(o.normals),
+                          points=c(o.points), weights=c(o.weights), aux={k: c(v) for k, v in o.aux.items()},
+                          prev_stage=_clone_render_output(o.prev_stage))
 
 
 class HoloDiffusionModel(nn.Module):
@@ -85,12 +97,33 @@ class HoloDiffusionModel(nn.Module):
         self._implicit_functions = nn.ModuleList([wrapper for _ in range(num_passes)])
         self._range_stats: Optional[torch.Tensor] = None
         self._t0: Optional[torch.Tensor] = None
-        # one CUDA graph per (device, grid shape, weights version): outputs live in static buffers that the next
-        # forward() overwrites -- clone what must outlive it
+        # one CUDA graph per (device, grid shape, weights version); its static output buffers are cloned on return
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
         self._sample_group = None   # set by shard_one_sample()
+
+    @classmethod
+    def from_parts(cls, *, resol: int, volume_extent: float, feature_size: int, net_3d, diffusion, raysampler, renderer,
+                   implicit_functions, render_image_width: int, render_image_height: int, chunk_size_grid: int = 4096,
+                   use_cuda_graph: bool = True) -> "HoloDiffusionModel":
+        """Assemble the model from plug-ins that something else constructed (the Implicitron config system through the
+        ``holo_diffusion`` shim: registry facades of SimpleUnet3D / the renderer / the implicit function, wrapped in
+        pytorch3d's own ImplicitFunctionWrapper).  Same forward path as the plain constructor."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.resol, self.volume_extent, self.feature_size = resol, volume_extent, feature_size
+        self.num_passes = len(implicit_functions)
+        self.render_image_width, self.render_image_height = render_image_width, render_image_height
+        self.chunk_size_grid = chunk_size_grid
+        self.net_3d_enabled, self.diffusion_enabled = net_3d is not None, diffusion is not None
+        self.net_3d, self.diffusion, self.raysampler, self.renderer = net_3d, diffusion, raysampler, renderer
+        self._implicit_functions = implicit_functions if isinstance(implicit_functions, nn.ModuleList) else \
+            nn.ModuleList(list(implicit_functions))
+        self._range_stats = self._t0 = None
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = self._graph_key = self._sample_group = None
+        return self
 
     def shard_one_sample(self, group=None, attn_min_tokens: int = 1 << 14):
         """Several GPUs cooperate on ONE grid and ONE view (BASELINE cfg #5): every rank calls
@@ -135,7 +168,7 @@ class HoloDiffusionModel(nn.Module):
             # output-range asserts (:426,:428) come from fused min/max passes and are checked once, after the
             # whole view has been queued
             ops.act_range(x_cl, V, C, 0, None, None, self._range_stats)
-            y_cl = self.net_3d._exec.forward_cl(x_cl, (R, R, R), self._t0)
+            y_cl = impl_of(self.net_3d)._exec.forward_cl(x_cl, (R, R, R), self._t0)
             grid_cl = torch.empty(V, C, device=dev)
             grid_cf = torch.empty(C * V, device=dev)
             ops.act_range(y_cl, V, C, 1, grid_cl, grid_cf, self._range_stats)
@@ -221,7 +254,12 @@ class HoloDiffusionModel(nn.Module):
             self._graph, self._graph_key = g, key
         self._copy_inputs(cam, voxel_features)
         self._graph.replay()
-        return self._g_out
+        # the graph writes into static buffers that the next replay overwrites; the reference returns fresh tensors
+        # on every call (a caller that collects preds across views must not end up with N copies of the last frame)
+        rendered, bundle, vox = self._g_out
+        bundle = ImplicitronRayBundle(*(t.clone() if torch.is_tensor(t) else t for t in (
+            bundle.origins, bundle.directions, bundle.lengths, bundle.xys, bundle.camera_ids, bundle.camera_counts)))
+        return _clone_render_output(rendered), bundle, vox.clone()
 
     def _copy_inputs(self, cam, voxel_features):
         self._g_vox.copy_(voxel_features, non_blocking=True)
@@ -238,14 +276,13 @@ class HoloDiffusionModel(nn.Module):
                 **kwargs) -> Dict[str, Any]:
         if image_rgb is not None:
             raise NotImplementedError("view-pooling encoder path (images -> voxel grid) is a 'next' row (SURVEY 8f)")
-        if evaluation_mode != EvaluationMode.EVALUATION:
+        if coerce_mode(evaluation_mode) != EvaluationMode.EVALUATION:
             raise NotImplementedError("training branch is a 'next' row (SURVEY 8f)")
         target_cameras = camera[[0]]  # n_targets = 1 (holo_diffusion_model.py:263-273,315)
         if voxel_features is None:
             voxel_features = self.sample_random_voxel_features()
         dev = voxel_features.device
-        if dev.type != "cuda":
-            raise ops.HoloError("HoloDiffusionModel: CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(dev, "HoloDiffusionModel")
         assert voxel_features.shape[0] == 1, "only one single voxel grid is supported per GPU"
         assert voxel_features.shape[1] == self.feature_size, "Wrong voxel feature size!"
         if self._range_stats is None or self._range_stats.device != dev:

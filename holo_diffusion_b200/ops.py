@@ -43,6 +43,13 @@ def _pair_f16(*ts) -> int:
     return 1 if fl == {True} else 0
 
 
+def require_cuda(device, who: str):
+    """There is no CPU fallback: anything that is not a CUDA device is an error (host-logic tests replace this
+    predicate together with the entry points they stand in for)."""
+    if torch.device(device).type != "cuda":
+        raise HoloError(f"{who}: CUDA tensors only (no CPU fallback)")
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -416,3 +423,49 @@ def decode_range(stats_host) -> Tuple[float, float, int]:
         return struct.unpack("f", struct.pack("i", i))[0]
 
     return dec(stats_host[0]), dec(stats_host[1]), int(stats_host[2])
+
+
+# ------------------------------------------------------------------ per-view post-processing (generate_samples.py)
+def depth_image(depth, mask, min_quantile=0.02, max_quantile=0.98, min_out=0.1, max_out=0.9, composite_white=True):
+    """(H, W) depth + mask -> ((3, H, W) depth visualisation, (2,) selected (min, max) depths)."""
+    H, W = depth.shape[-2:]
+    out = torch.empty(3, H, W, device=depth.device)
+    nf = torch.empty(2, device=depth.device)
+    lib().call("holo_depth_image", _ptr(depth), _ptr(mask), H * W, float(min_quantile), float(max_quantile),
+               float(min_out), float(max_out), 1 if composite_white else 0, _ptr(nf), _ptr(out), _stream())
+    return out, nf
+
+
+def frame_u8(src_chw, out_hw=None, out=None):
+    """(C, H, W) float image (C = 1 | 3) -> (h, w, 3) uint8 frame (clip, bilinear resize, round)."""
+    C, H, W = src_chw.shape
+    h, w = (H, W) if out_hw is None else out_hw
+    if out is None:
+        out = torch.empty(h, w, 3, dtype=torch.uint8, device=src_chw.device)
+    lib().call("holo_frame_u8", _ptr(src_chw), C, H, W, h, w, _ptr(out, torch.uint8), _stream())
+    return out
+
+
+MATERIALS = {   # shaded_depth_render.py:83-98: (ambient, diffuse, specular, shininess)
+    "high_contrast": ((0.5, 0.5, 0.5), (2.0, 2.0, 2.0), (1.0, 1.0, 0.9), 256.0),
+    "medium": ((1.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 0.9), 128.0),
+}
+
+
+def shade_depth(depth, mask, focal, pp, smooth_k: int, mask_thr=0.5, depth_thr=1e-2, material="medium",
+                bg=(1.0, 1.0, 1.0), light=(0.5, 0.3, 0.2)):
+    """(H, W) depth + mask of one view, NDC focal (fx, fy) / principal point (px, py) as floats ->
+    ((3, H, W) shaded render, (H, W) mask).  `light` = ambient / diffuse / specular strength of the point light at the
+    camera centre (pytorch3d PointLights defaults: mesh_render.py:66-68 builds it with none given); the material colours
+    multiply them (Gouraud: colour = ambient + diffuse * n.l + specular * (r.v)^shininess at every vertex)."""
+    H, W = depth.shape[-2:]
+    amb, dif, spec, shin = MATERIALS[material]
+    m10 = [a * light[0] for a in amb] + [d * light[1] for d in dif] + [s * light[2] for s in spec] + [shin]
+    dev = depth.device
+    out, om = torch.empty(3, H, W, device=dev), torch.empty(H, W, device=dev)
+    sd, ok = torch.empty(H, W, device=dev), torch.empty(H, W, dtype=torch.uint8, device=dev)
+    lib().call("holo_shade_depth", _ptr(depth), _ptr(mask), H, W, float(focal[0]), float(focal[1]), float(pp[0]),
+               float(pp[1]), int(smooth_k), float(mask_thr), float(depth_thr),
+               ctypes.cast((ctypes.c_float * 10)(*m10), ctypes.c_void_p), ctypes.cast(_host3(bg), ctypes.c_void_p),
+               _ptr(sd), _ptr(ok, torch.uint8), _ptr(out), _ptr(om), _stream())
+    return out, om

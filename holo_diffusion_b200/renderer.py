@@ -32,6 +32,16 @@ class EvaluationMode(enum.Enum):
     EVALUATION = "evaluation"
 
 
+def coerce_mode(mode) -> "EvaluationMode":
+    """Accept pytorch3d's own EvaluationMode (a different enum class with the same values) or the plain string."""
+    return mode if isinstance(mode, EvaluationMode) else EvaluationMode(getattr(mode, "value", mode))
+
+
+def impl_of(obj):
+    """The B200 module behind a registry facade (holo_diffusion/_plugin.py: `_impl` in the instance dict), or obj."""
+    return getattr(obj, "__dict__", {}).get("_impl", obj)
+
+
 @dataclass
 class RendererOutput:
     features: torch.Tensor
@@ -299,10 +309,10 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
             return False
         if len(implicit_functions) not in (1, 2) or type(self.raymarcher) is not EmissionAbsorptionRaymarcher:
             return False
-        w = implicit_functions[0]
-        if not isinstance(w, ImplicitFunctionWrapper) or any(f is not w for f in implicit_functions):
+        w = implicit_functions[0]   # ours or pytorch3d's ImplicitFunctionWrapper: `_fn` + late-bound `bound_args`
+        if not (hasattr(w, "_fn") and hasattr(w, "bound_args")) or any(f is not w for f in implicit_functions):
             return False
-        fn = w._fn
+        fn = impl_of(w._fn)
         if type(fn) is not HoloVoxelGridImplicitFunction or fn.render_normals or fn.render_mlp.head() is not None:
             return False
         return "voxel_grid_features" in w.bound_args or "voxel_grid_features_channels_last" in w.bound_args
@@ -310,7 +320,7 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
     def _forward_fused(self, ray_bundle: ImplicitronRayBundle, implicit_functions) -> RendererOutput:
         n_passes = len(implicit_functions)
         w = implicit_functions[0]
-        fn = w._fn
+        fn = impl_of(w._fn)
         grid = w.bound_args.get("voxel_grid_features")
         grid_cl = w.bound_args.get("voxel_grid_features_channels_last")
         if grid_cl is None:
@@ -363,6 +373,7 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
                 evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, **kwargs) -> RendererOutput:
         if not implicit_functions:
             raise ValueError("EA renderer expects implicit functions")
+        evaluation_mode = coerce_mode(evaluation_mode)
         if self.is_fused(implicit_functions, evaluation_mode):
             return self._forward_fused(ray_bundle, implicit_functions)
         return self._run_raymarcher(ray_bundle, list(implicit_functions), None, evaluation_mode)

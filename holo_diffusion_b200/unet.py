@@ -714,6 +714,5 @@ class SimpleUnet3D(Unet3DBase):
     def forward(self, x, timesteps, cond_features=None):
         if cond_features is not None:
             x = torch.cat([x, cond_features], dim=1)
-        if not x.is_cuda:
-            raise ops.HoloError("SimpleUnet3D: CUDA tensors only (no CPU fallback)")
+        ops.require_cuda(x.device, "SimpleUnet3D")
         return self._exec.forward(x, timesteps)

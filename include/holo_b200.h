@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 114
+#define HOLO_B200_VERSION 115
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -275,6 +275,34 @@ int holo_q_sample(const float* x0, const float* noise, const long long* t_i64, c
 int holo_range_init(int* stats4, void* stream);
 int holo_act_range(const float* x_cl, long long V, int C, int act, float* y_cl, float* y_cf, int* stats4,
                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Per-view post-processing of generate_samples.py
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Depth visualisation of one view: pytorch3d vis_utils.make_depth_image (exact order statistics at min_quantile /
+ * 1 - max_quantile over the pixels with depth > 1e-6 and mask > 0.5, normalisation into [min_out, max_out], * mask,
+ * clamp) followed by the white compositing v * mask + (1 - mask) and the repeat to 3 channels of
+ * _images_from_preds -- utils/render_utils/flyaround.py:470-479.  depth, mask (n_pixels); normfac2 (2) receives the
+ * selected (min, max); out_3n (3, n_pixels). */
+int holo_depth_image(const float* depth, const float* mask, int n_pixels, float min_quantile, float max_quantile,
+                     float min_out_depth, float max_out_depth, int composite_white, float* normfac2, float* out_3n,
+                     void* stream);
+
+/* One video frame: (C in {1,3}, H, W) float -> (out_h, out_w, 3) uint8: clip to [0, 1], bilinear resize, round.
+ * Replaces rendered_pred[k][0].clip(0, 1).cpu().numpy() + VideoWriter.write_frame(resize) --
+ * utils/render_utils/flyaround.py:588-595. */
+int holo_frame_u8(const float* src_chw, int C, int H, int W, int out_h, int out_w, void* dst_hw3_u8, void* stream);
+
+/* Shaded depth render of one view in screen space: box-smoothed depth (window 2 smooth_k + 1) -> camera-space vertex
+ * grid through the NDC intrinsics (fx, fy, px, py) -> area-weighted vertex normals of the valid quads' triangles ->
+ * Phong shading with a point light at the camera (material10 = ambient rgb, diffuse rgb, specular rgb, shininess),
+ * background bg3 elsewhere.  Replaces depth_to_shaded(method="mesh") -- utils/render_utils/shaded_depth_render.py:143-206
+ * (mesh construction :248-280, rendered from the mesh's own camera by mesh_render.py).  scratch_depth (H*W) floats,
+ * scratch_ok_u8 (H*W) bytes; out_3hw (3,H,W); out_mask (H*W) or NULL. */
+int holo_shade_depth(const float* depth, const float* mask, int H, int W, float fx, float fy, float px, float py,
+                     int smooth_k, float mask_thr, float depth_thr, const float* material10_host, const float* bg3_host,
+                     float* scratch_depth, void* scratch_ok_u8, float* out_3hw, float* out_mask, void* stream);
 
 #ifdef __cplusplus
 }

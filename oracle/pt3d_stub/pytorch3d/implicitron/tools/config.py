@@ -3,6 +3,7 @@ become constructor keyword arguments, torch.nn.Module.__init__ runs before the f
 (what expand_args_fields generates), `<field>_args` dicts exist for Configurable-typed fields, run_auto_creation
 calls create_<field>() / instantiates them."""
 import copy
+import dataclasses
 
 import torch
 
@@ -24,7 +25,11 @@ class Configurable:
         for name in hints:
             for klass in type(self).__mro__:
                 if name in vars(klass):
-                    setattr(self, name, copy.deepcopy(vars(klass)[name]))
+                    default = vars(klass)[name]
+                    if isinstance(default, dataclasses.Field):   # field(default_factory=...) as the real dataclass does
+                        default = default.default_factory() if default.default_factory is not dataclasses.MISSING \
+                            else default.default
+                    setattr(self, name, copy.deepcopy(default))
                     break
         for name, t in hints.items():
             if isinstance(t, type) and issubclass(t, Configurable) and name + "_args" not in kwargs:

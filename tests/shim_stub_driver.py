@@ -1,0 +1,121 @@
+"""Run by tests/test_shim_cpu.py in a fresh interpreter: the ``holo_diffusion`` drop-in package over the Implicitron
+config stand-in (oracle/pt3d_stub on sys.path => the registered facades) or without it (plain re-exports), with the
+C-ABI entry points replaced by torch / oracle stand-ins.  Prints one JSON object."""
+import json
+import math
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+mode = sys.argv[1]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+if mode == "stub":
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "pt3d_stub"))
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+import holo_diffusion_b200 as hd  # noqa: E402
+from holo_diffusion_b200 import ops  # noqa: E402
+
+import fake_model_ops  # noqa: E402
+
+fake_model_ops.install(ops)
+_fused_calls = []
+_rf = ops.render_fwd
+ops.render_fwd = lambda *a, **k: (_fused_calls.append(k.get("n_passes", 1)), _rf(*a, **k))[1]
+
+import holo_diffusion  # noqa: E402
+from holo_diffusion.holo_diffusion_model import HoloDiffusionModel  # noqa: E402  (experiment.py:73)
+from holo_diffusion.utils.checkpoint_utils import load_experiment  # noqa: E402  (generate_samples.py:28)
+from holo_diffusion.utils.render_utils.flyaround import render_flyaround  # noqa: E402  (generate_samples.py:29)
+
+res = {"have_config": holo_diffusion.HAVE_CONFIG}
+C, R, HW, S = 16, 8, 8, 8
+MODEL_ARGS = dict(   # the keys configs/base.yaml sets under model_HoloDiffusionModel_args
+    resol=R, feature_size=C, num_passes=2, render_image_width=HW, render_image_height=HW, chunk_size_grid=4096,
+    net_3d_enabled=True, net_3d_class_type="SimpleUnet3D",
+    net_3d_SimpleUnet3D_args=dict(model_channels=64, num_res_blocks=1, channel_mult=[1, 2], attention_resolutions=[2],
+                                  num_heads=2),
+    diffusion_enabled=True, diffusion_args=dict(num_steps=40),
+    raysampler_class_type="AdaptiveRaySampler", raysampler_AdaptiveRaySampler_args=dict(n_pts_per_ray_evaluation=S),
+    renderer_class_type="HoloMultiPassEmissionAbsorptionRenderer",
+    renderer_HoloMultiPassEmissionAbsorptionRenderer_args=dict(
+        n_pts_per_ray_fine_evaluation=4, raymarcher_EmissionAbsorptionRaymarcher_args=dict(bg_color=[1.0, 1.0, 1.0])),
+    implicit_function_class_type="HoloVoxelGridImplicitFunction",
+    implicit_function_HoloVoxelGridImplicitFunction_args=dict(render_mlp_args=dict(dnet_hidden_dim=32)))
+
+if mode == "stub":
+    from pytorch3d.implicitron.tools.config import registry
+    res["registered"] = sorted(registry.classes)
+    from holo_diffusion.utils.diffusion_utils import SimpleUnet3D, Unet3DBase
+    res["registry_get"] = registry.get(Unet3DBase, "SimpleUnet3D") is SimpleUnet3D
+
+def exact_pairs(m):   # the conv / attention stand-ins take exact operand "pairs": hi = value, lo = 0
+    ex = hd.renderer.impl_of(m.net_3d)._exec
+    ex.pair_dtype, ex.use_cuda_graph = torch.float32, False   # (no CUDA graphs on a CPU box)
+    return m
+
+
+torch.manual_seed(0)
+model = exact_pairs(HoloDiffusionModel(use_cuda_graph=False, **MODEL_ARGS))
+res["model_class"] = type(model).__module__ + "." + type(model).__name__
+keys = list(model.state_dict().keys())
+res["n_keys"] = len(keys)
+res["has_unet_key"] = "net_3d._net.input_blocks.0.0.weight" in keys
+res["has_mlp_key"] = "_implicit_functions.0._fn.render_mlp._density_net.mlp.0.0.weight" in keys
+res["foreign_keys"] = [k for k in keys if not k.startswith(("net_3d._net.", "_implicit_functions."))][:5]
+# the plain B200 model with the same weights gives the same view
+plain = exact_pairs(hd.HoloDiffusionModel(use_cuda_graph=False, **MODEL_ARGS))
+missing, unexpected = plain.load_state_dict(model.state_dict(), strict=True)
+grid = torch.tanh(torch.randn(1, C, R, R, R, generator=torch.Generator().manual_seed(1)))
+cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 4, -math.pi / 6, 10.0, (-0.0396, -0.8306, -0.5554), 3.2)
+a = model(camera=cams[[1]], voxel_features=grid, evaluation_mode=hd.EvaluationMode.EVALUATION)
+b = plain(camera=cams[[1]], voxel_features=grid)
+res["fused_render_calls"] = list(_fused_calls)   # facade plug-ins must still take the one-launch renderer
+res["preds_keys"] = sorted(a.keys())
+res["facade_vs_plain"] = float((a["images_render"] - b["images_render"]).abs().max())
+res["image_shape"] = list(a["images_render"].shape)
+res["prev_stage"] = a["rendered"].prev_stage is not None
+
+with tempfile.TemporaryDirectory() as tmp:
+    # generate_samples.py:87-138: exp_dir with expconfig.yaml + checkpoint -> load_experiment -> render_flyaround
+    cfg = {"model_factory_ImplicitronModelFactory_args": {"model_class_type": "HoloDiffusionModel",
+                                                          "model_HoloDiffusionModel_args": MODEL_ARGS},
+           "data_source_ImplicitronDataSource_args": {
+               "data_loader_map_provider_SequenceDataLoaderMapProvider_args": {"batch_size": 10}}}
+    yaml.safe_dump(cfg, open(os.path.join(tmp, "expconfig.yaml"), "w"))
+    sd = dict(model.state_dict())
+    sd["image_feature_extractor.stem.0.weight"] = torch.zeros(1)   # encoder-side keys of a real checkpoint are skipped
+    torch.save(sd, os.path.join(tmp, "model_epoch_00000007.pth"))
+    _, m2, data_source = load_experiment(None, tmp, None, (HW, HW), 3, torch.device("cpu"))
+    m2.use_cuda_graph = False
+    exact_pairs(m2)
+    if hasattr(m2, "_impl"):
+        m2._impl.use_cuda_graph = False
+    assert m2.net_3d_enabled and m2.diffusion_enabled
+    res["n_source_views"] = data_source.data_loader_map_provider.batch_size - m2.n_train_target_views
+    res["ckpt_loaded"] = bool(torch.equal(m2.state_dict()[keys[0]], model.state_dict()[keys[0]]))
+    out_dir = os.path.join(tmp, "generated_samples")
+    os.makedirs(out_dir)
+    written = render_flyaround(
+        dataset=None, sequence_name="sample_00000", model=m2, output_video_path=os.path.join(out_dir, "video"),
+        output_video_name="sample_00000", n_source_views=res["n_source_views"], n_flyaround_poses=3,
+        trajectory_type="simple_360", video_resize=(16, 16), device="cpu", up=(-0.0396, -0.8306, -0.5554),
+        trajectory_scale=1.3, camera_elevation=-30.0 * (2 * math.pi / 360), sample_mode=True,
+        progressive_sampling_steps_per_render=-1,
+        visualize_preds_keys=("images_render", "masks_render", "depths_render", "noise_render",
+                              "images_prev_stage_render", "features_prev_stage_render", "_shaded_depth_render",
+                              "_all_source_images"),
+        save_voxel_features=True)
+    import numpy as np
+    res["videos"] = {k: list(np.load(v).shape) for k, v in written.items() if v.endswith(".npy")}
+    res["video_dtype"] = str(np.load(next(iter(written.values()))).dtype) if written else None
+    res["saved_voxels"] = os.path.exists(os.path.join(out_dir, "sample_00000_voxel_features.pth"))
+    # progressive sampling: a render every k denoising steps (generate_samples.py:49)
+    written2 = render_flyaround(dataset=None, sequence_name="p", model=m2, output_video_path=os.path.join(out_dir, "pv"),
+                                n_flyaround_poses=2, trajectory_type="simple_360", device="cpu", sample_mode=True,
+                                progressive_sampling_steps_per_render=1, visualize_preds_keys=("images_render",))
+    res["progressive"] = {k: list(np.load(v).shape) for k, v in written2.items() if v.endswith(".npy")}
+print("RESULT " + json.dumps(res))
