@@ -13,6 +13,7 @@ from .cameras import (AdaptiveRaySampler, ImplicitronRayBundle, PerspectiveCamer
                       get_simple_360_camera_trajectory, look_at_view_transform)
 from .diffusion import ImplicitronGaussianDiffusion  # noqa: E402,F401
 from .model import HoloDiffusionModel  # noqa: E402,F401
+from .pipeline import ViewStream  # noqa: E402,F401
 from .renderer import (EmissionAbsorptionRaymarcher, EvaluationMode,  # noqa: E402,F401
                        HoloMultiPassEmissionAbsorptionRenderer, HoloVoxelGridImplicitFunction, ImplicitFunctionWrapper,
                        RayPointRefiner, RendererOutput, RenderMLP)

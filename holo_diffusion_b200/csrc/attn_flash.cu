@@ -501,7 +501,7 @@ __global__ void v_transpose_split_kernel(const float* __restrict__ qkv, int T, i
                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int pair_f16) {
     __shared__ float tile[32][33];
     const int C = heads * ch;
-    const int c0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const int c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;   // tokens on grid.x: T / 32 exceeds grid.y's 65535 at 128^3
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int t = t0 + i, c = c0 + threadIdx.x;
         float val = 0.f;
@@ -565,7 +565,7 @@ int launch_flash(const CUtensorMap* maps, const FlashParams& P, int q_tiles, int
 extern "C" int holo_v_transpose_split(const float* qkv_cl, int T, int heads, int ch, void* vt_hi_bf16,
                                       void* vt_lo_bf16, int pair_f16, void* stream) {
     HOLO_CHECK_ARG(qkv_cl && vt_hi_bf16 && vt_lo_bf16 && T > 0 && heads > 0 && ch > 0, "holo_v_transpose_split: bad args");
-    dim3 grid(holo_cdiv((long long)heads * ch, 32), holo_cdiv(T, 32));
+    dim3 grid(holo_cdiv(T, 32), holo_cdiv((long long)heads * ch, 32));
     v_transpose_split_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(qkv_cl, T, heads, ch, (uint16_t*)vt_hi_bf16,
                                                                             (uint16_t*)vt_lo_bf16, pair_f16);
     HOLO_CHECK_LAUNCH("holo_v_transpose_split");

@@ -38,7 +38,7 @@ struct Cfg {
     static constexpr int B_TILE_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 2);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*GN partials*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*GN partials*/ + 16 /*last-slice flag*/;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // [hi*hi + lo*hi | hi*lo]
 };
 
@@ -190,9 +190,14 @@ struct TcParams {
     float* out;
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
-    double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor (no split-K)
+    double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor
+    int* tile_counters;  // split-K + stats: one zeroed int per (M tile, N block); the LAST K slice to finish a tile
+                         // re-reads the summed tile and accumulates its statistics
     int k2_slabs;     // fused 1x1 "skip" operand: Cin2 / 64 extra K iterations after the taps x slabs main loop, reading
                       // the SECOND activation pair at the output voxel itself (no tap offset); 0 = none
+    long long* trace; // debug (holo_debug_conv_trace): CTA 0 stamps clock64 at [0] entry, [1] set-up done, [2] first TMA
+                      // issued, [3] first operands landed, [4] last MMA issued, [5] first accumulator ready, [6] first item
+                      // written, [7] exit
     int fmt;          // 0 = bf16 pairs, HOLO_FMT_F16 = fp16 pairs (all four operand halves)
     float acc_scale;  // accumulators are multiplied by this before bias / residual (undoes the weights' 2^e scale)
 };
@@ -218,6 +223,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     float* s_stat = reinterpret_cast<float*>(smem + n_stages * C::STAGE_BYTES + 256);  // [2][BLOCK_N] sum, sumsq
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#ifdef HOLO_CONV_TRACE   // debug build only (-DHOLO_CONV_TRACE): the stamps sit in the single-thread issue loops
+    const bool tr = P.trace != nullptr && blockIdx.x == 0;
+#else
+    constexpr bool tr = false;
+#endif
+    if (tr && threadIdx.x == 0) P.trace[0] = clock64();
     const int tiles_w = P.W / P.tw, tiles_h = P.H / P.th;
     const int rows = P.tw * P.th * P.td;
     const int taps = P.ksize * P.ksize * P.ksize;
@@ -250,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tr && threadIdx.x == 0) P.trace[1] = clock64();
     holo_pdl_trigger();   // (opt-in PDL build) the next kernel may be scheduled; it waits for this grid to complete
     holo_pdl_wait();      // everything above overlapped the predecessor's tail; no dependent access before this line
 
@@ -297,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kk, n0);
                     tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &map_b_lo, &full_bar[stage], kk, n0);
+                    if (tr && item == (int)blockIdx.x && it == it_begin) P.trace[2] = clock64();
                     if (++stage == n_stages) stage = 0, phase ^= 1;
                 }
             }
@@ -330,6 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int it = cb; it < ce; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (tr && lane == 0 && item == (int)blockIdx.x && it == it_begin) P.trace[3] = clock64();
                     if (elect_one()) {
                         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
                         const uint32_t a_lo = a_hi + A_TILE_BYTES;
@@ -350,13 +364,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
         }
+        if (tr && lane == 0) P.trace[4] = clock64();
     } else {
         // ================= epilogue =================
         const int q = warp % 4;  // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;
         const bool row_ok = r < rows;
         const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
-        const bool do_stats = P.stats != nullptr && !split;
+        const bool do_stats = P.stats != nullptr && (!split || P.tile_counters != nullptr);
+        int* s_last = reinterpret_cast<int*>(s_stat + 2 * BLOCK_N);   // "this CTA completed the tile" broadcast
         int stat_n0 = -1;
         auto flush_stats = [&]() {   // all 128 epilogue threads: smem partials -> global fp64, then clear
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -367,6 +383,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             for (int i = et; i < 2 * BLOCK_N; i += 128) s_stat[i] = 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        // GroupNorm statistics of the tensor being written: column sums of 16 columns over the warp's 32 rows by a butterfly
+        // reduce-scatter (16 values -> one complete column per lane pair), then shared atomics
+        auto add_stats = [&](const float (&vals)[16], int c0) {
+            float sv[16], qv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[j] = row_ok ? vals[j] : 0.f, qv[j] = sv[j] * sv[j];
+            int col = 0;
+#pragma unroll
+            for (int lvl = 16, n_keep = 8; lvl >= 2; lvl >>= 1, n_keep >>= 1) {
+                const bool up = (lane & lvl) != 0;
+#pragma unroll
+                for (int i = 0; i < n_keep; ++i) {
+                    const float ss = up ? sv[i] : sv[i + n_keep], sq = up ? qv[i] : qv[i + n_keep];
+                    float ks = up ? sv[i + n_keep] : sv[i], kq = up ? qv[i + n_keep] : qv[i];
+                    ks += __shfl_xor_sync(0xffffffffu, ss, lvl);
+                    kq += __shfl_xor_sync(0xffffffffu, sq, lvl);
+                    sv[i] = ks, qv[i] = kq;
+                }
+                col += up ? n_keep : 0;
+            }
+            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+            qv[0] += __shfl_xor_sync(0xffffffffu, qv[0], 1);
+            if ((lane & 1) == 0) {
+                atomicAdd(&s_stat[c0 + col], sv[0]);
+                atomicAdd(&s_stat[BLOCK_N + c0 + col], qv[0]);
+            }
         };
         if (do_stats) flush_stats();  // clears the partials
         int cl = 0;
@@ -389,6 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint32_t t_base = tmem_base + (uint32_t)(buf * C::TMEM_COLS) + ((uint32_t)(q * 32) << 16);
                 mbar_wait(&tmem_full_bar[buf], (cl >> 1) & 1);
                 tc_fence_after();
+                if (tr && et == 0 && cl == 0) P.trace[5] = clock64();
                 // pairs of 16-column loads with one wait each (LDW = 32 halves the round trips again where the register
                 // budget allows: BLOCK_N <= 64)
                 constexpr int LDW = (BLOCK_N == 32 || BLOCK_N == 64) ? HOLO_CONV_LDW : 16;
@@ -451,43 +495,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
                 }
-                if (do_stats) {
-                    // GroupNorm statistics of the tensor being written: column sums over the warp's 32 rows by a
-                    // butterfly reduce-scatter (16 values -> one complete column per lane pair), then shared atomics
-                    float sv[16], qv[16];
+                if (do_stats && !split) add_stats(vals, c0);
+            }
+            if (tr && et == 0 && item == (int)blockIdx.x) P.trace[6] = clock64();
+            if (do_stats && split) {
+                // split-K: the K slices of a tile add into the output with atomics, so no slice sees the sum -- the slice
+                // that arrives LAST at the tile's counter does: it re-reads the tile from L2 and accumulates its statistics
+                __threadfence();                                   // this thread's atomics before the count
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const int mt = item % P.m_tiles, nb = (item / P.m_tiles) % P.n_blocks;
+                    *s_last = atomicAdd(&P.tile_counters[mt * P.n_blocks + nb], 1) == P.nsplit - 1;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*s_last) {
+                    __threadfence();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sv[j] = row_ok ? vals[j] : 0.f, qv[j] = sv[j] * sv[j];
-                    int col = 0;
+                    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                        float vals[16];
+                        if (row_ok) {
+                            const float4* op = reinterpret_cast<const float4*>(P.out + v * P.out_pitch + n0 + c0);
 #pragma unroll
-                    for (int lvl = 16, n_keep = 8; lvl >= 2; lvl >>= 1, n_keep >>= 1) {
-                        const bool up = (lane & lvl) != 0;
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 t = __ldcg(op + j4);
+                                vals[j4 * 4] = t.x, vals[j4 * 4 + 1] = t.y, vals[j4 * 4 + 2] = t.z, vals[j4 * 4 + 3] = t.w;
+                            }
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < n_keep; ++i) {
-                            const float ss = up ? sv[i] : sv[i + n_keep], sq = up ? qv[i] : qv[i + n_keep];
-                            float ks = up ? sv[i + n_keep] : sv[i], kq = up ? qv[i + n_keep] : qv[i];
-                            ks += __shfl_xor_sync(0xffffffffu, ss, lvl);
-                            kq += __shfl_xor_sync(0xffffffffu, sq, lvl);
-                            sv[i] = ks, qv[i] = kq;
+                            for (int j = 0; j < 16; ++j) vals[j] = 0.f;
                         }
-                        col += up ? n_keep : 0;
-                    }
-                    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-                    qv[0] += __shfl_xor_sync(0xffffffffu, qv[0], 1);
-                    if ((lane & 1) == 0) {
-                        atomicAdd(&s_stat[c0 + col], sv[0]);
-                        atomicAdd(&s_stat[BLOCK_N + c0 + col], qv[0]);
+                        add_stats(vals, c0);
                     }
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last is rewritten by the next item
             }
         }
         if (do_stats) flush_stats();
     }
     __syncthreads();
+    if (tr && threadIdx.x == 0) P.trace[7] = clock64();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * C::TMEM_COLS));
     }
 }
+
+long long* g_conv_trace = nullptr;   // holo_debug_conv_trace
 
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -544,7 +597,7 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     TcParams Q = P;
     Q.m_tiles = tiles, Q.n_blocks = P.Cout / BLOCK_N, Q.nsplit = nsplit;
     Q.stages = Q.iters_per_split < Cfg<BLOCK_N>::STAGES ? Q.iters_per_split : Cfg<BLOCK_N>::STAGES;
-    const int smem = Q.stages * Cfg<BLOCK_N>::STAGE_BYTES + 1024 + 256 + 1024;
+    const int smem = Q.stages * Cfg<BLOCK_N>::STAGE_BYTES + 1024 + 256 + 1024 + 16;
     // persistent grid: as many CTAs as fit on the chip (shared memory and the 512 TMEM columns bound the residency)
     static int n_sm = 0;
     if (!n_sm) {
@@ -577,7 +630,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
                         double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f, const void* x2_hi = nullptr,
-                        const void* x2_lo = nullptr, int Cin2 = 0) {
+                        const void* x2_lo = nullptr, int Cin2 = 0, int* tile_counters = nullptr) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -661,7 +714,9 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.tw = tw, P.th = th, P.td = td, P.stride = stride, P.iters_per_split = per;
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
-    P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
+    P.tile_counters = tile_counters;
+    P.trace = g_conv_trace;
+    P.stats = ((nsplit == 1 || tile_counters) && out_pitch == Cout) ? stats : nullptr;
     P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
     // chunked accumulation (see the MMA issuer): chains of ~HOLO_CONV_CHUNK (tap, slab) iterations, 0 = one chain per item
     // (default 9 = three chains for a 27-tap x 1-slab item), balanced so that no short tail chain is left: every chain
@@ -697,7 +752,7 @@ int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int 
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, int operand_fmt,
-                              float acc_scale, void* stream) {
+                              float acc_scale, int* tile_counters, void* stream) {
     const int taps = ksize * ksize * ksize;
     // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
     // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
@@ -712,7 +767,11 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
-                        stats_ch, operand_fmt, acc_scale);
+                        stats_ch, operand_fmt, acc_scale, nullptr, nullptr, 0, tile_counters);
+}
+
+extern "C" long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout) {
+    return (long long)((D + 3) / 4) * ((H + 3) / 4) * ((W + 3) / 4) * ((Cout + 15) / 16);
 }
 
 // ResBlock tail in one launch: out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual): the 1x1 skip connection
@@ -722,14 +781,14 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
 extern "C" int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                                    int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo,
                                    const float* bias, const float* residual, int Cout, float* out, double* stats_ch,
-                                   int operand_fmt, float acc_scale, void* stream) {
+                                   int operand_fmt, float acc_scale, int* tile_counters, void* stream) {
     if (!skip_hi || !skip_lo || Cin_skip <= 0) {
         holo_set_error("holo_conv3d_tc_skip: the skip operand is missing");
         return HOLO_ERR_ARG;
     }
     return conv_tc_impl("holo_conv3d_tc_skip", x_hi, x_lo, Cin, Cin, D, H, W, 3, 1, w_hi, w_lo,
                         27LL * Cin + Cin_skip, bias, residual, Cout, Cout, out, nullptr, nullptr, stream, 0, stats_ch,
-                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip);
+                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip, tile_counters);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,
@@ -745,4 +804,11 @@ extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitc
     return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
                         residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream, out_is_zeroed, nullptr, operand_fmt,
                         acc_scale);
+}
+
+// Debug: subsequent convolution launches make CTA 0 write 8 clock64 stamps (TcParams::trace) into dev_buf8 (8 int64 on
+// the device); NULL switches it off.  Used by tools/conv_micro.py to see where a small launch spends its time.
+extern "C" int holo_debug_conv_trace(void* dev_buf8) {
+    g_conv_trace = reinterpret_cast<long long*>(dev_buf8);
+    return HOLO_OK;
 }

@@ -15,10 +15,12 @@
 // ------------------------------------------------------------------------------------------------
 // layout: (C, V) channels-first <-> (V, C) channels-last, smem-tiled transpose
 // ------------------------------------------------------------------------------------------------
-__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int swap_xy) {
     // src is (rows, cols) row-major, dst is (cols, rows)
     __shared__ float tile[32][33];
-    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    // the longer axis rides grid.x (2^31 - 1 blocks); grid.y is limited to 65535 (a 128^3 grid has V / 32 = 65536)
+    const int bx = swap_xy ? blockIdx.y : blockIdx.x, by = swap_xy ? blockIdx.x : blockIdx.y;
+    int c0 = bx * 32, r0 = by * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int r = r0 + i, c = c0 + threadIdx.x;
         if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
@@ -32,9 +34,10 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 
 extern "C" int holo_transpose2d(const float* src, float* dst, int rows, int cols, void* stream) {
     HOLO_CHECK_ARG(src && dst && rows > 0 && cols > 0, "holo_transpose2d: bad args");
-    dim3 grid(holo_cdiv(cols, 32), holo_cdiv(rows, 32));
-    HOLO_CHECK_ARG(grid.y <= 65535, "holo_transpose2d: too many rows (%d); put the long axis in cols", rows);
-    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, rows, cols);
+    const int swap_xy = rows > cols;
+    dim3 grid(holo_cdiv(swap_xy ? rows : cols, 32), holo_cdiv(swap_xy ? cols : rows, 32));
+    HOLO_CHECK_ARG(grid.y <= 65535, "holo_transpose2d: both dimensions exceed 65535 * 32 (%d x %d)", rows, cols);
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, rows, cols, swap_xy);
     HOLO_CHECK_LAUNCH("holo_transpose2d");
     return HOLO_OK;
 }

@@ -114,11 +114,12 @@ __global__ void frame_u8_kernel(const float* __restrict__ src, int C, int H, int
         const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
         const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
         const float wy = fy - (float)y0, wx = fx - (float)x0;
+        auto tap = [](float t) { return fminf(fmaxf(t, 0.f), 1.f); };   // the reference clips BEFORE it resizes
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float* p = src + (size_t)(C == 1 ? 0 : c) * H * W;
-            const float v = (1.f - wy) * ((1.f - wx) * p[y0 * W + x0] + wx * p[y0 * W + x1]) +
-                            wy * ((1.f - wx) * p[y1 * W + x0] + wx * p[y1 * W + x1]);
+            const float v = (1.f - wy) * ((1.f - wx) * tap(p[y0 * W + x0]) + wx * tap(p[y0 * W + x1])) +
+                            wy * ((1.f - wx) * tap(p[y1 * W + x0]) + wx * tap(p[y1 * W + x1]));
             dst[(size_t)i * 3 + c] = (uint8_t)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
         }
     }

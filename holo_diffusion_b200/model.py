@@ -12,6 +12,7 @@ Parameter names follow the reference so that checkpoints load: ``net_3d._net.*``
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional
 
@@ -56,7 +57,7 @@ def _clone_render_output(o: Optional[RendererOutput]) -> Optional[RendererOutput
         return t.clone() if torch.is_tensor(t) else t
 
     return RendererOutput(features=c(o.features), depths=c(o.depths), masks=c(o.masks), normals=c(o.normals),
-                          points=c(o.points), weights=c(o.weights), aux={k: c(v) for k, v in o.aux.items()},
+                          points=c(o.points), weights=c(o.weights), aux=dict(o.aux),
                           prev_stage=_clone_render_output(o.prev_stage))
 
 
@@ -254,11 +255,13 @@ class HoloDiffusionModel(nn.Module):
             self._graph, self._graph_key = g, key
         self._copy_inputs(cam, voxel_features)
         self._graph.replay()
-        # the graph writes into static buffers that the next replay overwrites; the reference returns fresh tensors
-        # on every call (a caller that collects preds across views must not end up with N copies of the last frame)
+        # The graph writes into static buffers that the next replay overwrites; the reference returns fresh tensors on
+        # every call, and a caller that collects preds across views must not end up with N copies of the last frame:
+        # the API outputs (images / depths / masks of every stage, the denoised grid) are cloned.  The ray bundle and
+        # the per-ray sample depths (aux["lengths"], 40 MB together) stay views of the static buffers.
         rendered, bundle, vox = self._g_out
-        bundle = ImplicitronRayBundle(*(t.clone() if torch.is_tensor(t) else t for t in (
-            bundle.origins, bundle.directions, bundle.lengths, bundle.xys, bundle.camera_ids, bundle.camera_counts)))
+        if os.environ.get("HOLO_GRAPH_NO_CLONE") == "1":   # A/B measurements only
+            return self._g_out
         return _clone_render_output(rendered), bundle, vox.clone()
 
     def _copy_inputs(self, cam, voxel_features):

@@ -304,29 +304,34 @@ FMT_F16 = 1   # include/holo_b200.h HOLO_FMT_F16
 
 
 def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None,
-              stride: int = 1, stats=None, w_scale: float = 1.0) -> int:
+              stride: int = 1, stats=None, w_scale: float = 1.0, counters=None) -> int:
     """dims = INPUT volume.  Returns the library status (0 ok, 1 ok but `stats` not produced, -3 unsupported shape);
     other errors raise.  stats: optional zeroed fp64 (Cout, 2) tensor receiving per-channel (sum, sumsq) of the output.
+    counters: optional zeroed int32 tensor (tile_counters(...) ints) that lets a split-K launch produce `stats` too.
     The operand format follows the dtype of the four halves (all bf16 or all fp16); the weight pair holds
     w_scale * w (a power of two; the kernel multiplies the accumulators by 1 / w_scale)."""
     fmt = FMT_F16 * _pair_f16(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo)
     rc = lib().try_call("holo_conv3d_tc", _ptr16(x_hi), _ptr16(x_lo), Cin, dims[0],
                         dims[1], dims[2], ksize, stride, _ptr16(w_hi), _ptr16(w_lo), _ptr(bias),
                         _ptr(residual), Cout, _ptr(out), _ptr16(out_hi), _ptr16(out_lo),
-                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _stream())
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(counters, torch.int32), _stream())
     if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
 
 
+def conv_tile_counters(out_dims, Cout) -> int:
+    return int(lib().cdll.holo_conv3d_tc_tile_counters(out_dims[0], out_dims[1], out_dims[2], Cout))
+
+
 def conv3d_tc_skip(x_hi, x_lo, Cin, skip_hi, skip_lo, Cin_skip, dims, w_hi, w_lo, bias, residual, Cout, out, stats=None,
-                   w_scale: float = 1.0) -> int:
+                   w_scale: float = 1.0, counters=None) -> int:
     """out = conv3^3(x) + conv1^1(skip) + bias (+ residual) in one launch (holo_conv3d_tc_skip); w = [Cout][27 Cin +
     Cin_skip] pairs.  Status as conv3d_tc."""
     fmt = FMT_F16 * _pair_f16(x_hi, x_lo, skip_hi, skip_lo, w_hi, w_lo)
     rc = lib().try_call("holo_conv3d_tc_skip", _ptr16(x_hi), _ptr16(x_lo), Cin, _ptr16(skip_hi), _ptr16(skip_lo), Cin_skip,
                         dims[0], dims[1], dims[2], _ptr16(w_hi), _ptr16(w_lo), _ptr(bias), _ptr(residual), Cout, _ptr(out),
-                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _stream())
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(counters, torch.int32), _stream())
     if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc_skip failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
@@ -469,3 +474,66 @@ def shade_depth(depth, mask, focal, pp, smooth_k: int, mask_thr=0.5, depth_thr=1
                ctypes.cast((ctypes.c_float * 10)(*m10), ctypes.c_void_p), ctypes.cast(_host3(bg), ctypes.c_void_p),
                _ptr(sd), _ptr(ok, torch.uint8), _ptr(out), _ptr(om), _stream())
     return out, om
+
+
+# ------------------------------------------------------------------ whole-graph denoiser (csrc/unet_exec.cu)
+class HoloUnetConfig(ctypes.Structure):   # include/holo_b200.h: holo_unet_config (same field order)
+    _fields_ = [("in_channels", _i), ("model_channels", _i), ("out_channels", _i), ("num_res_blocks", _i), ("n_levels", _i),
+                ("channel_mult", _i * 8), ("n_attention_resolutions", _i), ("attention_resolutions", _i * 8), ("num_heads", _i),
+                ("D", _i), ("H", _i), ("W", _i), ("pair_f16", _i), ("fuse_skip", _i), ("attn_kv_split", _i),
+                ("use_tensor_cores", _i)]
+
+
+class NativeUnet:
+    """holo_unet_* behind a small object: the C++ executor of the whole UNet forward.  `state_dict` maps the reference's
+    parameter names below `_net.` to fp32 CUDA tensors, which are BORROWED (kept alive here)."""
+
+    def __init__(self, state_dict, in_channels, model_channels, out_channels, num_res_blocks, channel_mult,
+                 attention_resolutions, num_heads, dims, pair_f16=True, fuse_skip=True, attn_kv_split=0,
+                 use_tensor_cores=True):
+        cm, ar = list(channel_mult), list(attention_resolutions)
+        cfg = HoloUnetConfig(in_channels, model_channels, out_channels, num_res_blocks, len(cm), (_i * 8)(*cm), len(ar),
+                             (_i * 8)(*ar), num_heads, dims[0], dims[1], dims[2], 1 if pair_f16 else 0,
+                             1 if fuse_skip else 0, int(attn_kv_split), 1 if use_tensor_cores else 0)
+        h = ctypes.c_void_p()
+        lib().call("holo_unet_create", ctypes.byref(cfg), ctypes.byref(h))
+        self._h, self.cfg = h, cfg
+        L = lib().cdll
+        self.names = [L.holo_unet_param_name(h, i).decode() for i in range(L.holo_unet_param_count(h))]
+        self._keep = {}
+        self.set_params(state_dict)
+
+    def set_params(self, state_dict, stream=None):
+        dev = None
+        for i, name in enumerate(self.names):
+            t = state_dict[name].detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            dev = t.device
+            self._keep[name] = t
+            lib().call("holo_unet_set_param", self._h, name.encode(), _ptr(t), t.numel())
+        self.packed = torch.empty(int(lib().cdll.holo_unet_packed_bytes(self._h)), dtype=torch.uint8, device=dev)
+        self.workspace = torch.empty(int(lib().cdll.holo_unet_workspace_bytes(self._h)), dtype=torch.uint8, device=dev)
+        lib().call("holo_unet_pack", self._h, _ptr(self.packed, torch.uint8), _stream())
+
+    def forward_cl(self, x_cl, t, out=None):
+        V = self.cfg.D * self.cfg.H * self.cfg.W
+        if out is None:
+            out = torch.empty(V, self.cfg.out_channels, device=x_cl.device)
+        lib().call("holo_unet_fwd_cl", self._h, _ptr(x_cl), _ptr(t, torch.int64), _ptr(out),
+                   _ptr(self.workspace, torch.uint8), _stream())
+        return out
+
+    def forward(self, x, t, out=None):
+        c = self.cfg
+        if out is None:
+            out = torch.empty(1, c.out_channels, c.D, c.H, c.W, device=x.device)
+        lib().call("holo_unet_fwd", self._h, _ptr(x), _ptr(t, torch.int64), _ptr(out), _ptr(self.workspace, torch.uint8),
+                   _stream())
+        return out
+
+    def __del__(self):
+        try:
+            lib().cdll.holo_unet_destroy(self._h)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass

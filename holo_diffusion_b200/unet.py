@@ -69,6 +69,8 @@ class UNetParams(nn.Module):
         super().__init__()
         self.in_channels, self.out_channels, self.model_channels = in_channels, out_channels, model_channels
         self.num_heads = num_heads
+        self.config = dict(num_res_blocks=num_res_blocks, channel_mult=tuple(channel_mult),
+                           attention_resolutions=tuple(attention_resolutions))
         emb = 4 * model_channels
         self.time_embed = nn.Sequential(nn.Linear(model_channels, emb), nn.SiLU(), nn.Linear(emb, emb))
         width = int(channel_mult[0] * model_channels)
@@ -260,6 +262,16 @@ class UNetExecutor:
         # n CTAs (auto: fill ~148 SMs, >= 2 key tiles per CTA) and merged by flash_combine_kernel: -0.23 ms per 64^3
         # step (profiles/r02a); "1" = one CTA per (query tile, head)
         self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "auto")
+        # HOLO_SPLITK_STATS=1: split-K convolutions produce the GroupNorm statistics themselves (the K slice that
+        # arrives last at a tile re-reads the atomically summed tile).  Measured on B200 (profiles/r02b): it removes 39
+        # gn_stats launches (0.59 -> 0.01 ms) but every slice then waits for its atomics to drain before it may count
+        # itself in (conv 6.20 -> 6.61 ms): a net LOSS of 0.13 ms per step, so it stays off
+        self.splitk_stats = os.environ.get("HOLO_SPLITK_STATS", "0") == "1"
+        # HOLO_UNET_NATIVE=1: one evaluation = ONE C-ABI call (holo_unet_fwd_cl, csrc/unet_exec.cu: the C++ twin of this
+        # executor, same kernels in the same order) instead of ~330 calls from the interpreter
+        self.native = os.environ.get("HOLO_UNET_NATIVE", "0") == "1"
+        self._native = None
+        self._native_key = None
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel
         self._graph = None
         self._graph_key = None
@@ -318,6 +330,19 @@ class UNetExecutor:
         self._arena_off += n
         return st
 
+    def _counter_slice(self, out_dims, cout: int):
+        """Zeroed per-tile arrival counters (int32 view of the same arena) for a convolution that may split K: the last
+        K slice of a tile then produces the GroupNorm statistics of the summed output (no separate statistics pass)."""
+        if not self.splitk_stats:
+            return None
+        n = ops.conv_tile_counters(out_dims, cout)
+        n8 = (n + 1) // 2   # fp64 slots
+        if self._arena_off + n8 > self._arena.numel():
+            return None
+        c = self._arena[self._arena_off:self._arena_off + n8].view(torch.int32)
+        self._arena_off += n8
+        return c
+
     # -- primitive ops -------------------------------------------------------------------------------------
     def _tc_ok(self, pc: _PackedConv, out_dims) -> bool:
         """Can this convolution (stride 1, after any upsample) run on the tcgen05 kernel?"""
@@ -374,8 +399,9 @@ class UNetExecutor:
             o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
             o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
         st = self._stats_slice(pc.cout) if want_stats else None
+        cnt = self._counter_slice(out_dims, pc.cout) if st is not None else None
         rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
-                           stride, st, pc.w_scale)
+                           stride, st, pc.w_scale, cnt)
         if rc not in (0, 1):
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
@@ -458,8 +484,9 @@ class UNetExecutor:
         Vo = h.V
         out = torch.empty(Vo, pf.cout, device=y_hi.device)
         st = self._stats_slice(pf.cout)
+        cnt = self._counter_slice(h.dims, pf.cout) if st is not None else None
         rc = ops.conv3d_tc_skip(y_hi, y_lo, pf.cin, raw[0], raw[1], pf.cin_skip, h.dims, pf.w_hi, pf.w_lo, pf.bias, None,
-                                pf.cout, out, st, pf.w_scale)
+                                pf.cout, out, st, pf.w_scale, cnt)
         if rc not in (0, 1):
             raise ops.HoloError("fused skip conv rejected a shape: " + ops.lib().cdll.holo_last_error().decode())
         self.tc_calls += 1
@@ -584,6 +611,8 @@ class UNetExecutor:
         """x_cl (V, Cin) channels-last fp32, t (1,) int64 on the device -> (V, Cout) channels-last."""
         p = self.p
         dev = x_cl.device
+        if self.native and self.attn_group is None and self.use_flash:
+            return self._native_forward_cl(x_cl, dims, t)
         if self._acc is None or self._acc.device != dev:
             self._acc = torch.zeros(2, 512, dtype=torch.float64, device=dev)
             self._acc_i = 0
@@ -615,6 +644,21 @@ class UNetExecutor:
             s = skips.pop()
             act = self._run(blk, _Act(act.x1, act.c1, act.dims, s.x1, s.c1, st1=act.st1, st2=s.st1), film_all)
         return self._conv_norm(p.out[2], act, p.out[0], None).x1
+
+    def _native_forward_cl(self, x_cl, dims, t):
+        key = (str(x_cl.device), tuple(dims), self._weights_signature(), self.pair_dtype, self.fuse_skip, self.attn_kv_split,
+               self.use_tc)
+        if self._native is None or self._native_key != key:
+            p = self.p
+            cfg = p.config
+            self._native = ops.NativeUnet(
+                {k: v for k, v in p.state_dict().items()}, p.in_channels, p.model_channels, p.out_channels,
+                cfg["num_res_blocks"], cfg["channel_mult"], cfg["attention_resolutions"], p.num_heads, dims,
+                pair_f16=self.pair_dtype == torch.float16, fuse_skip=self.fuse_skip,
+                attn_kv_split=0 if self.attn_kv_split == "auto" else int(self.attn_kv_split), use_tensor_cores=self.use_tc)
+            self._native_key = key
+        self.tc_calls += 1
+        return self._native.forward_cl(x_cl, t)
 
     # -- CUDA-graph replay of one denoiser evaluation (the 1000-step sampling loop calls it back to back) ------
     def _weights_signature(self):

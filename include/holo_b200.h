@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 115
+#define HOLO_B200_VERSION 117
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -178,23 +178,34 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
  * out_hi/out_lo (optional): the result as an operand pair in the same format (the attention's q, k).
  * Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
  * shapes it does not take.  stats_ch (optional, [Cout][2] doubles, pre-zeroed): per-channel (sum, sumsq) of the output
- * for the GroupNorm that consumes it, accumulated in the epilogue; the call returns 1 instead of 0 when it had to
- * split K and therefore did NOT produce them. */
+ * for the GroupNorm that consumes it, accumulated in the epilogue.  When the grid is split over K no slice sees the
+ * summed tile: with tile_counters (optional, holo_conv3d_tc_tile_counters(...) zeroed ints) the slice that finishes a
+ * tile last re-reads it and accumulates the statistics; without them the call returns 1 instead of 0 = done, but the
+ * statistics were NOT produced.  Long K loops are accumulated in chains (HOLO_CONV_CHUNK iterations, default 9) that
+ * the epilogue sums in registers: the tensor core truncates every add into the TMEM accumulator. */
 #define HOLO_FMT_F16 1
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
-                   void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, void* stream);
+                   void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, int* tile_counters,
+                   void* stream);
+/* Debug aid (library built with -DHOLO_CONV_TRACE, e.g. HOLO_NVCC_FLAGS=-DHOLO_CONV_TRACE python
+ * holo_diffusion_b200/build.py; a no-op otherwise): CTA 0 of every following tcgen05 convolution launch writes 8 clock64 stamps (entry, set-up done, first
+ * TMA issued, first operands landed, last MMA issued, first accumulator ready, first item written, exit) into the 8
+ * int64 at dev_buf8; NULL switches it off. */
+int holo_debug_conv_trace(void* dev_buf8);
+/* Number of ints tile_counters must hold for an OUTPUT volume (D, H, W) with Cout channels (an upper bound). */
+long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout);
 
 /* ResBlock tail in ONE launch (ResBlock._forward, unet.py:254-256, with a 1x1 skip_connection :222):
  *   out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual)
  * The skip convolution rides the 3^3 convolution's TMEM accumulator as Cin_skip / 64 extra K iterations.  w_hi / w_lo:
  * [Cout][27 * Cin + Cin_skip] pairs (taps first, then the 1x1 columns) under one common scale; bias = the sum of the two
  * biases.  Same shape rules, formats, statistics and return codes as holo_conv3d_tc (stride 1, Cin_skip % 64 == 0).
- * Numerically validated on a B200; opt-in in the executor (HOLO_FUSE_SKIP=1) until its speed has been measured. */
+ * The executor's default for ResBlocks with a skip convolution (HOLO_FUSE_SKIP=0 turns it off). */
 int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                         int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo, const float* bias,
                         const float* residual, int Cout, float* out, double* stats_ch, int operand_fmt,
-                        float acc_scale, void* stream);
+                        float acc_scale, int* tile_counters, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are 16-bit
  * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with
@@ -246,6 +257,48 @@ int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* ou
 int holo_timestep_embedding(const long long* t_i64, int n, int dim, const float* freqs, float* out, void* stream);
 int holo_linear_rows(const float* x, const float* W, const float* b, int M, int in_dim, int out_dim, int silu_in,
                      int silu_out, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole-graph denoiser: UNetModel.forward (unet.py:800-837) as configured by SimpleUnet3D
+ * (utils/diffusion_utils.py:41-86) in ONE call, for hosts without Python (csrc/unet_exec.cu walks the block list and
+ * issues the launches above in the order the Python executor does).
+ *   holo_unet_create         block list + parameter table + workspace plan from the configuration
+ *   holo_unet_param_*        enumerate the parameters: names are the reference's state-dict keys below `_net.`
+ *                            ("input_blocks.1.0.in_layers.2.weight", ...), numel their element counts
+ *   holo_unet_set_param      fp32 DEVICE pointer of one checkpoint tensor (borrowed; must stay valid)
+ *   holo_unet_pack           derived weight layouts (16-bit operand pairs, CUDA-core layouts, concatenated FiLM
+ *                            projection) into the caller's `packed` buffer of holo_unet_packed_bytes(); synchronises the
+ *                            stream once; call again after parameters change
+ *   holo_unet_fwd            x (1, C, D, H, W) fp32, t (1) int64 on the device -> out (1, C_out, D, H, W); asynchronous,
+ *                            graph-capturable; `workspace` of holo_unet_workspace_bytes() device bytes
+ *   holo_unet_fwd_cl         the same on channels-last tensors (V, C) -> (V, C_out) (no layout passes)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct holo_unet_config {
+    int in_channels, model_channels, out_channels, num_res_blocks;
+    int n_levels;
+    int channel_mult[8];
+    int n_attention_resolutions;
+    int attention_resolutions[8];   /* downsampling factors that carry attention (SimpleUnet3D.attention_resolutions) */
+    int num_heads;
+    int D, H, W;                    /* grid of one sample */
+    int pair_f16;                   /* 1 = fp16 operand pairs (default of the Python executor), 0 = bf16 pairs */
+    int fuse_skip;                  /* 1 = ResBlock tails with a skip convolution as one launch (holo_conv3d_tc_skip) */
+    int attn_kv_split;              /* 0 = auto (fill the SMs), n >= 1 = CTAs sharing the keys of one query tile */
+    int use_tensor_cores;           /* 0 = exact-fp32 CUDA-core kernels everywhere */
+} holo_unet_config;
+int holo_unet_create(const holo_unet_config* cfg, void** handle);
+int holo_unet_destroy(void* handle);
+int holo_unet_param_count(void* handle);
+const char* holo_unet_param_name(void* handle, int index);
+long long holo_unet_param_numel(void* handle, int index);
+int holo_unet_set_param(void* handle, const char* name, const float* dev_ptr, long long numel);
+long long holo_unet_packed_bytes(void* handle);
+long long holo_unet_workspace_bytes(void* handle);
+int holo_unet_pack(void* handle, void* packed_dev, void* stream);
+int holo_unet_fwd(void* handle, const float* x_ncdhw, const long long* t_dev, float* out_ncdhw, void* workspace,
+                  void* stream);
+int holo_unet_fwd_cl(void* handle, const float* x_cl, const long long* t_dev, float* out_cl, void* workspace,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Diffusion (gaussian_diffusion.py) and model glue (holo_diffusion_model.py)

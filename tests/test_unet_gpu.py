@@ -639,3 +639,43 @@ def test_attention_flash_split_kv(T, heads, ch, splits):
     print(f"split-KV T={T} ch={ch} x{splits}: vs un-split {rel_err(out, one):.2e}, vs fp64 {rel_err(out, ref):.2e}")
     assert rel_err(out, one) < 2e-5 and rel_err(out, ref) < 4e-5   # each split rounds against its own stabiliser
     assert rel_err(o_hi.float() + o_lo.float(), out) < 5e-7
+
+
+@pytest.mark.parametrize("R,kw", [
+    (16, dict(model_channels=64, num_res_blocks=2, channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(4, 8), num_heads=2)),
+    (32, dict(model_channels=64, num_res_blocks=2, channel_mult=(1, 1, 2, 4, 8), attention_resolutions=(4, 8), num_heads=2)),
+    (16, dict(model_channels=64, num_res_blocks=1, channel_mult=(1, 2), attention_resolutions=(1, 2), num_heads=2)),
+])
+def test_native_unet_matches_python_executor(R, kw):
+    """holo_unet_fwd (csrc/unet_exec.cu, the whole UNet forward behind one C-ABI call: parameter table by the
+    reference's names, packed weights, planned workspace) against the Python executor on the same kernels -- equal up
+    to the summation order of the split-K atomics -- and against the fp64 oracle; NCDHW entry point included."""
+    from holo_diffusion_b200 import ops
+    sd = uo.make_unet_state_dict(16, 16, seed=2, **{k: v for k, v in kw.items() if k in ("num_res_blocks", "channel_mult", "attention_resolutions")})
+    net = _build(16, 16, True, **kw)
+    net._net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = torch.tanh(torch.randn(1, 16, R, R, R, generator=torch.Generator().manual_seed(0))).cuda()
+    for tv in (0, 500):
+        tt = torch.full((1,), tv, dtype=torch.long, device="cuda")
+        ref_py = net(x, tt)
+        nat = ops.NativeUnet({k: v for k, v in net._net.state_dict().items()}, 16, kw["model_channels"], 16,
+                             kw["num_res_blocks"], kw["channel_mult"], kw["attention_resolutions"], kw["num_heads"], (R, R, R))
+        assert sorted(nat.names) == sorted(sd.keys())            # the reference's state-dict keys
+        out = nat.forward(x, tt)
+        torch.cuda.synchronize()
+        e_py = rel_err(out, ref_py)
+        e64 = rel_err(out, uo.unet_forward({k: v.double() for k, v in sd.items()}, x.cpu().double(), tt.cpu()))
+        print(f"native UNet {R}^3 t={tv}: vs python executor {e_py:.2e}, vs fp64 oracle {e64:.2e}, workspace "
+              f"{nat.workspace.numel() / 1e6:.0f} MB, packed {nat.packed.numel() / 1e6:.0f} MB")
+        assert e_py < 2e-6 and e64 < 2e-5
+    # through the executor switch, under CUDA-graph capture
+    net._exec.native = True
+    g = torch.cuda.CUDAGraph()
+    y0 = net(x, tt)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        y = net(x, tt)
+    g.replay()
+    torch.cuda.synchronize()
+    assert rel_err(y, ref_py) < 2e-6 and rel_err(y0, ref_py) < 2e-6
