@@ -28,7 +28,7 @@ constexpr int BM = 128;  // queries per CTA (UMMA M)
 constexpr int BN = 64;   // keys per tile = one 128-byte swizzle row of P
 constexpr int NTHREADS = 320;
 constexpr int SOFTMAX_THREADS = 256;
-constexpr int TMEM_COLS = 256;  // S0 [0,64) | S1 [64,128) | O [128, 128+ch)
+constexpr int TMEM_COLS = 512;  // S0 [0,64) | S1 [64,128) | O chain A [128, +ch) | O chain B [.., +ch) | O sum [.., +ch)
 constexpr int O_COL = 128;
 
 template <int CH>
@@ -137,6 +137,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n\t"
+        "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 // probabilities (a, b) in [0, 1] -> packed hi and lo halves (bf16x2, or fp16x2 without the saturation holo_split2
 // needs for unbounded values), a in the low half: 2 packed converts + 2 subtractions (+ 1 unpack for fp16)
 template <bool F16>
@@ -167,6 +184,7 @@ struct FlashParams {
     float* out;        // (T, C) fp32 or null
     __nv_bfloat16* out_hi;  // (T, C) hi/lo split of the result (same 16-bit format as the inputs), or null
     __nv_bfloat16* out_lo;
+    int o_chunk;            // key tiles per O accumulation chain (see "chunked O accumulation" in the kernel)
     int q_tile0;            // first 128-query tile of this launch (query-sharded attention: a rank owns a tile range)
     // split-KV (gridDim.z > 1): CTA z handles key tiles [z * kt_per_split, ...) with its OWN stabiliser m_z and writes
     // the un-normalised O_z (part_o: [z][T][C] fp32) and (m_z * scale_log2, rowsum_z) (part_ml: [z][heads][T] float2);
@@ -200,8 +218,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
     uint64_t* p_full = s_empty + 2;               // [2]
     uint64_t* p_empty = p_full + 2;               // [2]
     uint64_t* q_full = p_empty + 2;
-    uint64_t* o_full = q_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* o_full = q_full + 1;                // [2] chain buffer A / B holds a finished chain
+    uint64_t* o_free = o_full + 2;                // [2] the softmax warps have folded it into the running sum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m0 = (P.q_tile0 + (int)blockIdx.x) * BM;
@@ -224,7 +243,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         for (int b = 0; b < 2; ++b) mbar_init(&s_full[b], 1), mbar_init(&s_empty[b], SOFTMAX_THREADS / 32);
         for (int b = 0; b < 2; ++b) mbar_init(&p_full[b], SOFTMAX_THREADS), mbar_init(&p_empty[b], 1);
         mbar_init(q_full, 1);
-        mbar_init(o_full, 1);
+        for (int b = 0; b < 2; ++b) mbar_init(&o_full[b], 1), mbar_init(&o_free[b], SOFTMAX_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -305,28 +324,40 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         tc_fence_after();
         for (int j = 0; j < NT; ++j) issue_s(j);  // pass A
         issue_s(NT);                               // pass B prologue
+        // CHUNKED O ACCUMULATION: the tensor core truncates every add into the fp32 TMEM accumulator (a bias of
+        // ~3e-8 of the running sum per MMA, 12 MMAs per key tile): over T = 2 M keys (BASELINE cfg #5) one chain would
+        // be 1e-2 off.  O is therefore accumulated in chains of P.o_chunk key tiles, alternating between two TMEM
+        // buffers that start from zero; the softmax warps fold every finished chain into a running sum kept in a third
+        // TMEM region (tcgen05.ld / add in registers, round-to-nearest / tcgen05.st) while the next chain runs.
+        const int oc = P.o_chunk;
         for (int i = 0; i < NT; ++i) {
             const int j = NT + i;
             if (i + 1 < NT) issue_s(j + 1);        // S of the next tile overlaps the softmax of this one
             const int stage = j % F::STAGES;
             const int pb = i % F::PBUF;
+            const int chain = i / oc, ob = chain & 1, use = chain >> 1;
+            const bool first = (i % oc) == 0, last = (i % oc) == oc - 1 || i == NT - 1;
+            if (first && use > 0) {                // the chain that used this buffer two chains ago has been folded
+                mbar_wait(&o_free[ob], (uint32_t)(use - 1) & 1u);
+                tc_fence_after();
+            }
             mbar_wait(&p_full[pb], (uint32_t)(i / F::PBUF) & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d = tmem_base + O_COL;
+                const uint32_t d = tmem_base + O_COL + (uint32_t)(ob * CH);
                 const uint32_t v_base = smem_u32(kv_smem + stage * F::STAGE_BYTES + F::K_BYTES);
 #pragma unroll
                 for (int k = 0; k < BN / 16; ++k) {
                     const uint32_t a_hi = p_base + pb * F::P_BYTES + k * 32, a_lo = a_hi + F::P_HALF;
                     const uint32_t b_hi = v_base + k * 32, b_lo = b_hi + F::V_HALF;
                     const uint64_t dah = sw128_desc(a_hi), dbh = sw128_desc(b_hi);
-                    umma(d, dah, dbh, idesc_o, (i | k) != 0);
+                    umma(d, dah, dbh, idesc_o, (!first) || k != 0);
                     umma(d, dah, sw128_desc(b_lo), idesc_o, 1);
                     umma(d, sw128_desc(a_lo), dbh, idesc_o, 1);
                 }
                 umma_commit(&p_empty[pb]);
                 umma_commit(&kv_empty[stage]);
-                if (i == NT - 1) umma_commit(o_full);
+                if (last) umma_commit(&o_full[ob]);
             }
             __syncwarp();
         }
@@ -360,9 +391,36 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         float l0 = 0.f, l1 = 0.f;
         uint8_t* prow = p_smem + (size_t)(row / 8) * 1024 + (row % 8) * 128;
         const int swz = row % 8;
+        // chunked O accumulation (see the MMA warp): fold a finished chain into the running sum in TMEM; this thread
+        // owns its query row x half of the channels
+        const int oc = P.o_chunk;
+        const int n_chains = (NT + oc - 1) / oc;
+        const uint32_t o_sum = lane_addr + (uint32_t)(O_COL + 2 * CH);
+        auto fold = [&](int chain) {
+            const int ob = chain & 1;
+            mbar_wait(&o_full[ob], (uint32_t)(chain >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t src = lane_addr + (uint32_t)(O_COL + ob * CH);
+#pragma unroll 1
+            for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 16) {
+                uint32_t a[16];
+                tmem_ld16(src + (uint32_t)c0, a);
+                if (chain > 0) {
+                    uint32_t bsum[16];
+                    tmem_ld16(o_sum + (uint32_t)c0, bsum);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) a[k] = __float_as_uint(__uint_as_float(a[k]) + __uint_as_float(bsum[k]));
+                }
+                tmem_st16(o_sum + (uint32_t)c0, a);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[ob]);
+        };
         for (int i = 0; i < NT; ++i) {
             const int j = NT + i;
             const int b = j & 1;
+            if (i > oc && i % oc == 1) fold(i / oc - 1);   // one tile late: the chain's last P V has retired by now
             mbar_wait(&s_full[b], (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
             uint32_t hi[16], lo[16];  // 32 keys = 16 bf16x2 each
@@ -391,8 +449,27 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             mbar_arrive(&p_full[pb]);
         }
         // ---- epilogue: O / rowsum -> global (fp32 and / or the bf16 hi/lo split the projection conv consumes)
-        mbar_wait(o_full, 0);                            // all MMAs retired: the P buffer is free again
+        if (n_chains >= 2 && NT - (n_chains - 1) * oc < 2) fold(n_chains - 2);   // not reached inside the loop
+        const int last_chain = n_chains - 1;
+        mbar_wait(&o_full[last_chain & 1], (uint32_t)(last_chain >> 1) & 1u);   // all MMAs retired: P buffer free again
         tc_fence_after();
+        const uint32_t o_last = lane_addr + (uint32_t)(O_COL + (last_chain & 1) * CH);
+        // 32 channels of O = last chain (+ the folded earlier chains)
+        auto load_o = [&](int c0, uint32_t (&out)[32]) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t a[16];
+                tmem_ld16(o_last + (uint32_t)(c0 + 16 * hh), a);
+                if (n_chains >= 2) {
+                    uint32_t bsum[16];
+                    tmem_ld16(o_sum + (uint32_t)(c0 + 16 * hh), bsum);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) a[k] = __float_as_uint(__uint_as_float(a[k]) + __uint_as_float(bsum[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) out[16 * hh + k] = a[k];
+            }
+        };
         xch[half * BM + row] = l0 + l1;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float lsum = xch[row] + xch[BM + row];
@@ -405,7 +482,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
             float* po = P.part_o + (size_t)blockIdx.z * P.T * P.C + obase;
 #pragma unroll 1
             for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
-                tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
+                load_o(c0, v);
                 if (ok) {
                     float4* op = reinterpret_cast<float4*>(po + c0);
 #pragma unroll
@@ -420,7 +497,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
         const float inv = 1.0f / lsum;
 #pragma unroll 1
         for (int c0 = half * (CH / 2); c0 < (half + 1) * (CH / 2); c0 += 32) {
-            tmem_ld32(lane_addr + (uint32_t)(O_COL + c0), v);
+            load_o(c0, v);
             if (ok) {
                 float f[32];
 #pragma unroll
@@ -605,6 +682,12 @@ extern "C" int holo_attention_flash(const void* qkv_hi_bf16, const void* qkv_lo_
     P.scale_log2 = (softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf((float)ch)) * 1.4426950408889634f;
     P.out = out_cl, P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
     P.q_tile0 = q_begin / BM;
+    static const int o_chunk_env = [] {   // key tiles per O accumulation chain; >= 2 (64 tiles = 768 MMAs: bias ~2e-5)
+        const char* e = getenv("HOLO_ATTN_O_CHUNK");
+        const int v = e ? atoi(e) : 64;
+        return v < 2 ? (1 << 30) : v;
+    }();
+    P.o_chunk = o_chunk_env;
     const int q_tiles = (q_count + BM - 1) / BM;
     // split-KV: kv_splits CTAs share the key tiles of one (query tile, head); needs the caller's workspace
     const int nt_all = T / BN;

@@ -152,11 +152,44 @@ class HoloVoxelGridImplicitFunction(nn.Module):
     def allows_multiple_passes() -> bool:
         return True
 
-    @torch.no_grad()
+    differentiable = False   # True: autograd reaches the RenderMLP parameters even when the grid needs no gradient
+
     def forward(self, *, ray_bundle: Optional[ImplicitronRayBundle] = None, fun_viewpool=None, camera=None,
                 global_code=None, run_id=None, pass_number=None, pts_3d: Optional[torch.Tensor] = None,
                 voxel_grid_features: Optional[torch.Tensor] = None,
                 voxel_grid_features_channels_last: Optional[torch.Tensor] = None, **kwargs):
+        """Inference (no autograd graph) unless gradients are asked for: autograd enabled AND (the grid requires a
+        gradient or ``differentiable`` is set) -> the differentiable kernels of autograd.py (training)."""
+        if torch.is_grad_enabled() and (self.differentiable or
+                                        (voxel_grid_features is not None and voxel_grid_features.requires_grad)):
+            return self._forward_grad(ray_bundle=ray_bundle, pts_3d=pts_3d, voxel_grid_features=voxel_grid_features)
+        return self._forward_nograd(ray_bundle=ray_bundle, fun_viewpool=fun_viewpool, camera=camera,
+                                    global_code=global_code, run_id=run_id, pass_number=pass_number, pts_3d=pts_3d,
+                                    voxel_grid_features=voxel_grid_features,
+                                    voxel_grid_features_channels_last=voxel_grid_features_channels_last, **kwargs)
+
+    def _forward_grad(self, *, ray_bundle, pts_3d, voxel_grid_features):
+        from .autograd import ImplicitFunctionRays, compose_density_net
+        if ray_bundle is None or pts_3d is not None or self.render_normals or self.render_mlp.head() is not None:
+            raise NotImplementedError("differentiable implicit function: ray bundles only, no normals / feature head")
+        assert voxel_grid_features is not None and voxel_grid_features.shape[0] == 1, "one NCDHW voxel grid"
+        mlp = self.render_mlp
+        layers = [(seq[0].weight, seq[0].bias) for seq in mlp._density_net.mlp]
+        A, c = compose_density_net(layers, mlp._density_net.input_skips)
+        rl = mlp._radiance_net.mlp[0][0]
+        spatial = ray_bundle.lengths.shape
+        S = spatial[-1]
+        n = int(torch.Size(spatial[:-1]).numel())
+        dens, rgb = ImplicitFunctionRays.apply(voxel_grid_features, A, c, rl.weight, rl.bias,
+                                               ray_bundle.origins.reshape(n, 3), ray_bundle.directions.reshape(n, 3),
+                                               ray_bundle.lengths.reshape(n, S), self.volume_extent, mlp.dir_emb_dims)
+        return dens.view(*spatial, 1), rgb.view(*spatial, 3), {}
+
+    @torch.no_grad()
+    def _forward_nograd(self, *, ray_bundle: Optional[ImplicitronRayBundle] = None, fun_viewpool=None, camera=None,
+                        global_code=None, run_id=None, pass_number=None, pts_3d: Optional[torch.Tensor] = None,
+                        voxel_grid_features: Optional[torch.Tensor] = None,
+                        voxel_grid_features_channels_last: Optional[torch.Tensor] = None, **kwargs):
         """-> densities (...,S,1), features (...,S,3[+feature_dim]), aux {"normals": (...,S,3)} (:182-269).
         One ``holo_if_fwd`` launch: ray points, trilinear sampling, RenderMLP and the analytic normals."""
         assert voxel_grid_features is not None or voxel_grid_features_channels_last is not None, \
@@ -221,10 +254,35 @@ class EmissionAbsorptionRaymarcher(nn.Module):
         self.bg_color = tuple(float(x) for x in bg_color)
         self.background_opacity = float(background_opacity)
 
-    @torch.no_grad()
     def forward(self, rays_densities: torch.Tensor, rays_features: torch.Tensor, aux: Dict[str, Any],
                 ray_lengths: torch.Tensor, ray_deltas: Optional[torch.Tensor] = None, density_noise_std: float = 0.0,
                 **kwargs) -> RendererOutput:
+        if torch.is_grad_enabled() and (rays_densities.requires_grad or rays_features.requires_grad):
+            return self._forward_grad(rays_densities, rays_features, aux, ray_lengths, ray_deltas, density_noise_std)
+        return self._forward_nograd(rays_densities, rays_features, aux, ray_lengths, ray_deltas, density_noise_std, **kwargs)
+
+    def _forward_grad(self, rays_densities, rays_features, aux, ray_lengths, ray_deltas, density_noise_std):
+        from .autograd import EARaymarch
+        if ray_deltas is not None or "normals" in aux:
+            raise NotImplementedError("differentiable ray marcher: no explicit ray_deltas, no normals")
+        spatial = ray_lengths.shape[:-1]
+        S = ray_lengths.shape[-1]
+        n = int(torch.Size(spatial).numel())
+        Fd = rays_features.shape[-1]
+        if len(self.bg_color) not in (1, Fd):
+            raise ValueError(f"Wrong number of background color channels: {len(self.bg_color)} for {Fd} features")
+        noise = None
+        if density_noise_std > 0.0:   # rays_densities + randn_like * std before the relu (holo_multipass_ea.py:87-91)
+            noise = (torch.randn(n, S, device=ray_lengths.device) * density_noise_std).contiguous()
+        f, d, m, w = EARaymarch.apply(rays_densities.reshape(n, S), rays_features.reshape(n, S, Fd),
+                                      ray_lengths.reshape(n, S), noise, tuple(self.bg_color), self.background_opacity)
+        return RendererOutput(features=f.view(*spatial, Fd), depths=d.view(*spatial, 1), masks=m.view(*spatial, 1),
+                              weights=w.view(*spatial, S), aux=dict(aux))
+
+    @torch.no_grad()
+    def _forward_nograd(self, rays_densities: torch.Tensor, rays_features: torch.Tensor, aux: Dict[str, Any],
+                        ray_lengths: torch.Tensor, ray_deltas: Optional[torch.Tensor] = None, density_noise_std: float = 0.0,
+                        **kwargs) -> RendererOutput:
         if ray_deltas is not None:
             raise NotImplementedError("explicit ray_deltas")
         spatial = ray_lengths.shape[:-1]
@@ -363,17 +421,29 @@ class HoloMultiPassEmissionAbsorptionRenderer(nn.Module):
         if not self.return_weights:
             output.weights = None
         if len(implicit_functions) > 1:
-            fine_ray_bundle = self._refiners[evaluation_mode](ray_bundle, weights)
+            fine_ray_bundle = self._refiners[evaluation_mode](ray_bundle, weights.detach())
             output = self._run_raymarcher(fine_ray_bundle, implicit_functions[1:], output, evaluation_mode,
                                           pass_number=pass_number + 1)
         return output
 
-    @torch.no_grad()
+    @staticmethod
+    def _wants_grad(implicit_functions) -> bool:
+        for w in implicit_functions:
+            g = getattr(w, "bound_args", {}).get("voxel_grid_features")
+            if (g is not None and g.requires_grad) or getattr(impl_of(getattr(w, "_fn", w)), "differentiable", False):
+                return True
+        return False
+
     def forward(self, ray_bundle: ImplicitronRayBundle, implicit_functions: List[ImplicitFunctionWrapper],
                 evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, **kwargs) -> RendererOutput:
         if not implicit_functions:
             raise ValueError("EA renderer expects implicit functions")
         evaluation_mode = coerce_mode(evaluation_mode)
-        if self.is_fused(implicit_functions, evaluation_mode):
-            return self._forward_fused(ray_bundle, implicit_functions)
-        return self._run_raymarcher(ray_bundle, list(implicit_functions), None, evaluation_mode)
+        if torch.is_grad_enabled() and self._wants_grad(implicit_functions):
+            # training: the reference's recursion on the differentiable per-stage kernels (autograd.py); the refiner
+            # inside stays under no_grad as in pytorch3d
+            return self._run_raymarcher(ray_bundle, list(implicit_functions), None, evaluation_mode)
+        with torch.no_grad():
+            if self.is_fused(implicit_functions, evaluation_mode):
+                return self._forward_fused(ray_bundle, implicit_functions)
+            return self._run_raymarcher(ray_bundle, list(implicit_functions), None, evaluation_mode)

@@ -267,9 +267,11 @@ class UNetExecutor:
         # gn_stats launches (0.59 -> 0.01 ms) but every slice then waits for its atomics to drain before it may count
         # itself in (conv 6.20 -> 6.61 ms): a net LOSS of 0.13 ms per step, so it stays off
         self.splitk_stats = os.environ.get("HOLO_SPLITK_STATS", "0") == "1"
-        # HOLO_UNET_NATIVE=1: one evaluation = ONE C-ABI call (holo_unet_fwd_cl, csrc/unet_exec.cu: the C++ twin of this
-        # executor, same kernels in the same order) instead of ~330 calls from the interpreter
-        self.native = os.environ.get("HOLO_UNET_NATIVE", "0") == "1"
+        # One evaluation = ONE C-ABI call (holo_unet_fwd_cl, csrc/unet_exec.cu: the C++ twin of this executor, same
+        # kernels in the same order; equal to 7e-7, the split-K atomics' order) instead of ~330 calls from the
+        # interpreter: an eager step drops from 10.9 to 10.3 ms on B200 (profiles/r02c).  HOLO_UNET_NATIVE=0 walks the
+        # blocks in Python (kept for the query-sharded multi-GPU attention and for per-call instrumentation)
+        self.native = os.environ.get("HOLO_UNET_NATIVE", "1") == "1"
         self._native = None
         self._native_key = None
         self.use_cuda_graph = False   # set by SimpleUnet3D(use_cuda_graph=True) / HoloDiffusionModel

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 117
+#define HOLO_B200_VERSION 118
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -257,6 +257,29 @@ int holo_attention_simt(const float* qkv_cl, int T, int heads, int ch, float* ou
 int holo_timestep_embedding(const long long* t_i64, int n, int dim, const float* freqs, float* out, void* stream);
 int holo_linear_rows(const float* x, const float* W, const float* b, int M, int in_dim, int out_dim, int silu_in,
                      int silu_out, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward of the staged renderer (renderer half): what objective.backward()
+ * (trainer/training_loop.py:518-556) propagates through the ray marcher and the implicit function for the mask_sample
+ * rays of a training step (configs/base.yaml:132-134).  The refiner runs under no_grad; ray lengths carry no gradient.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* EmissionAbsorptionRaymarcher backward.  Inputs as holo_ea_raymarch (density_noise = the noise the forward added, or
+ * NULL); bg_dev (feat_dim) on the DEVICE; grad_* = dL/d(out_features (n,F), out_depths (n), out_masks (n), out_weights
+ * (n,S)), the last three optional.  d_densities (n,S), d_features (n,S,F). */
+int holo_ea_raymarch_bwd(const float* densities, const float* features, const float* lengths, const float* density_noise,
+                         int n_rays, int S, int feat_dim, const float* bg_dev, float background_opacity,
+                         const float* grad_features, const float* grad_depths, const float* grad_masks,
+                         const float* grad_weights, float* d_densities, float* d_features, void* stream);
+
+/* HoloVoxelGridImplicitFunction backward for ray points (same inputs as holo_if_fwd in ray mode, no feature head):
+ * grad_densities (P), grad_rgb (P,3) -> ACCUMULATED into caller-zeroed d_grid_dhwc (D,H,W,C) (trilinear scatter-add,
+ * grid_sampler_3d backward), d_W_eff (hidden+1, C), d_b_eff (hidden+1) of the collapsed density net and d_Wr (3, hidden +
+ * E), d_br (3) of the radiance layer.  Forward activations are recomputed. */
+int holo_if_bwd(const float* grid_dhwc, int D, int H, int W, int C, float volume_extent, const float* packed_mlp,
+                int hidden, int n_harmonic, const float* origins, const float* dirs, const float* lengths,
+                long long n_points, int S, const float* grad_densities, const float* grad_rgb, float* d_grid_dhwc,
+                float* d_W_eff, float* d_b_eff, float* d_Wr, float* d_br, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Whole-graph denoiser: UNetModel.forward (unet.py:800-837) as configured by SimpleUnet3D

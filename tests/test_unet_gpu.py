@@ -535,6 +535,7 @@ def test_unet_attention_at_every_level_16():
     from holo_diffusion_b200 import ops
     orig = ops.attention_flash
     ops.attention_flash = lambda *a, **k: (calls.append((a[4], a[6])), orig(*a, **k))[1]
+    net._exec.native = False     # walk the blocks from Python so that the dispatch can be observed
     try:
         out = net(x.cuda(), tt.cuda())
     finally:
@@ -542,8 +543,10 @@ def test_unet_attention_at_every_level_16():
     torch.cuda.synchronize()
     assert (4096, 64) in calls and (512, 64) in calls, calls   # (T, padded head width) of the fused launches
     e = rel_err(out, ref)
-    print(f"unet 16^3, attention at every level: vs fp32 oracle {e:.2e}")
-    assert e < 2e-5
+    net._exec.native = True      # the C++ executor pads the heads itself (pack_pairs_kernel, PadSpec)
+    e_native = rel_err(net(x.cuda(), tt.cuda()), ref)
+    print(f"unet 16^3, attention at every level: vs fp32 oracle {e:.2e} (python executor), {e_native:.2e} (native)")
+    assert e < 2e-5 and e_native < 2e-5
 
 
 @pytest.mark.parametrize("Cin,Cskip,Cout,dims", [
@@ -679,3 +682,34 @@ def test_native_unet_matches_python_executor(R, kw):
     g.replay()
     torch.cuda.synchronize()
     assert rel_err(y, ref_py) < 2e-6 and rel_err(y0, ref_py) < 2e-6
+
+
+def _attn_check(env_chunk, cases):
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    if env_chunk is None:
+        env.pop("HOLO_ATTN_O_CHUNK", None)
+    else:
+        env["HOLO_ATTN_O_CHUNK"] = str(env_chunk)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "diagnostics", "attn_chunk_check.py"), *cases],
+                       capture_output=True, text=True, timeout=150, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_attention_flash_chunked_o_accumulation():
+    """O is accumulated in chains of HOLO_ATTN_O_CHUNK key tiles that the softmax warps fold into a running sum
+    (the tensor core truncates every add into the TMEM accumulator).  Short chains (3, 2 tiles) exercise every
+    fold schedule: full chains, a one-tile last chain (folded after the loop), two chains only, with split-KV."""
+    cases = ["1024,1,64,1", "640,2,64,1", "192,1,64,1", "448,1,128,1", "2048,2,64,3", "128,1,64,1"]
+    for chunk in (3, 2):
+        res = _attn_check(chunk, cases)
+        print(res)
+        assert all(res[c] < 2e-5 for c in cases), res
+    # a long key axis: one chain per row (chunking off) vs chains of 64 tiles (the default)
+    long_case = ["32768,1,64,1"]
+    off, on = _attn_check(0, long_case)[long_case[0]], _attn_check(None, long_case)[long_case[0]]
+    print(f"T = 32768: one chain {off:.2e}, chains of 64 tiles {on:.2e}")
+    assert on < 3e-5 and on < off
