@@ -191,8 +191,8 @@ struct TcParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor
-    int* tile_counters;  // split-K + stats: one zeroed int per (M tile, N block); the LAST K slice to finish a tile
-                         // re-reads the summed tile and accumulates its statistics
+    int* tile_counters;  // split-K through the workspace: one zeroed int per (M tile, N block) -- the LAST K slice to
+    float* partials;     // finish a tile reduces the slices parked in `partials` ([slice][tile][128][BLOCK_N] floats)
     int k2_slabs;     // fused 1x1 "skip" operand: Cin2 / 64 extra K iterations after the taps x slabs main loop, reading
                       // the SECOND activation pair at the output voxel itself (no tap offset); 0 = none
     long long* trace; // debug (holo_debug_conv_trace): CTA 0 stamps clock64 at [0] entry, [1] set-up done, [2] first TMA
@@ -371,7 +371,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int r = q * 32 + lane;
         const bool row_ok = r < rows;
         const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
-        const bool do_stats = P.stats != nullptr && (!split || P.tile_counters != nullptr);
+        const bool ws = split && P.partials != nullptr;   // deterministic split-K through a workspace (see below)
+        const bool do_stats = P.stats != nullptr && (!split || ws);
         int* s_last = reinterpret_cast<int*>(s_stat + 2 * BLOCK_N);   // "this CTA completed the tile" broadcast
         int stat_n0 = -1;
         auto flush_stats = [&]() {   // all 128 epilogue threads: smem partials -> global fp64, then clear
@@ -451,21 +452,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
             }
-            // ---- scale, bias, residual, outputs, statistics
-#pragma unroll
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            // ---- scale, bias, residual, outputs, statistics of 16 finished columns
+            auto emit = [&](float (&vals)[16], int c0, bool add_bias_res, bool atomic) {
                 const int n = n0 + c0;
-                float vals[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) vals[j] = accv[c0 + j] * P.acc_scale;
-                if (P.bias && lead) {
+                if (P.bias && add_bias_res) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n) + j4);
                         vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
                     }
                 }
-                if (P.residual && lead && row_ok) {
+                if (P.residual && add_bias_res && row_ok) {
                     const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -474,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
                 if (row_ok) {
-                    if (P.out && split) {
+                    if (P.out && atomic) {
                         float* op = P.out + v * P.out_pitch + n;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) atomicAdd(op + j, vals[j]);
@@ -495,40 +492,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         lp[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]), lp[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                     }
                 }
-                if (do_stats && !split) add_stats(vals, c0);
-            }
-            if (tr && et == 0 && item == (int)blockIdx.x) P.trace[6] = clock64();
-            if (do_stats && split) {
-                // split-K: the K slices of a tile add into the output with atomics, so no slice sees the sum -- the slice
-                // that arrives LAST at the tile's counter does: it re-reads the tile from L2 and accumulates its statistics
-                __threadfence();                                   // this thread's atomics before the count
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    const int mt = item % P.m_tiles, nb = (item / P.m_tiles) % P.n_blocks;
-                    *s_last = atomicAdd(&P.tile_counters[mt * P.n_blocks + nb], 1) == P.nsplit - 1;
+                if (do_stats && !atomic) add_stats(vals, c0);
+            };
+            if (!ws) {
+#pragma unroll
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                    float vals[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) vals[j] = accv[c0 + j] * P.acc_scale;
+                    emit(vals, c0, lead, split);   // split without a workspace: fp32 atomics into the zeroed output
                 }
+            } else {
+                // DETERMINISTIC SPLIT-K: every K slice parks its raw partial tile in the workspace ([slice][tile][128][N],
+                // plain stores); the slice that arrives LAST at the tile's counter sums the slices in slice order (the
+                // result does not depend on who arrives last), applies scale / bias / residual, writes the output once
+                // (no zero-fill, no atomics) and accumulates the GroupNorm statistics of the finished tile.
+                const int mt = item % P.m_tiles, nb = (item / P.m_tiles) % P.n_blocks;
+                const size_t tile_floats = (size_t)BLOCK_M * BLOCK_N;
+                const size_t tile_id = (size_t)mt * P.n_blocks + nb;
+                float* mine = P.partials + ((size_t)z * P.m_tiles * P.n_blocks + tile_id) * tile_floats + (size_t)r * BLOCK_N;
+#pragma unroll
+                for (int c4 = 0; c4 < BLOCK_N / 4; ++c4)
+                    __stcg(reinterpret_cast<float4*>(mine) + c4,
+                           make_float4(accv[c4 * 4], accv[c4 * 4 + 1], accv[c4 * 4 + 2], accv[c4 * 4 + 3]));
+                __threadfence();                                   // this thread's partial before the count
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) *s_last = atomicAdd(&P.tile_counters[tile_id], 1) == P.nsplit - 1;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (*s_last) {
                     __threadfence();
+                    const float* base = P.partials + tile_id * tile_floats + (size_t)r * BLOCK_N;
+                    const size_t slice_stride = (size_t)P.m_tiles * P.n_blocks * tile_floats;
 #pragma unroll
                     for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
                         float vals[16];
-                        if (row_ok) {
-                            const float4* op = reinterpret_cast<const float4*>(P.out + v * P.out_pitch + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vals[j] = 0.f;
+                        for (int zz = 0; zz < P.nsplit; ++zz) {
+                            const float4* pp = reinterpret_cast<const float4*>(base + (size_t)zz * slice_stride + c0);
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 t = __ldcg(op + j4);
-                                vals[j4 * 4] = t.x, vals[j4 * 4 + 1] = t.y, vals[j4 * 4 + 2] = t.z, vals[j4 * 4 + 3] = t.w;
+                                const float4 t = __ldcg(pp + j4);
+                                vals[j4 * 4] += t.x, vals[j4 * 4 + 1] += t.y, vals[j4 * 4 + 2] += t.z, vals[j4 * 4 + 3] += t.w;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) vals[j] = 0.f;
                         }
-                        add_stats(vals, c0);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vals[j] *= P.acc_scale;
+                        emit(vals, c0, true, false);
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last is rewritten by the next item
             }
+            if (tr && et == 0 && item == (int)blockIdx.x) P.trace[6] = clock64();
         }
         if (do_stats) flush_stats();
     }
@@ -625,12 +640,15 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
 
 }  // namespace
 
+extern "C" long long holo_conv3d_tc_splitk_bytes(void) { return 64LL << 20; }
+
 static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int Cin, long long x_pitch, int Din, int Hin,
                         int Win, int ksize, int stride, const void* w_hi, const void* w_lo, long long w_pitch,
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
                         double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f, const void* x2_hi = nullptr,
-                        const void* x2_lo = nullptr, int Cin2 = 0, int* tile_counters = nullptr) {
+                        const void* x2_lo = nullptr, int Cin2 = 0, int* tile_counters = nullptr,
+                        float* splitk_partials = nullptr) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -681,17 +699,14 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         per = (k_total + nsplit - 1) / nsplit;
         nsplit = (k_total + per - 1) / per;
     }
-    // Accuracy knob (opt-in, HOLO_CONV_MAX_CHAIN=<n>): the tensor core adds every K = 16 step into the fp32 TMEM
-    // accumulator with truncation, an error that grows linearly with the chain length.  Capping
-    // the (tap, slab) iterations per accumulator at n and summing the chains with fp32 atomics (round-to-nearest) --
-    // the split-K path above, forced -- shortens the chains at the price of the atomics, a memset and the epilogue
-    // statistics (the GroupNorm then runs its own statistics pass).
-    static const int max_chain = [] {
-        const char* e = getenv("HOLO_CONV_MAX_CHAIN");
-        return e ? atoi(e) : 0;
+    // With a workspace the last slice of a tile reads every slice's partial tile: keep that serial tail short
+    static const int splitk_max = [] {
+        const char* e = getenv("HOLO_SPLITK_MAX");
+        const int v = e ? atoi(e) : 24;
+        return v < 2 ? 2 : v;
     }();
-    if (max_chain > 0 && per > max_chain && out && !out_hi_bf16 && (out_pitch == Cout || out_is_zeroed)) {
-        per = max_chain;
+    if (nsplit > splitk_max && tile_counters && splitk_partials) {
+        per = (k_total + splitk_max - 1) / splitk_max;
         nsplit = (k_total + per - 1) / per;
     }
     CUtensorMap ah, al, bh, bl, a2h, a2l;
@@ -714,9 +729,14 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.tw = tw, P.th = th, P.td = td, P.stride = stride, P.iters_per_split = per;
     P.bias = bias, P.residual = residual, P.out = out;
     P.out_hi = (__nv_bfloat16*)out_hi_bf16, P.out_lo = (__nv_bfloat16*)out_lo_bf16;
-    P.tile_counters = tile_counters;
+    // split-K through the caller's workspace (deterministic, no zero-fill, statistics and operand pairs from the last
+    // slice) when it is given and large enough; otherwise fp32 atomics into a zeroed output
+    const long long ws_need = (long long)nsplit * tiles * (Cout / block_n) * BLOCK_M * block_n * (long long)sizeof(float);
+    const bool ws = nsplit > 1 && tile_counters && splitk_partials && ws_need <= holo_conv3d_tc_splitk_bytes();
+    P.tile_counters = ws ? tile_counters : nullptr;
+    P.partials = ws ? splitk_partials : nullptr;
     P.trace = g_conv_trace;
-    P.stats = ((nsplit == 1 || tile_counters) && out_pitch == Cout) ? stats : nullptr;
+    P.stats = ((nsplit == 1 || ws) && out_pitch == Cout) ? stats : nullptr;
     P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
     // chunked accumulation (see the MMA issuer): chains of ~HOLO_CONV_CHUNK (tap, slab) iterations, 0 = one chain per item
     // (default 9 = three chains for a 27-tap x 1-slab item), balanced so that no short tail chain is left: every chain
@@ -732,7 +752,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         P.chunk = 1 << 30;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (nsplit > 1 && !out_is_zeroed)
+    if (nsplit > 1 && !ws && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
     int rc;
     switch (block_n) {
@@ -752,7 +772,7 @@ int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int 
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, int operand_fmt,
-                              float acc_scale, int* tile_counters, void* stream) {
+                              float acc_scale, int* tile_counters, float* splitk_partials, void* stream) {
     const int taps = ksize * ksize * ksize;
     // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
     // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
@@ -767,7 +787,7 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
-                        stats_ch, operand_fmt, acc_scale, nullptr, nullptr, 0, tile_counters);
+                        stats_ch, operand_fmt, acc_scale, nullptr, nullptr, 0, tile_counters, splitk_partials);
 }
 
 extern "C" long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout) {
@@ -781,14 +801,15 @@ extern "C" long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout)
 extern "C" int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                                    int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo,
                                    const float* bias, const float* residual, int Cout, float* out, double* stats_ch,
-                                   int operand_fmt, float acc_scale, int* tile_counters, void* stream) {
+                                   int operand_fmt, float acc_scale, int* tile_counters, float* splitk_partials,
+                                   void* stream) {
     if (!skip_hi || !skip_lo || Cin_skip <= 0) {
         holo_set_error("holo_conv3d_tc_skip: the skip operand is missing");
         return HOLO_ERR_ARG;
     }
     return conv_tc_impl("holo_conv3d_tc_skip", x_hi, x_lo, Cin, Cin, D, H, W, 3, 1, w_hi, w_lo,
                         27LL * Cin + Cin_skip, bias, residual, Cout, Cout, out, nullptr, nullptr, stream, 0, stats_ch,
-                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip, tile_counters);
+                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip, tile_counters, splitk_partials);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,

@@ -262,11 +262,14 @@ class UNetExecutor:
         # n CTAs (auto: fill ~148 SMs, >= 2 key tiles per CTA) and merged by flash_combine_kernel: -0.23 ms per 64^3
         # step (profiles/r02a); "1" = one CTA per (query tile, head)
         self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "auto")
-        # HOLO_SPLITK_STATS=1: split-K convolutions produce the GroupNorm statistics themselves (the K slice that
-        # arrives last at a tile re-reads the atomically summed tile).  Measured on B200 (profiles/r02b): it removes 39
-        # gn_stats launches (0.59 -> 0.01 ms) but every slice then waits for its atomics to drain before it may count
-        # itself in (conv 6.20 -> 6.61 ms): a net LOSS of 0.13 ms per step, so it stays off
-        self.splitk_stats = os.environ.get("HOLO_SPLITK_STATS", "0") == "1"
+        # HOLO_SPLITK_WS=1 (deterministic mode): split-K convolutions (the coarse UNet levels) reduce through a scratch
+        # buffer -- every K slice parks its partial tile, the slice that arrives last at a tile sums them in slice order,
+        # writes the output once and produces the consumer GroupNorm's statistics: bit-reproducible results, no zero-fill,
+        # no fp32 atomics, no separate statistics passes (390 fewer launches per 10 steps).  Measured on B200
+        # (profiles/r02e): the last slice's serial reduction costs more than the atomics + 39 gn_stats launches it
+        # replaces (10.3 vs 9.72 ms per step), so the default stays fp32 atomics into a zeroed output
+        self.splitk_stats = os.environ.get("HOLO_SPLITK_WS", "0") == "1"
+        self._splitk_ws = None
         # One evaluation = ONE C-ABI call (holo_unet_fwd_cl, csrc/unet_exec.cu: the C++ twin of this executor, same
         # kernels in the same order; equal to 7e-7, the split-K atomics' order) instead of ~330 calls from the
         # interpreter: an eager step drops from 10.9 to 10.3 ms on B200 (profiles/r02c).  HOLO_UNET_NATIVE=0 walks the
@@ -403,7 +406,7 @@ class UNetExecutor:
         st = self._stats_slice(pc.cout) if want_stats else None
         cnt = self._counter_slice(out_dims, pc.cout) if st is not None else None
         rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
-                           stride, st, pc.w_scale, cnt)
+                           stride, st, pc.w_scale, cnt, self._splitk_ws if cnt is not None else None)
         if rc not in (0, 1):
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
@@ -488,7 +491,7 @@ class UNetExecutor:
         st = self._stats_slice(pf.cout)
         cnt = self._counter_slice(h.dims, pf.cout) if st is not None else None
         rc = ops.conv3d_tc_skip(y_hi, y_lo, pf.cin, raw[0], raw[1], pf.cin_skip, h.dims, pf.w_hi, pf.w_lo, pf.bias, None,
-                                pf.cout, out, st, pf.w_scale, cnt)
+                                pf.cout, out, st, pf.w_scale, cnt, self._splitk_ws if cnt is not None else None)
         if rc not in (0, 1):
             raise ops.HoloError("fused skip conv rejected a shape: " + ops.lib().cdll.holo_last_error().decode())
         self.tc_calls += 1
@@ -613,7 +616,7 @@ class UNetExecutor:
         """x_cl (V, Cin) channels-last fp32, t (1,) int64 on the device -> (V, Cout) channels-last."""
         p = self.p
         dev = x_cl.device
-        if self.native and self.attn_group is None and self.use_flash:
+        if self.native and ops.NativeUnet is not None and self.attn_group is None and self.use_flash:
             return self._native_forward_cl(x_cl, dims, t)
         if self._acc is None or self._acc.device != dev:
             self._acc = torch.zeros(2, 512, dtype=torch.float64, device=dev)
@@ -624,6 +627,8 @@ class UNetExecutor:
             self._arena = torch.zeros(1 << 18, dtype=torch.float64, device=dev)   # 2 MB: per-conv channel statistics
         self._arena.zero_()
         self._arena_off = 0
+        if self.splitk_stats and (self._splitk_ws is None or self._splitk_ws.device != dev):
+            self._splitk_ws = torch.empty(ops.splitk_ws_floats(), device=dev)
         mc = p.model_channels
         e0 = torch.empty(1, mc, device=dev)
         ops.timestep_embedding(t, mc, e0)
@@ -649,7 +654,7 @@ class UNetExecutor:
 
     def _native_forward_cl(self, x_cl, dims, t):
         key = (str(x_cl.device), tuple(dims), self._weights_signature(), self.pair_dtype, self.fuse_skip, self.attn_kv_split,
-               self.use_tc)
+               self.use_tc, self.splitk_stats)
         if self._native is None or self._native_key != key:
             p = self.p
             cfg = p.config
@@ -657,7 +662,8 @@ class UNetExecutor:
                 {k: v for k, v in p.state_dict().items()}, p.in_channels, p.model_channels, p.out_channels,
                 cfg["num_res_blocks"], cfg["channel_mult"], cfg["attention_resolutions"], p.num_heads, dims,
                 pair_f16=self.pair_dtype == torch.float16, fuse_skip=self.fuse_skip,
-                attn_kv_split=0 if self.attn_kv_split == "auto" else int(self.attn_kv_split), use_tensor_cores=self.use_tc)
+                attn_kv_split=0 if self.attn_kv_split == "auto" else int(self.attn_kv_split), use_tensor_cores=self.use_tc,
+                splitk_workspace=self.splitk_stats)
             self._native_key = key
         self.tc_calls += 1
         return self._native.forward_cl(x_cl, t)

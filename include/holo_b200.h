@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 118
+#define HOLO_B200_VERSION 119
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -176,18 +176,21 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
  * acc_scale multiplies the accumulators before bias and residual; pass 1 otherwise).  fp16 pairs bring the UNet's
  * distance to exact arithmetic from 7e-5 to 4e-6 -- fp32's own -- at the same MMA count.
  * out_hi/out_lo (optional): the result as an operand pair in the same format (the attention's q, k).
- * Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Small grids are split over K with fp32 atomics (summation order then varies run to run at the 1e-7 level).  Returns HOLO_ERR_UNSUPPORTED (-3) for
+ * Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Returns HOLO_ERR_UNSUPPORTED (-3) for
  * shapes it does not take.  stats_ch (optional, [Cout][2] doubles, pre-zeroed): per-channel (sum, sumsq) of the output
- * for the GroupNorm that consumes it, accumulated in the epilogue.  When the grid is split over K no slice sees the
- * summed tile: with tile_counters (optional, holo_conv3d_tc_tile_counters(...) zeroed ints) the slice that finishes a
- * tile last re-reads it and accumulates the statistics; without them the call returns 1 instead of 0 = done, but the
- * statistics were NOT produced.  Long K loops are accumulated in chains (HOLO_CONV_CHUNK iterations, default 9) that
+ * for the GroupNorm that consumes it, accumulated in the epilogue.  Small grids are split over K: with tile_counters
+ * (holo_conv3d_tc_tile_counters(...) ZEROED ints) and splitk_partials (holo_conv3d_tc_splitk_bytes() bytes of scratch)
+ * every K slice parks its partial tile in the scratch and the slice that finishes a tile last sums the slices in slice
+ * order -- a deterministic result, no zero-fill of `out`, statistics produced; without them the slices add into a zeroed
+ * `out` with fp32 atomics (summation order varies run to run at the 1e-7 level) and the call returns 1 instead of 0 =
+ * done, but the statistics were NOT produced.  Long K loops are accumulated in chains (HOLO_CONV_CHUNK iterations, default 9) that
  * the epilogue sums in registers: the tensor core truncates every add into the TMEM accumulator. */
 #define HOLO_FMT_F16 1
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
                    void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, int* tile_counters,
-                   void* stream);
+                   float* splitk_partials, void* stream);
+long long holo_conv3d_tc_splitk_bytes(void);
 /* Debug aid (library built with -DHOLO_CONV_TRACE, e.g. HOLO_NVCC_FLAGS=-DHOLO_CONV_TRACE python
  * holo_diffusion_b200/build.py; a no-op otherwise): CTA 0 of every following tcgen05 convolution launch writes 8 clock64 stamps (entry, set-up done, first
  * TMA issued, first operands landed, last MMA issued, first accumulator ready, first item written, exit) into the 8
@@ -205,7 +208,7 @@ long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout);
 int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                         int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo, const float* bias,
                         const float* residual, int Cout, float* out, double* stats_ch, int operand_fmt,
-                        float acc_scale, int* tile_counters, void* stream);
+                        float acc_scale, int* tile_counters, float* splitk_partials, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are 16-bit
  * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with
@@ -308,6 +311,8 @@ typedef struct holo_unet_config {
     int fuse_skip;                  /* 1 = ResBlock tails with a skip convolution as one launch (holo_conv3d_tc_skip) */
     int attn_kv_split;              /* 0 = auto (fill the SMs), n >= 1 = CTAs sharing the keys of one query tile */
     int use_tensor_cores;           /* 0 = exact-fp32 CUDA-core kernels everywhere */
+    int splitk_workspace;           /* 1 = split-K convolutions reduce deterministically through scratch (and produce the
+                                       GroupNorm statistics); 0 = fp32 atomics + separate statistics passes */
 } holo_unet_config;
 int holo_unet_create(const holo_unet_config* cfg, void** handle);
 int holo_unet_destroy(void* handle);

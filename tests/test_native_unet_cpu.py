@@ -22,7 +22,7 @@ def _create(c):
     _i = ctypes.c_int
     cm, ar = list(c["channel_mult"]), list(c["attention_resolutions"])
     cfg = ops.HoloUnetConfig(c["in_channels"], c["model_channels"], c["in_channels"], c["num_res_blocks"], len(cm), (_i * 8)(*cm),
-                             len(ar), (_i * 8)(*ar), 2, *c["dims"], 1, 1, 0, 1)
+                             len(ar), (_i * 8)(*ar), 2, *c["dims"], 1, 1, 0, 1, 1)
     h = ctypes.c_void_p()
     lib().call("holo_unet_create", ctypes.byref(cfg), ctypes.byref(h))
     return h, lib()

@@ -58,5 +58,7 @@ def test_query_sharded_attention_two_gpus():
     [p.join(60) for p in ps]
     for rank, d_single, err in res:
         print(f"rank {rank}: sharded vs un-sharded {d_single:.2e}, vs oracle {err:.2e}")
-        assert d_single < 2e-6, f"rank {rank}: sharded attention differs from the single-GPU result ({d_single})"
+        # the single-GPU attention shares the keys of a query tile between CTAs (split-KV, the default) and merges the
+        # partial softmaxes; the query-sharded one keeps one CTA per tile: same arithmetic, another rounding order
+        assert d_single < 2e-5, f"rank {rank}: sharded attention differs from the single-GPU result ({d_single})"
         assert err < 2e-5, (rank, err)

@@ -713,3 +713,43 @@ def test_attention_flash_chunked_o_accumulation():
     off, on = _attn_check(0, long_case)[long_case[0]], _attn_check(None, long_case)[long_case[0]]
     print(f"T = 32768: one chain {off:.2e}, chains of 64 tiles {on:.2e}")
     assert on < 3e-5 and on < off
+
+
+@pytest.mark.parametrize("Cin,Cout,dims", [(256, 256, (8, 8, 8)), (512, 512, (4, 4, 4)), (128, 128, (16, 16, 16)), (1024, 512, (4, 4, 4))])
+def test_conv_tc_splitk_workspace_is_deterministic(Cin, Cout, dims):
+    """Split-K through the scratch buffer (tile counters + parked partial tiles, summed in slice order by the last
+    slice): result vs fp64 F.conv3d, GroupNorm statistics of the summed output, rc = 0, and BIT-identical repeats
+    (the atomics path varies run to run)."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(41)
+    D, H, W = dims
+    V = D * H * W
+    x = torch.randn(1, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / math.sqrt(Cin * 27)
+    b = torch.randn(Cout, generator=g)
+    res = torch.randn(1, Cout, D, H, W, generator=g)
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=1) + res.double()
+    pdt = torch.float16
+    x_hi = torch.empty(V, Cin, device="cuda", dtype=pdt)
+    x_lo = torch.empty_like(x_hi)
+    ops.split_bf16(_cl(x), V, Cin, Cin, x_hi, x_lo)
+    wk = w.reshape(Cout, Cin, 27).permute(0, 2, 1).contiguous().cuda()
+    w_scale = 2.0 ** (9 - math.floor(math.log2(float(wk.abs().max()))))
+    w_hi = (wk * w_scale).to(pdt)
+    w_lo = (wk * w_scale - w_hi.float()).to(pdt)
+    ws = torch.empty(ops.splitk_ws_floats(), device="cuda")
+    outs = []
+    for rep in range(3):
+        out = torch.full((V, Cout), float("nan"), device="cuda")     # no zero-fill needed
+        st = torch.zeros(Cout, 2, dtype=torch.float64, device="cuda")
+        cnt = torch.zeros(ops.conv_tile_counters(dims, Cout), dtype=torch.int32, device="cuda")
+        rc = ops.conv3d_tc(x_hi, x_lo, Cin, dims, 3, w_hi, w_lo, b.cuda(), _cl(res), Cout, out, None, None, 1, st, w_scale, cnt, ws)
+        torch.cuda.synchronize()
+        assert rc == 0
+        outs.append(out)
+    err = rel_err(_from_cl(outs[0], Cout, dims), ref)
+    o = outs[0].double()
+    e_st = max(rel_err(st[:, 0], o.sum(0)), rel_err(st[:, 1], (o * o).sum(0)))
+    print(f"split-K workspace conv {Cin}->{Cout}@{dims}: rel err {err:.2e}, stats {e_st:.2e}")
+    assert err < 1e-5 and e_st < 1e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

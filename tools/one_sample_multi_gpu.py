@@ -37,6 +37,8 @@ def parse(argv=None):
     ap.add_argument("--fine", type=int, default=16)
     ap.add_argument("--attn-min-tokens", type=int, default=1 << 14)
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--profile-attention", action="store_true",
+                    help="CUDA-event time of every sharded attention block: fused kernel on this rank's queries, all-gather")
     return ap.parse_args(argv)
 
 
@@ -82,6 +84,29 @@ def run(a, rank, world, dev, unet_sd=None, mlp_sd=None, grid=None):
     cam = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, UP_AXIS, 3.2)[[3]].to(dev)
     preds = model(camera=cam, voxel_features=grid)   # warm-up: packs weights, NCCL channels
     torch.cuda.synchronize()
+    prof = []
+    if a.profile_attention and world > 1:
+        from holo_diffusion_b200 import ops
+        ex = model.net_3d._exec
+        orig_flash, orig_gather = ops.attention_flash, dist.all_gather_into_tensor
+
+        def flash(*args, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_flash(*args, **kw)
+            e.record()
+            prof.append(["attn", args[4], s, e])
+            return r
+
+        def gather(out, inp, group=None, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_gather(out, inp, group=group, **kw)
+            e.record()
+            prof.append(["gather", out.numel() * out.element_size(), s, e])
+            return r
+
+        ops.attention_flash, dist.all_gather_into_tensor = flash, gather
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -96,6 +121,21 @@ def run(a, rank, world, dev, unet_sd=None, mlp_sd=None, grid=None):
     rec = {"workload": f"cfg#5-style: one {a.resol}^3 x {a.channels}ch grid, UNet with attention at every level, "
                        f"{a.image}^2 view, {a.pts}+{a.fine} pts/ray", "n_gpus": world, "ms_per_view": float(ms),
            "steps": a.steps, "sharding": "attention queries + image rows, all-gather" if world > 1 else "none"}
+    if prof:
+        ops.attention_flash, dist.all_gather_into_tensor = orig_flash, orig_gather
+        n = max(1, a.steps)
+        att = [(T, s.elapsed_time(e)) for k, T, s, e in prof if k == "attn"]
+        gat = [(b, s.elapsed_time(e)) for k, b, s, e in prof if k == "gather"]
+        by_T = {}
+        for T, t in att:
+            d = by_T.setdefault(int(T), [0, 0.0])
+            d[0] += 1
+            d[1] += t
+        rec["rank0_attention_blocks"] = {str(T): {"launches_per_view": c // n, "ms_per_launch": t / c} for T, (c, t) in sorted(by_T.items())}
+        rec["rank0_attention_ms_per_view"] = sum(t for _, t in att) / n
+        rec["rank0_all_gather_ms_per_view"] = sum(t for _, t in gat) / n
+        rec["rank0_all_gather_bytes_per_view"] = sum(b for b, _ in gat) // n
+        rec["rank0_all_gather_calls_per_view"] = len(gat) // n
     return preds, model, cam, grid, rec
 
 
