@@ -191,8 +191,7 @@ struct TcParams {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     double* stats;  // optional per-output-channel (sum, sumsq) for the GroupNorm that consumes this tensor
-    int* tile_counters;  // split-K through the workspace: one zeroed int per (M tile, N block) -- the LAST K slice to
-    float* partials;     // finish a tile reduces the slices parked in `partials` ([slice][tile][128][BLOCK_N] floats)
+    float* partials;     // deterministic split-K: the K slices park their partial tiles here ([slice][tile][128][BLOCK_N])
     int k2_slabs;     // fused 1x1 "skip" operand: Cin2 / 64 extra K iterations after the taps x slabs main loop, reading
                       // the SECOND activation pair at the output voxel itself (no tap offset); 0 = none
     long long* trace; // debug (holo_debug_conv_trace): CTA 0 stamps clock64 at [0] entry, [1] set-up done, [2] first TMA
@@ -372,8 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const bool row_ok = r < rows;
         const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
         const bool ws = split && P.partials != nullptr;   // deterministic split-K through a workspace (see below)
-        const bool do_stats = P.stats != nullptr && (!split || ws);
-        int* s_last = reinterpret_cast<int*>(s_stat + 2 * BLOCK_N);   // "this CTA completed the tile" broadcast
+        const bool do_stats = P.stats != nullptr && !split;
         int stat_n0 = -1;
         auto flush_stats = [&]() {   // all 128 epilogue threads: smem partials -> global fp64, then clear
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -504,9 +502,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             } else {
                 // DETERMINISTIC SPLIT-K: every K slice parks its raw partial tile in the workspace ([slice][tile][128][N],
-                // plain stores); the slice that arrives LAST at the tile's counter sums the slices in slice order (the
-                // result does not depend on who arrives last), applies scale / bias / residual, writes the output once
-                // (no zero-fill, no atomics) and accumulates the GroupNorm statistics of the finished tile.
+                // plain stores: no zero-fill, no atomics); splitk_reduce_kernel then sums the slices in slice order, applies
+                // scale / bias / residual, writes the output once and accumulates the GroupNorm statistics.
                 const int mt = item % P.m_tiles, nb = (item / P.m_tiles) % P.n_blocks;
                 const size_t tile_floats = (size_t)BLOCK_M * BLOCK_N;
                 const size_t tile_id = (size_t)mt * P.n_blocks + nb;
@@ -515,33 +512,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int c4 = 0; c4 < BLOCK_N / 4; ++c4)
                     __stcg(reinterpret_cast<float4*>(mine) + c4,
                            make_float4(accv[c4 * 4], accv[c4 * 4 + 1], accv[c4 * 4 + 2], accv[c4 * 4 + 3]));
-                __threadfence();                                   // this thread's partial before the count
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) *s_last = atomicAdd(&P.tile_counters[tile_id], 1) == P.nsplit - 1;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (*s_last) {
-                    __threadfence();
-                    const float* base = P.partials + tile_id * tile_floats + (size_t)r * BLOCK_N;
-                    const size_t slice_stride = (size_t)P.m_tiles * P.n_blocks * tile_floats;
-#pragma unroll
-                    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                        float vals[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) vals[j] = 0.f;
-                        for (int zz = 0; zz < P.nsplit; ++zz) {
-                            const float4* pp = reinterpret_cast<const float4*>(base + (size_t)zz * slice_stride + c0);
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 t = __ldcg(pp + j4);
-                                vals[j4 * 4] += t.x, vals[j4 * 4 + 1] += t.y, vals[j4 * 4 + 2] += t.z, vals[j4 * 4 + 3] += t.w;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) vals[j] *= P.acc_scale;
-                        emit(vals, c0, true, false);
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // s_last is rewritten by the next item
             }
             if (tr && et == 0 && item == (int)blockIdx.x) P.trace[6] = clock64();
         }
@@ -552,6 +522,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * C::TMEM_COLS));
+    }
+}
+
+// Second half of the deterministic split-K: out[v][n] = acc_scale * sum_z partial[z][tile(v, n)][row(v)][n % BLOCK_N] + bias
+// + residual, in slice order; per-channel (sum, sumsq) of the result for the consumer GroupNorm.  Thread = one voxel row of
+// a tile x 4 channels; a warp covers 32 rows of the same 4 channels, so the statistics reduce with shuffles.
+struct ReduceParams {
+    const float* partials;
+    int nsplit, m_tiles, n_blocks, block_n;
+    int D, H, W, tw, th, td, rows, Cout;
+    long long out_pitch;
+    float acc_scale;
+    const float* bias;
+    const float* residual;
+    float* out;
+    double* stats;
+};
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceParams P) {
+    const int lane = threadIdx.x & 31;
+    const int c4_per_tile = P.block_n / 4;
+    const long long row_groups = (long long)P.m_tiles * P.n_blocks * c4_per_tile * (BLOCK_M / 32);   // warps of work
+    const size_t tile_floats = (size_t)BLOCK_M * P.block_n;
+    const size_t slice_stride = (size_t)P.m_tiles * P.n_blocks * tile_floats;
+    const int tiles_w = P.W / P.tw, tiles_h = P.H / P.th;
+    for (long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32; wg < row_groups;
+         wg += ((long long)gridDim.x * blockDim.x) / 32) {
+        const int c4 = (int)(wg % c4_per_tile);
+        const int rq = (int)((wg / c4_per_tile) % (BLOCK_M / 32));
+        const long long tile_id = wg / ((long long)c4_per_tile * (BLOCK_M / 32));
+        const int nb = (int)(tile_id % P.n_blocks), mt = (int)(tile_id / P.n_blocks);
+        const int r = rq * 32 + lane;
+        const bool row_ok = r < P.rows;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) {
+            const float* base = P.partials + (size_t)tile_id * tile_floats + (size_t)r * P.block_n + c4 * 4;
+            for (int z = 0; z < P.nsplit; ++z) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(base + (size_t)z * slice_stride));
+                acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+            }
+            const int n = nb * P.block_n + c4 * 4;
+            acc.x *= P.acc_scale, acc.y *= P.acc_scale, acc.z *= P.acc_scale, acc.w *= P.acc_scale;
+            if (P.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+                acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+            }
+            const int w0 = (mt % tiles_w) * P.tw, h0 = ((mt / tiles_w) % tiles_h) * P.th, d0 = (mt / (tiles_w * tiles_h)) * P.td;
+            const int w = w0 + (r % P.tw), h = h0 + ((r / P.tw) % P.th), d = d0 + r / (P.tw * P.th);
+            const size_t v = ((size_t)d * P.H + h) * P.W + w;
+            if (P.residual) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n));
+                acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+            }
+            *reinterpret_cast<float4*>(P.out + v * P.out_pitch + n) = acc;
+        }
+        if (P.stats) {   // uniform per warp
+            float sv[4] = {acc.x, acc.y, acc.z, acc.w};
+            const int n = nb * P.block_n + c4 * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float s1 = warp_sum(row_ok ? sv[k] : 0.f), s2 = warp_sum(row_ok ? sv[k] * sv[k] : 0.f);
+                if (lane == 0) {
+                    atomicAdd(&P.stats[(size_t)(n + k) * 2], (double)s1);
+                    atomicAdd(&P.stats[(size_t)(n + k) * 2 + 1], (double)s2);
+                }
+            }
+        }
     }
 }
 
@@ -647,8 +683,7 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
                         double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f, const void* x2_hi = nullptr,
-                        const void* x2_lo = nullptr, int Cin2 = 0, int* tile_counters = nullptr,
-                        float* splitk_partials = nullptr) {
+                        const void* x2_lo = nullptr, int Cin2 = 0, float* splitk_partials = nullptr) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -699,13 +734,14 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         per = (k_total + nsplit - 1) / nsplit;
         nsplit = (k_total + per - 1) / per;
     }
-    // With a workspace the last slice of a tile reads every slice's partial tile: keep that serial tail short
+    // Upper bound on the slices of the workspace path (HOLO_SPLITK_MAX; the reduce launch reads every slice once: 24 vs 40
+    // slices measured 9.31 vs 9.27 ms per step, profiles/r02g)
     static const int splitk_max = [] {
         const char* e = getenv("HOLO_SPLITK_MAX");
-        const int v = e ? atoi(e) : 24;
+        const int v = e ? atoi(e) : 64;
         return v < 2 ? 2 : v;
     }();
-    if (nsplit > splitk_max && tile_counters && splitk_partials) {
+    if (nsplit > splitk_max && splitk_partials) {
         per = (k_total + splitk_max - 1) / splitk_max;
         nsplit = (k_total + per - 1) / per;
     }
@@ -732,11 +768,10 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     // split-K through the caller's workspace (deterministic, no zero-fill, statistics and operand pairs from the last
     // slice) when it is given and large enough; otherwise fp32 atomics into a zeroed output
     const long long ws_need = (long long)nsplit * tiles * (Cout / block_n) * BLOCK_M * block_n * (long long)sizeof(float);
-    const bool ws = nsplit > 1 && tile_counters && splitk_partials && ws_need <= holo_conv3d_tc_splitk_bytes();
-    P.tile_counters = ws ? tile_counters : nullptr;
+    const bool ws = nsplit > 1 && splitk_partials && ws_need <= holo_conv3d_tc_splitk_bytes() && out && !out_hi_bf16;
     P.partials = ws ? splitk_partials : nullptr;
     P.trace = g_conv_trace;
-    P.stats = ((nsplit == 1 || ws) && out_pitch == Cout) ? stats : nullptr;
+    P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
     P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
     // chunked accumulation (see the MMA issuer): chains of ~HOLO_CONV_CHUNK (tap, slab) iterations, 0 = one chain per item
     // (default 9 = three chains for a 27-tap x 1-slab item), balanced so that no short tail chain is left: every chain
@@ -761,6 +796,19 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
         case 32: rc = launch<32>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
         default: rc = launch<16>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
     }
+    if (rc == HOLO_OK && ws) {
+        ReduceParams R;
+        R.partials = splitk_partials, R.nsplit = nsplit, R.m_tiles = tiles, R.n_blocks = Cout / block_n, R.block_n = block_n;
+        R.D = D, R.H = H, R.W = W, R.tw = tw, R.th = th, R.td = td, R.rows = tw * th * td, R.Cout = Cout;
+        R.out_pitch = out_pitch, R.acc_scale = acc_scale, R.bias = bias, R.residual = residual, R.out = out;
+        R.stats = out_pitch == Cout ? stats : nullptr;
+        const long long warps = (long long)tiles * (Cout / block_n) * (block_n / 4) * (BLOCK_M / 32);
+        long long blocks = (warps + 7) / 8;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(R);
+        HOLO_CHECK_LAUNCH(who);
+        return (stats && !R.stats) ? 1 : HOLO_OK;
+    }
     if (rc == HOLO_OK && stats && !P.stats) return 1;  // done, but the statistics were not produced (split-K / pitch)
     return rc;
 }
@@ -772,7 +820,7 @@ int holo_conv3d_tc_halo(const void* x_hi, const void* x_lo, int Cin, int D, int 
 extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                               const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout,
                               float* out, void* out_hi_bf16, void* out_lo_bf16, double* stats_ch, int operand_fmt,
-                              float acc_scale, int* tile_counters, float* splitk_partials, void* stream) {
+                              float acc_scale, float* splitk_partials, void* stream) {
     const int taps = ksize * ksize * ksize;
     // Optional (HOLO_CONV_HALO=1): halo-resident activation tile (conv_tc_halo.cu), 3x less L2->SMEM traffic.
     // Measured on B200 it ties the tap-reload kernel before and loses to it after that kernel became persistent
@@ -787,12 +835,10 @@ extern "C" int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D
     }
     return conv_tc_impl("holo_conv3d_tc", x_hi, x_lo, Cin, Cin, D, H, W, ksize, stride, w_hi, w_lo,
                         (long long)taps * Cin, bias, residual, Cout, Cout, out, out_hi_bf16, out_lo_bf16, stream, 0,
-                        stats_ch, operand_fmt, acc_scale, nullptr, nullptr, 0, tile_counters, splitk_partials);
+                        stats_ch, operand_fmt, acc_scale, nullptr, nullptr, 0, splitk_partials);
 }
 
-extern "C" long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout) {
-    return (long long)((D + 3) / 4) * ((H + 3) / 4) * ((W + 3) / 4) * ((Cout + 15) / 16);
-}
+
 
 // ResBlock tail in one launch: out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual): the 1x1 skip connection
 // (unet.py:222,255) rides the same TMEM accumulator as Cin_skip / 64 extra K iterations, so its fp32 result is never
@@ -801,15 +847,14 @@ extern "C" long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout)
 extern "C" int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                                    int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo,
                                    const float* bias, const float* residual, int Cout, float* out, double* stats_ch,
-                                   int operand_fmt, float acc_scale, int* tile_counters, float* splitk_partials,
-                                   void* stream) {
+                                   int operand_fmt, float acc_scale, float* splitk_partials, void* stream) {
     if (!skip_hi || !skip_lo || Cin_skip <= 0) {
         holo_set_error("holo_conv3d_tc_skip: the skip operand is missing");
         return HOLO_ERR_ARG;
     }
     return conv_tc_impl("holo_conv3d_tc_skip", x_hi, x_lo, Cin, Cin, D, H, W, 3, 1, w_hi, w_lo,
                         27LL * Cin + Cin_skip, bias, residual, Cout, Cout, out, nullptr, nullptr, stream, 0, stats_ch,
-                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip, tile_counters, splitk_partials);
+                        operand_fmt, acc_scale, skip_hi, skip_lo, Cin_skip, splitk_partials);
 }
 
 // Plain GEMM on the same kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] * b[n][k]  (both K-major,

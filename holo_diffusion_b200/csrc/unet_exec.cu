@@ -375,16 +375,6 @@ struct Exec {
         arena_off += n;
         return s;
     }
-    // zeroed per-tile arrival counters of one (possibly split-K) convolution: an int32 view of the statistics arena
-    int* counter_slice(const Dims& out, int cout) {
-        const size_t n = (size_t)holo_conv3d_tc_tile_counters(out.d, out.h, out.w, cout);
-        const size_t n8 = (n + 1) / 2;
-        if (arena_off + n8 > arena_n) return nullptr;
-        int* c = reinterpret_cast<int*>(arena64 + arena_off);
-        arena_off += n8;
-        return c;
-    }
-    bool splitk_ws_on() const { return u.cfg.splitk_workspace != 0; }
     bool tc_ok(const Conv& c, const Dims& out) const { return c.cout_p % 16 == 0 && c.cout_p <= 4096 && tile_ok(out); }
 
     // ---- GroupNorm (+FiLM) (+SiLU) of a one- or two-source activation -> fp32 y or the operand pair (+ raw pair)
@@ -417,12 +407,11 @@ struct Exec {
         r.x1 = alloc<float>((size_t)Vo * c.cout_p);
         if (o_hi) *o_hi = alloc<uint16_t>((size_t)Vo * c.cout_p), *o_lo = alloc<uint16_t>((size_t)Vo * c.cout_p);
         double* sts = want_stats ? stats_slice(c.cout_p) : nullptr;
-        int* cnt = (sts && splitk_ws_on()) ? counter_slice(r.dims, c.cout_p) : nullptr;
         int ret = 1;
         if (!dry) {
             ret = holo_conv3d_tc(hi, lo, c.cin_pad, in.d, in.h, in.w, k, stride, pk(c.off_hi), pk(c.off_lo),
                                  (const float*)pk(c.off_bias), residual, c.cout_p, r.x1, o_hi ? *o_hi : nullptr,
-                                 o_lo ? *o_lo : nullptr, sts, fmt, 1.0f / c.scale, cnt, cnt ? splitk_ws : nullptr, st);
+                                 o_lo ? *o_lo : nullptr, sts, fmt, 1.0f / c.scale, splitk_ws, st);
             check(ret);
         }
         r.st1 = (ret == 0) ? sts : nullptr;
@@ -515,12 +504,11 @@ struct Exec {
                 r.dims = h.dims, r.c1 = b.cout;
                 r.x1 = alloc<float>((size_t)V * b.cout);
                 double* sts = stats_slice(b.cout);
-                int* cnt = (sts && splitk_ws_on()) ? counter_slice(h.dims, b.cout) : nullptr;
                 int ret = 1;
                 if (!dry) {
                     ret = holo_conv3d_tc_skip(y_hi, y_lo, b.c2.cin, raw_hi, raw_lo, b.skip.cin, h.dims.d, h.dims.h, h.dims.w,
                                               pk(b.f_hi), pk(b.f_lo), (const float*)pk(b.f_bias), nullptr, b.cout, r.x1, sts, fmt,
-                                              1.0f / b.f_scale, cnt, cnt ? splitk_ws : nullptr, st);
+                                              1.0f / b.f_scale, splitk_ws, st);
                     check(ret);
                 }
                 r.st1 = ret == 0 ? sts : nullptr;

@@ -304,19 +304,18 @@ FMT_F16 = 1   # include/holo_b200.h HOLO_FMT_F16
 
 
 def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None,
-              stride: int = 1, stats=None, w_scale: float = 1.0, counters=None, splitk_ws=None) -> int:
+              stride: int = 1, stats=None, w_scale: float = 1.0, splitk_ws=None) -> int:
     """dims = INPUT volume.  Returns the library status (0 ok, 1 ok but `stats` not produced, -3 unsupported shape);
     other errors raise.  stats: optional zeroed fp64 (Cout, 2) tensor receiving per-channel (sum, sumsq) of the output.
-    counters + splitk_ws: zeroed int32 tensor (conv_tile_counters(...) ints) and fp32 scratch (splitk_ws_floats()): split-K
-    launches then reduce deterministically through the scratch and produce `stats` too.
+    splitk_ws: fp32 scratch of splitk_ws_floats() elements: split-K launches then reduce deterministically through it (a
+    second launch) and produce `stats` too.
     The operand format follows the dtype of the four halves (all bf16 or all fp16); the weight pair holds
     w_scale * w (a power of two; the kernel multiplies the accumulators by 1 / w_scale)."""
     fmt = FMT_F16 * _pair_f16(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo)
     rc = lib().try_call("holo_conv3d_tc", _ptr16(x_hi), _ptr16(x_lo), Cin, dims[0],
                         dims[1], dims[2], ksize, stride, _ptr16(w_hi), _ptr16(w_lo), _ptr(bias),
                         _ptr(residual), Cout, _ptr(out), _ptr16(out_hi), _ptr16(out_lo),
-                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(counters, torch.int32), _ptr(splitk_ws),
-                        _stream())
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(splitk_ws), _stream())
     if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc
@@ -326,19 +325,14 @@ def splitk_ws_floats() -> int:
     return int(lib().cdll.holo_conv3d_tc_splitk_bytes()) // 4
 
 
-def conv_tile_counters(out_dims, Cout) -> int:
-    return int(lib().cdll.holo_conv3d_tc_tile_counters(out_dims[0], out_dims[1], out_dims[2], Cout))
-
-
 def conv3d_tc_skip(x_hi, x_lo, Cin, skip_hi, skip_lo, Cin_skip, dims, w_hi, w_lo, bias, residual, Cout, out, stats=None,
-                   w_scale: float = 1.0, counters=None, splitk_ws=None) -> int:
+                   w_scale: float = 1.0, splitk_ws=None) -> int:
     """out = conv3^3(x) + conv1^1(skip) + bias (+ residual) in one launch (holo_conv3d_tc_skip); w = [Cout][27 Cin +
     Cin_skip] pairs.  Status as conv3d_tc."""
     fmt = FMT_F16 * _pair_f16(x_hi, x_lo, skip_hi, skip_lo, w_hi, w_lo)
     rc = lib().try_call("holo_conv3d_tc_skip", _ptr16(x_hi), _ptr16(x_lo), Cin, _ptr16(skip_hi), _ptr16(skip_lo), Cin_skip,
                         dims[0], dims[1], dims[2], _ptr16(w_hi), _ptr16(w_lo), _ptr(bias), _ptr(residual), Cout, _ptr(out),
-                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(counters, torch.int32), _ptr(splitk_ws),
-                        _stream())
+                        _ptr(stats, torch.float64), fmt, 1.0 / float(w_scale), _ptr(splitk_ws), _stream())
     if rc not in (0, 1, -3):
         raise HoloError(f"holo_conv3d_tc_skip failed ({rc}): {lib().cdll.holo_last_error().decode()}")
     return rc

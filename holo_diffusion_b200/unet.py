@@ -262,13 +262,12 @@ class UNetExecutor:
         # n CTAs (auto: fill ~148 SMs, >= 2 key tiles per CTA) and merged by flash_combine_kernel: -0.23 ms per 64^3
         # step (profiles/r02a); "1" = one CTA per (query tile, head)
         self.attn_kv_split = os.environ.get("HOLO_ATTN_KV_SPLIT", "auto")
-        # HOLO_SPLITK_WS=1 (deterministic mode): split-K convolutions (the coarse UNet levels) reduce through a scratch
-        # buffer -- every K slice parks its partial tile, the slice that arrives last at a tile sums them in slice order,
-        # writes the output once and produces the consumer GroupNorm's statistics: bit-reproducible results, no zero-fill,
-        # no fp32 atomics, no separate statistics passes (390 fewer launches per 10 steps).  Measured on B200
-        # (profiles/r02e): the last slice's serial reduction costs more than the atomics + 39 gn_stats launches it
-        # replaces (10.3 vs 9.72 ms per step), so the default stays fp32 atomics into a zeroed output
-        self.splitk_stats = os.environ.get("HOLO_SPLITK_WS", "0") == "1"
+        # Deterministic split-K (default): the K slices of a small-grid convolution park their partial tiles in a scratch
+        # buffer and a reduce launch sums them in slice order, applies scale / bias / residual, writes the output once and
+        # produces the consumer GroupNorm's statistics -- bit-reproducible results, no zero-fill, no fp32 atomics, no
+        # separate statistics passes: 9.50 -> 9.27-9.31 ms per step on B200 (profiles/r02g; an in-kernel "last slice
+        # reduces" variant was slower than the atomics, profiles/r02e).  HOLO_SPLITK_WS=0: atomics + gn_stats launches
+        self.splitk_stats = os.environ.get("HOLO_SPLITK_WS", "1") == "1"
         self._splitk_ws = None
         # One evaluation = ONE C-ABI call (holo_unet_fwd_cl, csrc/unet_exec.cu: the C++ twin of this executor, same
         # kernels in the same order; equal to 7e-7, the split-K atomics' order) instead of ~330 calls from the
@@ -335,18 +334,6 @@ class UNetExecutor:
         self._arena_off += n
         return st
 
-    def _counter_slice(self, out_dims, cout: int):
-        """Zeroed per-tile arrival counters (int32 view of the same arena) for a convolution that may split K: the last
-        K slice of a tile then produces the GroupNorm statistics of the summed output (no separate statistics pass)."""
-        if not self.splitk_stats:
-            return None
-        n = ops.conv_tile_counters(out_dims, cout)
-        n8 = (n + 1) // 2   # fp64 slots
-        if self._arena_off + n8 > self._arena.numel():
-            return None
-        c = self._arena[self._arena_off:self._arena_off + n8].view(torch.int32)
-        self._arena_off += n8
-        return c
 
     # -- primitive ops -------------------------------------------------------------------------------------
     def _tc_ok(self, pc: _PackedConv, out_dims) -> bool:
@@ -404,9 +391,8 @@ class UNetExecutor:
             o_hi = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
             o_lo = torch.empty(Vo, pc.cout, device=dev, dtype=self.pair_dtype)
         st = self._stats_slice(pc.cout) if want_stats else None
-        cnt = self._counter_slice(out_dims, pc.cout) if st is not None else None
         rc = ops.conv3d_tc(hi, lo, pc.cin_pad, in_dims, k, pc.w_hi, pc.w_lo, pc.bias, residual, pc.cout, out, o_hi, o_lo,
-                           stride, st, pc.w_scale, cnt, self._splitk_ws if cnt is not None else None)
+                           stride, st, pc.w_scale, self._splitk_ws if self.splitk_stats else None)
         if rc not in (0, 1):
             raise ops.HoloError("tensor-core conv rejected a shape that _tc_ok accepted: "
                                 + ops.lib().cdll.holo_last_error().decode())
@@ -489,9 +475,8 @@ class UNetExecutor:
         Vo = h.V
         out = torch.empty(Vo, pf.cout, device=y_hi.device)
         st = self._stats_slice(pf.cout)
-        cnt = self._counter_slice(h.dims, pf.cout) if st is not None else None
         rc = ops.conv3d_tc_skip(y_hi, y_lo, pf.cin, raw[0], raw[1], pf.cin_skip, h.dims, pf.w_hi, pf.w_lo, pf.bias, None,
-                                pf.cout, out, st, pf.w_scale, cnt, self._splitk_ws if cnt is not None else None)
+                                pf.cout, out, st, pf.w_scale, self._splitk_ws if self.splitk_stats else None)
         if rc not in (0, 1):
             raise ops.HoloError("fused skip conv rejected a shape: " + ops.lib().cdll.holo_last_error().decode())
         self.tc_calls += 1

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 119
+#define HOLO_B200_VERSION 120
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -178,17 +178,16 @@ int holo_conv3d_simt(const float* x1, int C1, const float* x2, int C2, int Din, 
  * out_hi/out_lo (optional): the result as an operand pair in the same format (the attention's q, k).
  * Cin % 64 == 0, Cout % 16 == 0, output dims multiples of (4,4,4).  Returns HOLO_ERR_UNSUPPORTED (-3) for
  * shapes it does not take.  stats_ch (optional, [Cout][2] doubles, pre-zeroed): per-channel (sum, sumsq) of the output
- * for the GroupNorm that consumes it, accumulated in the epilogue.  Small grids are split over K: with tile_counters
- * (holo_conv3d_tc_tile_counters(...) ZEROED ints) and splitk_partials (holo_conv3d_tc_splitk_bytes() bytes of scratch)
- * every K slice parks its partial tile in the scratch and the slice that finishes a tile last sums the slices in slice
- * order -- a deterministic result, no zero-fill of `out`, statistics produced; without them the slices add into a zeroed
- * `out` with fp32 atomics (summation order varies run to run at the 1e-7 level) and the call returns 1 instead of 0 =
- * done, but the statistics were NOT produced.  Long K loops are accumulated in chains (HOLO_CONV_CHUNK iterations, default 9) that
+ * for the GroupNorm that consumes it, accumulated in the epilogue.  Small grids are split over K: with splitk_partials
+ * (holo_conv3d_tc_splitk_bytes() bytes of scratch) every K slice parks its partial tile there and a second launch sums
+ * the slices in slice order, applies scale / bias / residual and writes `out` once -- a deterministic result, no
+ * zero-fill, statistics produced; without it the slices add into a zeroed `out` with fp32 atomics (summation order varies
+ * run to run at the 1e-7 level) and the call returns 1 instead of 0 = done, but the statistics were NOT produced.  Long K loops are accumulated in chains (HOLO_CONV_CHUNK iterations, default 9) that
  * the epilogue sums in registers: the tensor core truncates every add into the TMEM accumulator. */
 #define HOLO_FMT_F16 1
 int holo_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, int D, int H, int W, int ksize, int stride,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int Cout, float* out,
-                   void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale, int* tile_counters,
+                   void* out_hi, void* out_lo, double* stats_ch, int operand_fmt, float acc_scale,
                    float* splitk_partials, void* stream);
 long long holo_conv3d_tc_splitk_bytes(void);
 /* Debug aid (library built with -DHOLO_CONV_TRACE, e.g. HOLO_NVCC_FLAGS=-DHOLO_CONV_TRACE python
@@ -196,8 +195,6 @@ long long holo_conv3d_tc_splitk_bytes(void);
  * TMA issued, first operands landed, last MMA issued, first accumulator ready, first item written, exit) into the 8
  * int64 at dev_buf8; NULL switches it off. */
 int holo_debug_conv_trace(void* dev_buf8);
-/* Number of ints tile_counters must hold for an OUTPUT volume (D, H, W) with Cout channels (an upper bound). */
-long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout);
 
 /* ResBlock tail in ONE launch (ResBlock._forward, unet.py:254-256, with a 1x1 skip_connection :222):
  *   out = conv3^3(x) + conv1^1(skip_x) + bias (+ residual)
@@ -208,7 +205,7 @@ long long holo_conv3d_tc_tile_counters(int D, int H, int W, int Cout);
 int holo_conv3d_tc_skip(const void* x_hi, const void* x_lo, int Cin, const void* skip_hi, const void* skip_lo,
                         int Cin_skip, int D, int H, int W, const void* w_hi, const void* w_lo, const float* bias,
                         const float* residual, int Cout, float* out, double* stats_ch, int operand_fmt,
-                        float acc_scale, int* tile_counters, float* splitk_partials, void* stream);
+                        float acc_scale, float* splitk_partials, void* stream);
 
 /* Plain GEMM on the tcgen05 kernel: out[m][n] = bias[n] + residual[m][n] + sum_k a[m][k] b[n][k]; a, b are 16-bit
  * hi/lo pairs (operand_fmt as for holo_conv3d_tc; out_hi/out_lo are written in the same format), K-major with

@@ -99,7 +99,7 @@ def split_bf16(x, V, C, Cpad, hi, lo, ups_dims=None, x2=None, C2=0):
 
 
 def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, out, out_hi=None, out_lo=None, stride=1,
-              stats=None, w_scale=1.0, counters=None, splitk_ws=None):
+              stats=None, w_scale=1.0, splitk_ws=None):
     x = _cl_to_ncdhw(x_hi + x_lo, Cin, dims)
     w = ((w_hi + w_lo) / w_scale).reshape(Cout, ksize, ksize, ksize, Cin).permute(0, 4, 1, 2, 3)
     y = _ncdhw_to_cl(F.conv3d(x, w, bias, stride=stride, padding=ksize // 2))
@@ -118,7 +118,7 @@ def conv3d_tc(x_hi, x_lo, Cin, dims, ksize, w_hi, w_lo, bias, residual, Cout, ou
 
 
 def conv3d_tc_skip(x_hi, x_lo, Cin, skip_hi, skip_lo, Cin_skip, dims, w_hi, w_lo, bias, residual, Cout, out, stats=None,
-                   w_scale=1.0, counters=None, splitk_ws=None):
+                   w_scale=1.0, splitk_ws=None):
     w = (w_hi + w_lo) / w_scale                               # [Cout][27 Cin + Cin_skip]
     w3 = w[:, : 27 * Cin].reshape(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)
     w1 = w[:, 27 * Cin:].reshape(Cout, Cin_skip, 1, 1, 1)
