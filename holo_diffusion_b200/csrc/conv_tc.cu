@@ -557,7 +557,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceParams P) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row_ok) {
             const float* base = P.partials + (size_t)tile_id * tile_floats + (size_t)r * P.block_n + c4 * 4;
-            for (int z = 0; z < P.nsplit; ++z) {
+            // 8 slices in flight per thread (the loads are independent, the adds keep the slice order)
+            int z = 0;
+            for (; z + 8 <= P.nsplit; z += 8) {
+                float4 t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t[k] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(z + k) * slice_stride));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc.x += t[k].x, acc.y += t[k].y, acc.z += t[k].z, acc.w += t[k].w;
+            }
+            for (; z < P.nsplit; ++z) {
                 const float4 t = __ldcg(reinterpret_cast<const float4*>(base + (size_t)z * slice_stride));
                 acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
             }

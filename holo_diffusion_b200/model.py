@@ -6,7 +6,8 @@ render_image_width/height, raysampler/renderer argument groups), ``sample_random
 (image_rgb=None, voxel_features given, evaluation_mode=EVALUATION):
     asserts on the grid range :381 -> ``voxel_features = tanh(net_3d(voxel_features, t=0))`` :420-428 ->
     bind ``voxel_grid_features`` :431-438 -> ray sampler :442-448 -> ``_render`` :451-457 -> preds :469-523.
-The view-pooling encoder, the training branch and the losses are out of this round's scope and raise.
+The view-pooling encoder and the training branch (losses; it needs the UNet kernels' backward) are not built and raise;
+the renderer is differentiable on its own (autograd.py).
 Parameter names follow the reference so that checkpoints load: ``net_3d._net.*``,
 ``_implicit_functions.{i}._fn.render_mlp.*``.
 """

@@ -313,7 +313,8 @@ class UNetExecutor:
 
     def _film(self):
         blocks = self._res_blocks()
-        ver = tuple((b.emb_layers[1].weight._version, b.emb_layers[1].weight.data_ptr()) for b in blocks)
+        ver = tuple((b.emb_layers[1].weight._version, b.emb_layers[1].weight.data_ptr(), b.emb_layers[1].bias._version,
+                     b.emb_layers[1].bias.data_ptr()) for b in blocks)
         if ver != self._film_version:
             self._film_version = ver
             self._film_w = torch.cat([b.emb_layers[1].weight.detach() for b in blocks], 0).float().contiguous()
@@ -525,7 +526,7 @@ class UNetExecutor:
                 ws = ops.attention_flash_workspace(T, heads, chp, splits, dev) if splits > 1 else None
                 rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, a_hi, a_lo, scale,
                                          kv_splits=splits, workspace=ws)
-                assert rc == 0
+                self._check(rc, "holo_attention_flash")
             else:
                 a_hi, a_lo = self._attn_sharded(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, scale, world, rank)
             self.tc_calls += 1
@@ -541,18 +542,24 @@ class UNetExecutor:
         for h in range(heads):
             base = h * 3 * ch
             rc = ops.gemm_tc(q_hi, q_lo, base, 3 * C, T, ch, q_hi, q_lo, base + ch, 3 * C, T, None, None, T, S)
-            assert rc == 0
+            self._check(rc, "holo_gemm_tc (Q K^T)")
             ps = ops.softmax_split(S, T, T, 1.0 / math.sqrt(ch), P_hi, P_lo)   # (q s)(k s) = s^2 q k, s = ch^-1/4
             ops.transpose_split(qkv.x1, base + 2 * ch, 3 * C, T, ch, vt_hi, vt_lo)
             rc = ops.gemm_tc(P_hi, P_lo, 0, T, T, T, vt_hi, vt_lo, 0, T, ch, None, None, C, a, h * ch, out_is_zeroed=True,
                              acc_scale=1.0 / ps)
-            assert rc == 0
+            self._check(rc, "holo_gemm_tc (P V)")
             self.tc_calls += 2
         a_hi = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
         a_lo = torch.empty(T, C, device=dev, dtype=self.pair_dtype)
         ops.split_bf16(a, T, C, C, a_hi, a_lo)
         out = self._conv_tc(pcp, a_hi, a_lo, gdims, residual=act.x1)
         return _Act(out.x1, C, act.dims, st1=out.st1)
+
+    @staticmethod
+    def _check(rc: int, what: str):
+        """A kernel that answers "unsupported shape" after the dispatch chose it is a bug, not a fallback case."""
+        if rc != 0:
+            raise ops.HoloError(f"{what} failed ({rc}): {ops.lib().cdll.holo_last_error().decode()}")
 
     def _attn_world(self, T: int) -> Tuple[int, int]:
         if self.attn_group is None or T < self.attn_shard_min_tokens:
@@ -572,7 +579,7 @@ class UNetExecutor:
         buf = torch.empty(2, world * chunk, Cp, device=q_hi.device, dtype=self.pair_dtype)
         if qn > 0:
             rc = ops.attention_flash(q_hi, q_lo, vt_hi, vt_lo, T, heads, chp, None, buf[0], buf[1], scale, q0, qn)
-            assert rc == 0
+            self._check(rc, "holo_attention_flash (query range)")
         in_place = dist.get_backend(self.attn_group) == "nccl"   # NCCL gathers in place when the input is the rank's
         for half in (0, 1):                                      # slice of the output; gloo (CPU tests) wants a copy
             mine = buf[half, rank * chunk:(rank + 1) * chunk]

@@ -116,3 +116,33 @@ def test_short_sampling_chain_matches_oracle(graph):
         t = torch.full((1,), i, dtype=torch.long)
         x = do.p_sample(tab, lambda z, tt: uo.unet_forward(sd, z, tt), x, t, noises[i])["sample"]
     assert rel_err(got, x) < 2e-4  # 4 chained UNet evaluations
+
+
+def test_view_stream_matches_direct_forward_and_keeps_the_asserts():
+    """hd.ViewStream (double-buffered uploads from pinned host memory, bench.py's e2e path): every view equals the direct
+    forward() on the same inputs bit for bit, outputs of earlier views survive later ones (fresh tensors per call), and a
+    grid outside [-1, 1] still trips the reference's range assert for ITS view."""
+    import holo_diffusion_b200 as hd
+    C, R, HW, S = 16, 16, 24, 16
+    m, _, _ = _model(C, R, HW, S, 2, True)
+    cams = hd.get_simple_360_camera_trajectory(2 * math.pi, 8, -math.pi / 6, 10.0, ro.CANONICAL_CO3D_UP_AXIS, 3.2)
+    grids = [make_grid(C, R, seed=s).pin_memory() for s in (0, 1, 2, 3)]
+    views = [(g, cams[[i]]) for i, g in enumerate(grids)]
+    img_host = torch.empty(5, HW, HW).pin_memory()
+    vs = hd.ViewStream(m)
+    got, hosts = [], []
+    for preds, ih in vs.render(views, img_host):
+        got.append(preds)
+        hosts.append(ih.clone())
+    assert len(got) == 4
+    for i, (g, cam) in enumerate(views):
+        ref = m(camera=cam.to("cuda"), voxel_features=g.cuda())
+        assert torch.equal(got[i]["images_render"], ref["images_render"]), i      # earlier preds were not overwritten
+        assert torch.equal(got[i]["voxel_features"], ref["voxel_features"]), i
+        packed = torch.cat([ref["images_render"][0], ref["depths_render"][0], ref["masks_render"][0]], 0).cpu()
+        assert torch.equal(hosts[i], packed), i
+    bad = (grids[1] * 1.5).pin_memory()
+    t_ok, t_bad = vs.prefetch(grids[0], cams[[0]]), vs.prefetch(bad, cams[[1]])
+    vs.run(t_ok)
+    with pytest.raises(AssertionError, match="out of"):
+        vs.run(t_bad)

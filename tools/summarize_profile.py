@@ -66,6 +66,11 @@ KEYS = ["Kernel Name", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum"]
 
+# every counter that talks about the tcgen05 pipe / tensor memory (profiles/README.md says which one to trust)
+TENSOR_SUBSTR = ["pipe_tensor", "mem_tensor_reads", "mem_tensor_writes", "inst_executed_pipe_tensor", "inst_executed_pipe_tmem",
+                 "data_pipe_tc_wavefronts", "inst_executed_pipe_uniform"]
+
+
 def rep(path, out):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -73,7 +78,7 @@ def rep(path, out):
     with open(out, "w") as f:
         for r in rows[2:]:
             for i, h in enumerate(hdr):
-                if any(h == k or h.endswith(k) for k in KEYS):
+                if any(h == k or h.endswith(k) for k in KEYS) or any(t in h for t in TENSOR_SUBSTR):
                     f.write(f"{h} [{units[i]}] = {r[i]}\n")
             st = [(float(r[i]), h) for i, h in enumerate(hdr) if "pcsamp_warps_issue_stalled" in h and not h.endswith("_not_issued") and r[i]]
             tot = sum(v for v, _ in st) or 1
