@@ -24,9 +24,6 @@
 
 namespace {
 
-#ifndef HOLO_CONV_LDW
-#define HOLO_CONV_LDW 16
-#endif
 constexpr int TILE_W = 8, TILE_H = 4, TILE_D = 4;
 constexpr int BLOCK_M = TILE_W * TILE_H * TILE_D;  // 128
 constexpr int SLAB = 64;                           // bf16 channels per K slab = 128 bytes = one swizzle row
@@ -133,15 +130,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // Two TMEM loads (the [hi.hi + lo.hi] and [hi.lo] halves of W accumulator columns) and ONE wait in a single asm
 // statement: the loads overlap each other, and no consumer of the registers can be scheduled before the wait.
 __device__ __forceinline__ void tmem_ld_pair16(uint32_t ta, uint32_t tb, uint32_t (&a)[16], uint32_t (&b)[16]) {
@@ -156,25 +144,6 @@ __device__ __forceinline__ void tmem_ld_pair16(uint32_t ta, uint32_t tb, uint32_
         : "r"(ta), "r"(tb)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld_pair32(uint32_t ta, uint32_t tb, uint32_t (&a)[32], uint32_t (&b)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
-          "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
-          "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
-          "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]), "=r"(b[0]), "=r"(b[1]),
-          "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]),
-          "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]),
-          "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]),
-          "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
-        : "r"(ta), "r"(tb)
-        : "memory");
-}
-
 struct TcParams {
     int Cin, D, H, W, ksize, Cout;   // D, H, W = OUTPUT volume
     int tw, th, td;                  // voxel box of one M tile: 8x4x4 (128 rows) or 4x4x4 (64 rows, upper half idle)
@@ -432,16 +401,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 mbar_wait(&tmem_full_bar[buf], (cl >> 1) & 1);
                 tc_fence_after();
                 if (tr && et == 0 && cl == 0) P.trace[5] = clock64();
-                // pairs of 16-column loads with one wait each (LDW = 32 halves the round trips again where the register
-                // budget allows: BLOCK_N <= 64)
-                constexpr int LDW = (BLOCK_N == 32 || BLOCK_N == 64) ? HOLO_CONV_LDW : 16;
+                // pairs of 16-column loads with one wait each (32-column pairs measured no faster and cost 60 registers)
 #pragma unroll
-                for (int c0 = 0; c0 < BLOCK_N; c0 += LDW) {
-                    uint32_t acc[LDW], acc2[LDW];
-                    if constexpr (LDW == 32) tmem_ld_pair32(t_base + (uint32_t)c0, t_base + (uint32_t)(BLOCK_N + c0), acc, acc2);
-                    else tmem_ld_pair16(t_base + (uint32_t)c0, t_base + (uint32_t)(BLOCK_N + c0), acc, acc2);
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                    uint32_t acc[16], acc2[16];
+                    tmem_ld_pair16(t_base + (uint32_t)c0, t_base + (uint32_t)(BLOCK_N + c0), acc, acc2);
 #pragma unroll
-                    for (int j = 0; j < LDW; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const float s2 = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
                         accv[c0 + j] = ch == 0 ? s2 : accv[c0 + j] + s2;
                     }
@@ -736,7 +702,12 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     int nsplit = 1, per = k_total;
     const int base = tiles * (Cout / block_n);
     if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && (out_pitch == Cout || out_is_zeroed)) {
-        int want = (296 + base - 1) / base;
+        static const int target = [] {   // work items aimed at (2 per SM); HOLO_SPLITK_TARGET for tuning
+            const char* e = getenv("HOLO_SPLITK_TARGET");
+            const int v = e ? atoi(e) : 296;
+            return v < 148 ? 148 : v;
+        }();
+        int want = (target + base - 1) / base;
         int maxs = k_total / 4;
         nsplit = want < maxs ? want : maxs;
         if (nsplit < 1) nsplit = 1;
