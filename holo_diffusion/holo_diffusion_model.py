@@ -46,6 +46,12 @@ if HAVE_CONFIG:
             raysampler_class_type: str = "AdaptiveRaySampler"
             renderer_class_type: str = "MultiPassEmissionAbsorptionRenderer"
             implicit_function_class_type: str = "NeuralRadianceFieldImplicitFunction"
+            view_pooler_enabled: bool = False
+            image_feature_extractor_class_type: Optional[str] = None
+            mask_images: bool = True
+            mask_depths: bool = True
+            mask_threshold: float = 0.5
+            bg_color: tuple = (0.0, 0.0, 0.0)
 
             def __post_init__(self):
                 rs = plain(getattr(self, f"raysampler_{self.raysampler_class_type}_args", {}) or {})
@@ -58,6 +64,14 @@ if HAVE_CONFIG:
                 self.create_net_3d()
                 self.create_diffusion()
                 self._implicit_functions = self._construct_implicit_functions()
+                self.image_feature_extractor = self.view_pooler = None
+                if self.view_pooler_enabled:   # GenericModel.create_image_feature_extractor / create_view_pooler
+                    if self.image_feature_extractor_class_type is not None:
+                        if self.image_feature_extractor_class_type != "ResNetFeatureExtractor":
+                            raise NotImplementedError(self.image_feature_extractor_class_type)
+                        self.image_feature_extractor = _b200.encoder.ResNetFeatureExtractor(**plain(getattr(
+                            self, "image_feature_extractor_ResNetFeatureExtractor_args", {}) or {}))
+                    self.view_pooler = _b200.encoder.ViewPooler(**plain(getattr(self, "view_pooler_args", {}) or {}))
 
     @registry.register
     class HoloDiffusionModel(_Base):
@@ -91,7 +105,13 @@ if HAVE_CONFIG:
                 diffusion=self.diffusion, raysampler=rs, renderer=self.renderer,
                 implicit_functions=self._implicit_functions, render_image_width=self.render_image_width,
                 render_image_height=self.render_image_height, chunk_size_grid=self.chunk_size_grid,
-                use_cuda_graph=self.use_cuda_graph)
+                use_cuda_graph=self.use_cuda_graph,
+                image_feature_extractor=getattr(self, "image_feature_extractor", None),
+                view_pooler=getattr(self, "view_pooler", None) if getattr(self, "view_pooler_enabled", False) else None,
+                mask_images=getattr(self, "mask_images", True), mask_threshold=getattr(self, "mask_threshold", 0.5),
+                bg_color=tuple(getattr(self, "bg_color", (0.0, 0.0, 0.0))))
+            if core.pooled_feature_mapper is not None:   # :113, registered on the facade under the reference's name
+                self.pooled_feature_mapper = core.pooled_feature_mapper
             if self.net_3d is not None:   # the sampling loop replays the denoiser as one CUDA graph too
                 _b200.renderer.impl_of(self.net_3d)._exec.use_cuda_graph = self.use_cuda_graph
             adopt(self, core)   # children (net_3d, renderer, _implicit_functions) are already registered on the facade

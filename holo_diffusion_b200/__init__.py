@@ -12,6 +12,9 @@ lib()
 from .cameras import (AdaptiveRaySampler, ImplicitronRayBundle, PerspectiveCameras,  # noqa: E402,F401
                       get_simple_360_camera_trajectory, look_at_view_transform)
 from .diffusion import ImplicitronGaussianDiffusion  # noqa: E402,F401
+from . import encoder  # noqa: E402,F401
+from .encoder import (AngleWeightedReductionFeatureAggregator, MLPMeanFeatureAggregator,  # noqa: E402,F401
+                      ResNetFeatureExtractor, ViewPooler)
 from .model import HoloDiffusionModel  # noqa: E402,F401
 from .pipeline import ViewStream  # noqa: E402,F401
 from .renderer import (EmissionAbsorptionRaymarcher, EvaluationMode,  # noqa: E402,F401

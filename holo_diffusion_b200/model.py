@@ -6,8 +6,9 @@ render_image_width/height, raysampler/renderer argument groups), ``sample_random
 (image_rgb=None, voxel_features given, evaluation_mode=EVALUATION):
     asserts on the grid range :381 -> ``voxel_features = tanh(net_3d(voxel_features, t=0))`` :420-428 ->
     bind ``voxel_grid_features`` :431-438 -> ray sampler :442-448 -> ``_render`` :451-457 -> preds :469-523.
-The view-pooling encoder and the training branch (losses; it needs the UNet kernels' backward) are not built and raise;
-the renderer is differentiable on its own (autograd.py).
+The view-pooling encoder (image_rgb given: :327-373) runs on the kernels of encoder.py and feeds the same path.  The
+training branch (losses; it needs the UNet kernels' backward) is not built and raises; the renderer is differentiable
+on its own (autograd.py).
 Parameter names follow the reference so that checkpoints load: ``net_3d._net.*``,
 ``_implicit_functions.{i}._fn.render_mlp.*``.
 """
@@ -23,6 +24,7 @@ import torch.nn as nn
 from . import ops
 from .cameras import AdaptiveRaySampler, ImplicitronRayBundle, PerspectiveCameras
 from .diffusion import ImplicitronGaussianDiffusion
+from . import encoder as _enc
 from .renderer import (EvaluationMode, HoloMultiPassEmissionAbsorptionRenderer, HoloVoxelGridImplicitFunction,
                        ImplicitFunctionWrapper, RendererOutput, coerce_mode, impl_of)
 from .unet import SimpleUnet3D
@@ -72,7 +74,11 @@ class HoloDiffusionModel(nn.Module):
                  renderer_HoloMultiPassEmissionAbsorptionRenderer_args: Optional[dict] = None,
                  implicit_function_class_type: str = "HoloVoxelGridImplicitFunction",
                  implicit_function_HoloVoxelGridImplicitFunction_args: Optional[dict] = None,
-                 chunk_size_grid: int = 4096, use_cuda_graph: bool = True, **unused):
+                 chunk_size_grid: int = 4096, use_cuda_graph: bool = True, view_pooler_enabled: bool = False,
+                 image_feature_extractor_class_type: Optional[str] = None,
+                 image_feature_extractor_ResNetFeatureExtractor_args: Optional[dict] = None,
+                 view_pooler_args: Optional[dict] = None, mask_images: bool = True, mask_threshold: float = 0.5,
+                 bg_color=(0.0, 0.0, 0.0), **unused):
         super().__init__()
         if implicit_function_class_type != "HoloVoxelGridImplicitFunction":
             raise ValueError(f"{type(self)} supports only HoloVoxelGridImplicitFunction!")
@@ -104,11 +110,29 @@ class HoloDiffusionModel(nn.Module):
         self._graph = None
         self._graph_key = None
         self._sample_group = None   # set by shard_one_sample()
+        # view-pooling encoder (holo_diffusion_model.py:111-116 + GenericModel's image_feature_extractor / view_pooler)
+        self.view_pooler_enabled = view_pooler_enabled
+        self.mask_images, self.mask_threshold, self.bg_color = mask_images, mask_threshold, tuple(bg_color)
+        self.image_feature_extractor = self.view_pooler = self.pooled_feature_mapper = None
+        if view_pooler_enabled:
+            if image_feature_extractor_class_type not in (None, "ResNetFeatureExtractor"):
+                raise NotImplementedError(f"image feature extractor {image_feature_extractor_class_type}")
+            if image_feature_extractor_class_type is not None:
+                self.image_feature_extractor = _enc.ResNetFeatureExtractor(
+                    **(image_feature_extractor_ResNetFeatureExtractor_args or {}))
+            self.view_pooler = _enc.ViewPooler(**(view_pooler_args or {}))
+            self._init_encoder()
+
+    def _init_encoder(self):
+        self.pooled_feature_mapper = _enc.LazyLinearWithXavierInit(self.feature_size)       # :113
+        self.view_pooler.feature_aggregator.exclude_target_view = False                     # :115 ("by hard")
+        self.view_pooler.feature_aggregator.exclude_target_view_mask_features = False       # :116
 
     @classmethod
     def from_parts(cls, *, resol: int, volume_extent: float, feature_size: int, net_3d, diffusion, raysampler, renderer,
                    implicit_functions, render_image_width: int, render_image_height: int, chunk_size_grid: int = 4096,
-                   use_cuda_graph: bool = True) -> "HoloDiffusionModel":
+                   use_cuda_graph: bool = True, image_feature_extractor=None, view_pooler=None, mask_images: bool = True,
+                   mask_threshold: float = 0.5, bg_color=(0.0, 0.0, 0.0)) -> "HoloDiffusionModel":
         """Assemble the model from plug-ins that something else constructed (the Implicitron config system through the
         ``holo_diffusion`` shim: registry facades of SimpleUnet3D / the renderer / the implicit function, wrapped in
         pytorch3d's own ImplicitFunctionWrapper).  Same forward path as the plain constructor."""
@@ -125,6 +149,11 @@ class HoloDiffusionModel(nn.Module):
         self._range_stats = self._t0 = None
         self.use_cuda_graph = use_cuda_graph
         self._graph = self._graph_key = self._sample_group = None
+        self.view_pooler_enabled = view_pooler is not None
+        self.mask_images, self.mask_threshold, self.bg_color = mask_images, mask_threshold, tuple(bg_color)
+        self.image_feature_extractor, self.view_pooler, self.pooled_feature_mapper = image_feature_extractor, view_pooler, None
+        if view_pooler is not None:
+            self._init_encoder()
         return self
 
     def shard_one_sample(self, group=None, attn_min_tokens: int = 1 << 14):
@@ -234,7 +263,8 @@ class HoloDiffusionModel(nn.Module):
         return _cat_render_outputs(outs, B, spatial)
 
     def _weights_signature(self):
-        return sum(p._version for p in self.parameters()), next(self.parameters()).data_ptr()
+        ps = [p for m in (self.net_3d, self._implicit_functions) if m is not None for p in m.parameters()]
+        return sum(p._version for p in ps), ps[0].data_ptr()
 
     def _graph_forward(self, cam: PerspectiveCameras, voxel_features: torch.Tensor):
         """Replay the whole view (UNet + tanh + rays + render, ~600 launches) as one CUDA graph with static I/O."""
@@ -272,17 +302,55 @@ class HoloDiffusionModel(nn.Module):
         self._g_cam.focal_length.copy_(cam.focal_length, non_blocking=True)
         self._g_cam.principal_point.copy_(cam.principal_point, non_blocking=True)
 
+    # ------------------------------------------------------------------ views -> voxel grid
+    @torch.no_grad()
+    def encode_views(self, *, image_rgb: torch.Tensor, camera: PerspectiveCameras, fg_probability=None, mask_crop=None,
+                     sequence_name=None, n_targets: int = 1) -> torch.Tensor:
+        """The encoder branch of forward (holo_diffusion_model.py:248-257,327-373): (B, 3, H, W) views -> (1, C, R, R, R)
+        grid in [-1, 1].  Source views = the views of the first view's sequence after the n_targets targets (all of
+        them when none is left, :293-306)."""
+        dev = image_rgb.device
+        ops.require_cuda(dev, "HoloDiffusionModel.encode_views")
+        B = camera.R.shape[0]
+        if self.mask_images and fg_probability is not None:   # preprocess_input (:248-257)
+            image_rgb = _enc.mask_background(image_rgb, fg_probability, self.mask_threshold, self.bg_color)
+        if B <= n_targets:
+            n_targets = 1
+        sel = _enc.select_sources(sequence_name, B, n_targets) if B > 1 else [0]
+
+        def src(t):
+            return None if t is None else t[sel]
+
+        feats = self.image_feature_extractor(src(image_rgb), src(fg_probability))
+        C, R = self.feature_size, self.resol
+        pts = self.__dict__.get("_grid_pts")
+        if pts is None or pts.device != dev or pts.shape[0] != R ** 3:
+            pts = self.__dict__["_grid_pts"] = _enc.coord_grid(R, self.volume_extent, dev)
+        cams = camera[sel]
+        cams = PerspectiveCameras(cams.focal_length, cams.principal_point, cams.R, cams.T).to(dev)
+        vw = None if sequence_name is None else _enc.view_weights(sequence_name[:1], [sequence_name[i] for i in sel], dev)
+        rows = _enc.pool_views(self.view_pooler, pts, cams, feats, src(mask_crop), vw, mapper=self.pooled_feature_mapper)
+        grid_cf = torch.empty(C * R ** 3, device=dev)
+        ops.act_range(rows, R ** 3, C, 1, None, grid_cf, None)   # tanh (:373) + (V, C) rows -> (1, C, R, R, R)
+        return grid_cf.view(1, C, R, R, R)
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, *, image_rgb: Optional[torch.Tensor] = None, camera: PerspectiveCameras,
                 fg_probability=None, mask_crop=None, depth_map=None, sequence_name=None, frame_timestamp=None,
                 evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION, voxel_features: Optional[torch.Tensor] = None,
                 **kwargs) -> Dict[str, Any]:
-        if image_rgb is not None:
-            raise NotImplementedError("view-pooling encoder path (images -> voxel grid) is a 'next' row (SURVEY 8f)")
         if coerce_mode(evaluation_mode) != EvaluationMode.EVALUATION:
             raise NotImplementedError("training branch is a 'next' row (SURVEY 8f)")
         target_cameras = camera[[0]]  # n_targets = 1 (holo_diffusion_model.py:263-273,315)
+        if image_rgb is not None:
+            # fmt: off
+            assert self.view_pooler_enabled, "view_pooler must be enabled to use image_rgb"
+            assert voxel_features is None, "Cannot provide both image_rgb and voxel_features"
+            assert self.image_feature_extractor is not None, "Need an image_feature_extractor"
+            # fmt: on
+            voxel_features = self.encode_views(image_rgb=image_rgb, camera=camera, fg_probability=fg_probability,
+                                               mask_crop=mask_crop, sequence_name=sequence_name)
         if voxel_features is None:
             voxel_features = self.sample_random_voxel_features()
         dev = voxel_features.device

@@ -477,6 +477,59 @@ def shade_depth(depth, mask, focal, pp, smooth_k: int, mask_thr=0.5, depth_thr=1
     return out, om
 
 
+# ------------------------------------------------------------------ view-pooling encoder (csrc/viewpool.cu)
+class HoloFeatureMap(ctypes.Structure):   # include/holo_b200.h: holo_feature_map
+    _fields_ = [("data", ctypes.c_void_p), ("channels", _i), ("height", _i), ("width", _i)]
+
+
+VP_ACT = {"identity": 0, "relu": 1, "leakyrelu": 2, "softplus": 3}
+
+
+def viewpool_sample(pts, cam_R, cam_T, cam_focal, cam_pp, maps_cl, n_harmonic: int, Kpad: int, rows_per_view: int,
+                    x_hi, x_lo, mean_hi, mean_lo, mask_map=None, view_weight=None, eps: float = 1e-2, x_f32=None,
+                    mean_f32=None):
+    """pts (P, 3); maps_cl: list of channels-last (n_src, H, W, C) feature maps; rows of X / mean as operand pairs."""
+    n_src = cam_R.shape[0]
+    arr = _feature_map_array(maps_cl, n_src)
+    Hm, Wm = (mask_map.shape[-2], mask_map.shape[-1]) if mask_map is not None else (0, 0)
+    lib().call("holo_viewpool_sample", _ptr(pts), pts.shape[0], _ptr(cam_R), _ptr(cam_T), _ptr(cam_focal), _ptr(cam_pp),
+               n_src, ctypes.cast(arr, ctypes.c_void_p), len(maps_cl), _ptr(mask_map), Hm, Wm, _ptr(view_weight),
+               int(n_harmonic), float(eps), int(Kpad), int(rows_per_view), _ptr16(x_hi), _ptr16(x_lo), _ptr16(mean_hi),
+               _ptr16(mean_lo), _ptr(x_f32), _ptr(mean_f32), _pair_f16(x_hi, x_lo, mean_hi, mean_lo), _stream())
+
+
+def _feature_map_array(maps_cl, n_src: int):
+    arr = (HoloFeatureMap * len(maps_cl))()
+    for k, m in enumerate(maps_cl):
+        if m.dim() != 4 or m.shape[0] != n_src:
+            raise HoloError(f"feature map {k}: expected (n_src={n_src}, H, W, C), got {tuple(m.shape)}")
+        arr[k].data, arr[k].channels, arr[k].height, arr[k].width = _ptr(m, name=f"feature map {k}").value, m.shape[3], \
+            m.shape[1], m.shape[2]
+    return arr
+
+
+def viewpool_angle_reduce(pts, cam_R, cam_T, cam_focal, cam_pp, maps_cl, Kpad: int, out_hi, out_lo, mask_map=None,
+                          view_weight=None, eps: float = 1e-2, gamma: float = 1.0, min_ray_angle_weight: float = 0.1,
+                          with_std: bool = True, out_f32=None):
+    n_src = cam_R.shape[0]
+    arr = _feature_map_array(maps_cl, n_src)
+    Hm, Wm = (mask_map.shape[-2], mask_map.shape[-1]) if mask_map is not None else (0, 0)
+    lib().call("holo_viewpool_angle_reduce", _ptr(pts), pts.shape[0], _ptr(cam_R), _ptr(cam_T), _ptr(cam_focal),
+               _ptr(cam_pp), n_src, ctypes.cast(arr, ctypes.c_void_p), len(maps_cl), _ptr(mask_map), Hm, Wm,
+               _ptr(view_weight), float(eps), float(gamma), float(min_ray_angle_weight), 1 if with_std else 0, int(Kpad),
+               _ptr16(out_hi), _ptr16(out_lo), _ptr(out_f32), _pair_f16(out_hi, out_lo), _stream())
+
+
+def viewpool_act_split(y, point_term, n_views: int, rows_per_view: int, C: int, act: str, hi, lo):
+    lib().call("holo_viewpool_act_split", _ptr(y), _ptr(point_term), int(n_views), int(rows_per_view), int(C), VP_ACT[act],
+               _ptr16(hi), _ptr16(lo), _pair_f16(hi, lo), _stream())
+
+
+def viewpool_reduce(z, n_views: int, rows_per_view: int, n_pts: int, C: int, out=None, out_hi=None, out_lo=None):
+    lib().call("holo_viewpool_reduce", _ptr(z), int(n_views), int(rows_per_view), int(n_pts), int(C), _ptr(out),
+               _ptr16(out_hi), _ptr16(out_lo), _pair_f16(out_hi, out_lo), _stream())
+
+
 # ------------------------------------------------------------------ whole-graph denoiser (csrc/unet_exec.cu)
 class HoloUnetConfig(ctypes.Structure):   # include/holo_b200.h: holo_unet_config (same field order)
     _fields_ = [("in_channels", _i), ("model_channels", _i), ("out_channels", _i), ("num_res_blocks", _i), ("n_levels", _i),

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 120
+#define HOLO_B200_VERSION 121
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -381,6 +381,52 @@ int holo_frame_u8(const float* src_chw, int C, int H, int W, int out_h, int out_
 int holo_shade_depth(const float* depth, const float* mask, int H, int W, float fx, float fy, float px, float py,
                      int smooth_k, float mask_thr, float depth_thr, const float* material10_host, const float* bg3_host,
                      float* scratch_depth, void* scratch_ok_u8, float* out_3hw, float* out_mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * View-pooling encoder: source views -> voxel grid.
+ *   holo_diffusion_model.py:327-373: VolumeLocator grid points -> view_pooler (pytorch3d ViewSampler +
+ *   custom_modules.py:162-334 MLPMeanFeatureAggregator) -> pooled_feature_mapper -> tanh.
+ * The Linear layers run on holo_gemm_tc; these three kernels are the gather and the reductions around them.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct holo_feature_map {
+    const float* data;          /* channels-LAST (n_src, height, width, channels) fp32 on the device */
+    int channels, height, width;
+} holo_feature_map;
+
+/* Project n_pts world points into the n_src source cameras, sample every feature map there (bilinear, zeros padding,
+ * align_corners = False, NDC -> grid_sample coordinates as pytorch3d ndc_grid_sample), append the harmonic embedding
+ * of the unit vector camera centre -> point, and multiply by the aggregation weight
+ *   w[s][p] = view_weight[s] * (mask_map ? nearest(mask_map[s]) : 1)
+ * -- ViewSampler.forward / project_points_and_sample (eps: clamp of the perspective divide) and
+ * custom_modules.py:241-260,283-334.  Rows: X[(s * rows_per_view + p) * Kpad + j] as a 16-bit hi/lo pair (pair_f16 as
+ * for holo_conv3d_tc), columns [features of map 0 | map 1 | ... | sin | cos | dir | zero padding to Kpad];
+ * mean[p * Kpad + j] = sum_s X w / max(sum_s w, 1e-2) (wmean of _avgmaxstd_reduction_function, AVG).
+ * x_f32 (n_src, n_pts, F + E) / mean_f32 (n_pts, F + E): optional fp32 copies.  maps: HOST array. Kpad <= 256. */
+int holo_viewpool_sample(const float* pts, long long n_pts, const float* R, const float* T, const float* focal,
+                         const float* pp, int n_src, const holo_feature_map* maps, int n_maps, const float* mask_map,
+                         int Hm, int Wm, const float* view_weight, int n_harmonic, float eps, int Kpad,
+                         long long rows_per_view, void* x_hi, void* x_lo, void* mean_hi, void* mean_lo, float* x_f32,
+                         float* mean_f32, int pair_f16, void* stream);
+/* pytorch3d AngleWeightedReductionFeatureAggregator (the view_pooler's default aggregator, configs/base.yaml:165-168
+ * leaves it in place; restated from memory of pytorch3d 0.7.4): same projection / sampling as holo_viewpool_sample,
+ *   w[s][p] = view_weight[s] * mask * ((0.5 (d_s . d_0 + 1))^gamma + min_ray_angle_weight)
+ * (d_s: unit vector camera s -> point; camera 0 is the reference view), reduced over the views to
+ * [wmean | sqrt(max(wvar, 1e-4))] per feature map (with_std = 0: the mean alone): out row p = hi/lo pair of
+ * [mu_0 | std_0 | mu_1 | std_1 | ... | zero padding to Kpad]; out_f32 (n_pts, (1 + with_std) * F) optional. */
+int holo_viewpool_angle_reduce(const float* pts, long long n_pts, const float* R, const float* T, const float* focal,
+                               const float* pp, int n_src, const holo_feature_map* maps, int n_maps,
+                               const float* mask_map, int Hm, int Wm, const float* view_weight, float eps, float gamma,
+                               float min_ray_angle_weight, int with_std, int Kpad, void* out_hi, void* out_lo,
+                               float* out_f32, int pair_f16, void* stream);
+/* H = act(Y[s][p] + point_term[p]) as a hi/lo pair; Y (n_views * rows_per_view, C), point_term (rows_per_view, C) or
+ * NULL.  act: 0 identity, 1 ReLU, 2 LeakyReLU(0.2), 3 Softplus -- the activations of MLPWithInputSkips
+ * (custom_modules.py:62-88) between the aggregator's Linear layers (:255-261). */
+int holo_viewpool_act_split(const float* y, const float* point_term, int n_views, long long rows_per_view, int C,
+                            int act, void* hi, void* lo, int pair_f16, void* stream);
+/* G[p] = sum_s softmax_s(Z[s][p][0]) Z[s][p][:] -- custom_modules.py:262-264; Z (n_views, rows_per_view, C);
+ * out (n_pts, C) fp32 and/or its hi/lo pair (the operand of the pooled_feature_mapper GEMM). */
+int holo_viewpool_reduce(const float* z, int n_views, long long rows_per_view, long long n_pts, int C, float* out,
+                         void* out_hi, void* out_lo, int pair_f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,10 @@ class _Registry:
         self.classes = {}
 
     def register(self, cls):
+        # class X(torch.nn.Module, SomeReplaceableBase): Module.__init__ comes first in the MRO; the real
+        # expand_args_fields generates a dataclass __init__ on X itself (fields, then __post_init__)
+        if issubclass(cls, Configurable) and cls.__init__ is torch.nn.Module.__init__:
+            cls.__init__ = Configurable.__init__
         self.classes[cls.__name__] = cls
         return cls
 

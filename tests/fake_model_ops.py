@@ -28,9 +28,10 @@ def _dec(i: int) -> float:
 
 def act_range(x_cl, V, C, act, y_cl, y_cf, stats):
     y = torch.tanh(x_cl) if act == 1 else x_cl
-    stats[0] = _enc(min(_dec(stats[0]), float(y.min())))
-    stats[1] = _enc(max(_dec(stats[1]), float(y.max())))
-    stats[2] += int(torch.isnan(y).sum())
+    if stats is not None:
+        stats[0] = _enc(min(_dec(stats[0]), float(y.min())))
+        stats[1] = _enc(max(_dec(stats[1]), float(y.max())))
+        stats[2] += int(torch.isnan(y).sum())
     if y_cl is not None:
         y_cl.copy_(y)
     if y_cf is not None:

@@ -29,7 +29,7 @@ UNET = dict(model_ch=32, num_res_blocks=1, channel_mult=(1, 2), attention_resolu
 
 
 def generate():
-    for p in (REF, ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "pt3d_stub")):
+    for p in (ROOT, REF, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "pt3d_stub")):   # REF ahead of ROOT: holo_diffusion = the reference, not the shim
         if p not in sys.path:
             sys.path.insert(0, p)
     from fixtures import make_grid, make_mlp

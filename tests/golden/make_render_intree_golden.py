@@ -22,7 +22,7 @@ OUT = os.path.join(HERE, "render_intree_ref.npz")
 
 
 def generate():
-    for p in (REF, ROOT, os.path.join(ROOT, "oracle", "pt3d_stub")):
+    for p in (ROOT, REF, os.path.join(ROOT, "oracle", "pt3d_stub")):   # REF ahead of ROOT: holo_diffusion = the reference, not the shim
         if p not in sys.path:
             sys.path.insert(0, p)
     from holo_diffusion.holo_multipass_ea import HoloMultiPassEmissionAbsorptionRenderer

@@ -29,7 +29,7 @@ UNET = dict(image_size=16, in_channels=16, out_channels=16, model_channels=64, n
 
 
 def generate():
-    for p in (REF, ROOT, os.path.join(ROOT, "oracle", "pt3d_stub")):
+    for p in (ROOT, REF, os.path.join(ROOT, "oracle", "pt3d_stub")):   # REF ahead of ROOT: holo_diffusion = the reference, not the shim
         if p not in sys.path:
             sys.path.insert(0, p)
     from holo_diffusion.utils.diffusion_utils import ImplicitronGaussianDiffusion, SimpleUnet3D

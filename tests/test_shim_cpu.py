@@ -25,9 +25,10 @@ def _run(mode):
 def test_drop_in_package(mode):
     res = _run(mode)
     assert res["have_config"] == (mode == "stub")
-    if mode == "stub":   # the four @registry.register names of the reference, resolvable like create_net_3d does
+    if mode == "stub":   # the five @registry.register names of the reference's holo_diffusion package (custom_modules.py:162,
+        # holo_multipass_ea.py:15, holo_voxel_grid_implicit_function.py:148, holo_diffusion_model.py:44, diffusion_utils.py:41)
         assert res["registered"] == ["HoloDiffusionModel", "HoloMultiPassEmissionAbsorptionRenderer",
-                                     "HoloVoxelGridImplicitFunction", "SimpleUnet3D"]
+                                     "HoloVoxelGridImplicitFunction", "MLPMeanFeatureAggregator", "SimpleUnet3D"]
         assert res["registry_get"]
         assert res["model_class"] == "holo_diffusion.holo_diffusion_model.HoloDiffusionModel"
     else:
