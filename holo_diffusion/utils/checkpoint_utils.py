@@ -19,7 +19,11 @@ _MODEL_KEYS = ("resol", "volume_extent", "feature_size", "num_passes", "render_i
                "net_3d_enabled", "net_3d_class_type", "net_3d_SimpleUnet3D_args", "diffusion_enabled", "diffusion_args",
                "raysampler_class_type", "raysampler_AdaptiveRaySampler_args", "renderer_class_type",
                "renderer_HoloMultiPassEmissionAbsorptionRenderer_args", "implicit_function_class_type",
-               "implicit_function_HoloVoxelGridImplicitFunction_args", "chunk_size_grid")
+               "implicit_function_HoloVoxelGridImplicitFunction_args", "chunk_size_grid",
+               # the view-pooling encoder (configs/base.yaml:160-168)
+               "view_pooler_enabled", "image_feature_extractor_class_type", "image_feature_extractor_ResNetFeatureExtractor_args",
+               "view_pooler_args", "mask_images", "mask_threshold", "bg_color")
+_ENCODER_PREFIXES = ("image_feature_extractor.", "view_pooler.", "pooled_feature_mapper.")
 
 
 def _get_config_from_experiment_directory(experiment_directory: str) -> dict:
@@ -67,10 +71,13 @@ def load_experiment(ExperimentClass, exp_dir: str, restrict_sequence_name: Optio
     if ckpt is not None:
         sd = torch.load(ckpt, map_location="cpu")
         missing, unexpected = model.load_state_dict(sd, strict=False)
-        # the encoder side of the checkpoint (image_feature_extractor.*, view_pooler.*, pooled_feature_mapper.*) has
-        # no counterpart on the sampling path; anything else that does not match is an error
-        bad = [k for k in missing] + [k for k in unexpected
-                                      if not k.startswith(("image_feature_extractor.", "view_pooler.", "pooled_feature_mapper."))]
+        # the encoder side (image_feature_extractor.*, view_pooler.*, pooled_feature_mapper.*) loads when the config
+        # enables the view pooler; a model built without it skips those keys, and a sampling-only checkpoint (no
+        # encoder keys at all) may leave the encoder at its initialisation.  Anything else that does not match is an error
+        ckpt_has_encoder = any(k.startswith(_ENCODER_PREFIXES) for k in sd)
+        model_has_encoder = bool(getattr(model, "view_pooler_enabled", False))
+        bad = [k for k in missing if not (k.startswith(_ENCODER_PREFIXES) and not ckpt_has_encoder)] + \
+              [k for k in unexpected if not (k.startswith(_ENCODER_PREFIXES) and not model_has_encoder)]
         if bad:
             raise RuntimeError(f"checkpoint {ckpt} does not match the model: {bad[:8]} ...")
     model.to(device)

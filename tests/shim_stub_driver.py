@@ -19,9 +19,12 @@ import yaml  # noqa: E402
 import holo_diffusion_b200 as hd  # noqa: E402
 from holo_diffusion_b200 import ops  # noqa: E402
 
+import fake_encoder_ops  # noqa: E402
 import fake_model_ops  # noqa: E402
 
 fake_model_ops.install(ops)
+fake_encoder_ops.install(ops)
+hd.encoder.PAIR_DTYPE = torch.float32   # the GEMM stand-in keeps exact operand "pairs"
 _fused_calls = []
 _rf = ops.render_fwd
 ops.render_fwd = lambda *a, **k: (_fused_calls.append(k.get("n_passes", 1)), _rf(*a, **k))[1]
@@ -78,6 +81,36 @@ res["preds_keys"] = sorted(a.keys())
 res["facade_vs_plain"] = float((a["images_render"] - b["images_render"]).abs().max())
 res["image_shape"] = list(a["images_render"].shape)
 res["prev_stage"] = a["rendered"].prev_stage is not None
+
+# ---- the view-pooling encoder through the same constructor keys (configs/base.yaml:160-168, hydrant.yaml:184-193)
+ENC_ARGS = dict(MODEL_ARGS, view_pooler_enabled=True, image_feature_extractor_class_type="ResNetFeatureExtractor",
+                image_feature_extractor_ResNetFeatureExtractor_args=dict(proj_dim=4, image_rescale=0.5, stages=[1, 2]),
+                view_pooler_args=dict(view_sampler_args=dict(masked_sampling=False, sampling_mode="bilinear"),
+                                      feature_aggregator_class_type="MLPMeanFeatureAggregator",
+                                      feature_aggregator_MLPMeanFeatureAggregator_args=dict(n_hidden=16, dim_out=16)))
+enc_model = exact_pairs(HoloDiffusionModel(use_cuda_graph=False, **ENC_ARGS)).eval()
+g2 = torch.Generator().manual_seed(2)
+views = dict(image_rgb=torch.rand(4, 3, 32, 32, generator=g2), fg_probability=torch.rand(4, 1, 32, 32, generator=g2),
+             mask_crop=torch.ones(4, 1, 32, 32), sequence_name=["seq"] * 4, camera=cams)
+pe = enc_model(**views)
+res["encoder_modules"] = sorted({k.split(".")[0] for k in enc_model.state_dict()})
+res["encoder_grid"] = [list(pe["voxel_features"].shape), float(pe["voxel_features"].abs().max())]
+plain_enc = exact_pairs(hd.HoloDiffusionModel(use_cuda_graph=False, **ENC_ARGS)).eval()
+plain_enc.load_state_dict(enc_model.state_dict(), strict=True)
+res["encoder_facade_vs_plain"] = float((plain_enc(**views)["images_render"] - pe["images_render"]).abs().max())
+
+with tempfile.TemporaryDirectory() as tmp:
+    # a checkpoint of the encoder model loads with its encoder keys (image_feature_extractor.*, view_pooler.*, pooled_feature_mapper.*)
+    cfg_e = {"model_factory_ImplicitronModelFactory_args": {"model_class_type": "HoloDiffusionModel",
+                                                            "model_HoloDiffusionModel_args": ENC_ARGS}}
+    yaml.safe_dump(cfg_e, open(os.path.join(tmp, "expconfig.yaml"), "w"))
+    torch.save(dict(enc_model.state_dict()), os.path.join(tmp, "model_epoch_00000001.pth"))
+    _, m3, _ = load_experiment(None, tmp, None, (HW, HW), 3, torch.device("cpu"))
+    m3.use_cuda_graph = False
+    exact_pairs(m3).eval()
+    if hasattr(m3, "_impl"):
+        m3._impl.use_cuda_graph = False
+    res["encoder_ckpt_roundtrip"] = float((m3(**views)["images_render"] - pe["images_render"]).abs().max())
 
 with tempfile.TemporaryDirectory() as tmp:
     # generate_samples.py:87-138: exp_dir with expconfig.yaml + checkpoint -> load_experiment -> render_flyaround

@@ -46,3 +46,8 @@ def test_drop_in_package(mode):
                                                          "_shaded_depth_render")}
     assert res["video_dtype"] == "uint8" and res["saved_voxels"]
     assert res["progressive"] == {"images_render": [2, 8, 8, 3]}
+    # the view-pooling encoder under the reference's constructor keys and state-dict names: forward(image_rgb=...) runs,
+    # facade == plain implementation, and a checkpoint with its encoder keys round-trips through load_experiment
+    assert {"image_feature_extractor", "view_pooler", "pooled_feature_mapper"} <= set(res["encoder_modules"])
+    assert res["encoder_grid"][0] == [1, 16, 8, 8, 8] and 0 < res["encoder_grid"][1] <= 1.0
+    assert res["encoder_facade_vs_plain"] == 0.0 and res["encoder_ckpt_roundtrip"] == 0.0
