@@ -59,21 +59,6 @@ __device__ __forceinline__ void ndc_to_pixel(float x_ndc, float y_ndc, int H, in
     iy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
 }
 
-__device__ __forceinline__ float bilinear_cl(const float* __restrict__ img, int C, int H, int W, int c, float ix, float iy) {
-    // zeros padding: a tap outside the image contributes nothing
-    if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return 0.f;
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
-    const bool xa = x0 >= 0, xb = x1 < W, ya = y0 >= 0, yb = y1 < H;
-    float v = 0.f;
-    if (ya && xa) v += __ldg(img + ((size_t)y0 * W + x0) * C + c) * (wx0 * wy0);
-    if (ya && xb) v += __ldg(img + ((size_t)y0 * W + x1) * C + c) * (wx1 * wy0);
-    if (yb && xa) v += __ldg(img + ((size_t)y1 * W + x0) * C + c) * (wx0 * wy1);
-    if (yb && xb) v += __ldg(img + ((size_t)y1 * W + x1) * C + c) * (wx1 * wy1);
-    return v;
-}
-
 __device__ __forceinline__ float nearest_1ch(const float* __restrict__ img, int H, int W, float ix, float iy) {
     if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return 0.f;
     const int x = (int)nearbyintf(ix), y = (int)nearbyintf(iy);   // round half to even, as F.grid_sample(mode="nearest")
@@ -81,103 +66,185 @@ __device__ __forceinline__ float nearest_1ch(const float* __restrict__ img, int 
     return __ldg(img + (size_t)y * W + x);
 }
 
+// Cameras staged in shared memory once per block: R(9) T(3) focal(2) pp(2) centre(3) view weight(1)
+constexpr int CAM_FLOATS = 20;
+
+__device__ __forceinline__ void stage_cameras(const VpParams& P, float* cam) {
+    for (int s = threadIdx.x; s < P.n_src; s += blockDim.x) {
+        float* c = cam + s * CAM_FLOATS;
+        const float* R = P.R + s * 9;
+        for (int i = 0; i < 9; ++i) c[i] = R[i];
+        const float t0 = P.T[s * 3], t1 = P.T[s * 3 + 1], t2 = P.T[s * 3 + 2];
+        c[9] = t0, c[10] = t1, c[11] = t2;
+        c[12] = P.focal[s * 2], c[13] = P.focal[s * 2 + 1], c[14] = P.pp[s * 2], c[15] = P.pp[s * 2 + 1];
+        // centre = -T R^T (custom_modules.py:283-304: "does not produce nans randomly unlike get_camera_center()")
+        c[16] = -(t0 * R[0] + t1 * R[1] + t2 * R[2]);
+        c[17] = -(t0 * R[3] + t1 * R[4] + t2 * R[5]);
+        c[18] = -(t0 * R[6] + t1 * R[7] + t2 * R[8]);
+        c[19] = P.view_weight ? P.view_weight[s] : 1.f;
+    }
+    __syncthreads();
+}
+
 // Per (view, point): NDC projection, aggregation weight w = view_weight * sampled mask, unit vector centre -> point
-__device__ __forceinline__ void view_geometry(const VpParams& P, int s, float px, float py, float pz, float& x_ndc,
-                                              float& y_ndc, float& vw, float& w, float& dx, float& dy, float& dz) {
-    const float* R = P.R + s * 9;
-    const float t0 = __ldg(P.T + s * 3), t1 = __ldg(P.T + s * 3 + 1), t2 = __ldg(P.T + s * 3 + 2);
+__device__ __forceinline__ void view_geometry(const VpParams& P, const float* __restrict__ c, int s, float px, float py,
+                                              float pz, float& x_ndc, float& y_ndc, float& vw, float& w, float& dx,
+                                              float& dy, float& dz) {
     // X_cam = X_world R + T (row vectors)
-    const float xc = px * __ldg(R + 0) + py * __ldg(R + 3) + pz * __ldg(R + 6) + t0;
-    const float yc = px * __ldg(R + 1) + py * __ldg(R + 4) + pz * __ldg(R + 7) + t1;
-    const float zc = px * __ldg(R + 2) + py * __ldg(R + 5) + pz * __ldg(R + 8) + t2;
+    const float xc = px * c[0] + py * c[3] + pz * c[6] + c[9];
+    const float yc = px * c[1] + py * c[4] + pz * c[7] + c[10];
+    const float zc = px * c[2] + py * c[5] + pz * c[8] + c[11];
     // NDC projection with the sign-preserving clamp of the homogeneous divide (Transform3d.transform_points eps)
-    const float sgn = zc < 0.f ? -1.f : 1.f;
-    const float den = sgn * fmaxf(fabsf(zc), P.eps);
-    x_ndc = (__ldg(P.focal + s * 2) * xc + __ldg(P.pp + s * 2) * zc) / den;
-    y_ndc = (__ldg(P.focal + s * 2 + 1) * yc + __ldg(P.pp + s * 2 + 1) * zc) / den;
-    vw = P.view_weight ? __ldg(P.view_weight + s) : 1.f;
+    const float den = (zc < 0.f ? -1.f : 1.f) * fmaxf(fabsf(zc), P.eps);
+    const float rden = 1.f / den;
+    x_ndc = (c[12] * xc + c[14] * zc) * rden;
+    y_ndc = (c[13] * yc + c[15] * zc) * rden;
+    vw = c[19];
     w = vw;
     if (P.mask_map) {
         float ix, iy;
         ndc_to_pixel(x_ndc, y_ndc, P.Hm, P.Wm, ix, iy);
         w *= nearest_1ch(P.mask_map + (size_t)s * P.Hm * P.Wm, P.Hm, P.Wm, ix, iy);
     }
-    // ray direction point <- camera centre, centre = -T R^T (custom_modules.py:283-304), F.normalize eps 1e-12
-    const float cx = -(t0 * __ldg(R + 0) + t1 * __ldg(R + 1) + t2 * __ldg(R + 2));
-    const float cy = -(t0 * __ldg(R + 3) + t1 * __ldg(R + 4) + t2 * __ldg(R + 5));
-    const float cz = -(t0 * __ldg(R + 6) + t1 * __ldg(R + 7) + t2 * __ldg(R + 8));
-    dx = px - cx, dy = py - cy, dz = pz - cz;
+    dx = px - c[16], dy = py - c[17], dz = pz - c[18];   // F.normalize, eps 1e-12
     const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
     dx *= inv, dy *= inv, dz *= inv;
 }
 
-__device__ __forceinline__ float sample_column(const VpParams& P, int s, int j, float x_ndc, float y_ndc) {
-    VpMap m = P.maps[0];
+// Four consecutive columns of one feature map, owned by one lane for the whole kernel.  Every map's channel count is a
+// multiple of 4 (the host pads with zero channels), so a group never straddles two maps and its taps are one float4.
+struct ColGroup {
+    const float* base;        // map data + first channel of the group (view 0)
+    size_t view_stride;       // H * W * C floats
+    int C, H, W;
+    float ax, bx, ay, by;     // pixel = ndc * a + b  (negation, aspect scaling and the align_corners=False shift folded)
+    int kind;                 // 0 feature, 1 ray embedding, 2 zero padding, 3 beyond the row
+};
+
+__device__ __forceinline__ ColGroup make_group(const VpParams& P, int j0, int n_cols) {
+    ColGroup g;
+    g.base = nullptr, g.view_stride = 0, g.C = g.H = g.W = 1, g.ax = g.bx = g.ay = g.by = 0.f;
+    if (j0 >= n_cols) {
+        g.kind = 3;
+    } else if (j0 < P.F) {
+        VpMap m = P.maps[0];
 #pragma unroll
-    for (int k = 1; k < VP_MAX_MAPS; ++k)   // static indices: the parameter struct stays in the constant bank
-        if (k < P.n_maps && j >= P.maps[k].c0) m = P.maps[k];
-    float ix, iy;
-    ndc_to_pixel(x_ndc, y_ndc, m.H, m.W, ix, iy);
-    return bilinear_cl(m.data + (size_t)s * m.H * m.W * m.C, m.C, m.H, m.W, j - m.c0, ix, iy);
+        for (int k = 1; k < VP_MAX_MAPS; ++k)   // static indices: the parameter struct stays in the constant bank
+            if (k < P.n_maps && j0 >= P.maps[k].c0) m = P.maps[k];
+        g.kind = 0, g.base = m.data + (j0 - m.c0), g.view_stride = (size_t)m.H * m.W * m.C, g.C = m.C, g.H = m.H, g.W = m.W;
+        const float sx = m.H >= m.W ? 1.f : (float)m.H / (float)m.W, sy = m.H >= m.W ? (float)m.W / (float)m.H : 1.f;
+        g.ax = -0.5f * sx * (float)m.W, g.bx = 0.5f * ((float)m.W - 1.f);
+        g.ay = -0.5f * sy * (float)m.H, g.by = 0.5f * ((float)m.H - 1.f);
+    } else {
+        g.kind = j0 < P.Kx ? 1 : 2;
+    }
+    return g;
 }
 
-// One warp per point; lanes walk the columns of the row, the view loop is inside (the mean needs all views).
+// bilinear, zeros padding: a tap outside the image contributes nothing
+__device__ __forceinline__ float4 sample_group(const ColGroup& g, int s, float x_ndc, float y_ndc) {
+    const float ix = fmaf(x_ndc, g.ax, g.bx), iy = fmaf(y_ndc, g.ay, g.by);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(ix > -1.f && ix < (float)g.W && iy > -1.f && iy < (float)g.H)) return v;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float wx1 = ix - fx0, wx0 = 1.f - wx1, wy1 = iy - fy0, wy0 = 1.f - wy1;
+    const bool xa = x0 >= 0, xb = x0 + 1 < g.W, ya = y0 >= 0, yb = y0 + 1 < g.H;
+    const float* p = g.base + (size_t)s * g.view_stride + ((ptrdiff_t)y0 * g.W + x0) * g.C;
+    const int dxs = g.C, dys = g.W * g.C;
+    if (ya && xa) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); const float k = wx0 * wy0; v.x += t.x * k, v.y += t.y * k, v.z += t.z * k, v.w += t.w * k; }
+    if (ya && xb) { const float4 t = __ldg(reinterpret_cast<const float4*>(p + dxs)); const float k = wx1 * wy0; v.x += t.x * k, v.y += t.y * k, v.z += t.z * k, v.w += t.w * k; }
+    if (yb && xa) { const float4 t = __ldg(reinterpret_cast<const float4*>(p + dys)); const float k = wx0 * wy1; v.x += t.x * k, v.y += t.y * k, v.z += t.z * k, v.w += t.w * k; }
+    if (yb && xb) { const float4 t = __ldg(reinterpret_cast<const float4*>(p + dys + dxs)); const float k = wx1 * wy1; v.x += t.x * k, v.y += t.y * k, v.z += t.z * k, v.w += t.w * k; }
+    return v;
+}
+
+// HarmonicEmbedding(append_input): [sin(d_i 2^f)] (i major, f minor), [cos(...)], d ; e = column within the embedding
+__device__ __forceinline__ float embed_column(int e, int n_harm, float dx, float dy, float dz) {
+    const int nh3 = 3 * n_harm;
+    if (e < 2 * nh3) {
+        const int q = e < nh3 ? e : e - nh3;
+        const int comp = q / n_harm, f = q - comp * n_harm;
+        const float a = (comp == 0 ? dx : (comp == 1 ? dy : dz)) * (float)(1 << f);
+        return e < nh3 ? sinf(a) : cosf(a);
+    }
+    const int comp = e - 2 * nh3;
+    return comp == 0 ? dx : (comp == 1 ? dy : (comp == 2 ? dz : 0.f));
+}
+
+__device__ __forceinline__ void store_pair4(uint16_t* hi, uint16_t* lo, size_t at, float4 v, bool f16) {
+    uint2 h, l;
+    holo_split2(v.x, v.y, f16, h.x, l.x);
+    holo_split2(v.z, v.w, f16, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + at) = h;
+    *reinterpret_cast<uint2*>(lo + at) = l;
+}
+
+constexpr int VP_GROUPS = VP_MAX_K / 128;   // 4-column groups per lane
+
+// One warp per point; every lane owns up to two 4-column groups of the row; the view loop is inside (the mean needs
+// all views).  Rows: [features of map 0 | map 1 | ... | sin | cos | dir | zero padding to Kpad].
 __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) {
+    extern __shared__ float cam[];
+    stage_cameras(P, cam);
     const int lane = threadIdx.x & 31;
+    const bool f16 = P.pair_f16 != 0;
+    ColGroup grp[VP_GROUPS];
+#pragma unroll
+    for (int g = 0; g < VP_GROUPS; ++g) grp[g] = make_group(P, (g * 32 + lane) * 4, P.Kpad);
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    constexpr int ROUNDS = VP_MAX_K / 32;
     for (long long p = warp0; p < P.n_pts; p += n_warps) {
         const float px = __ldg(P.pts + p * 3), py = __ldg(P.pts + p * 3 + 1), pz = __ldg(P.pts + p * 3 + 2);
-        float acc[ROUNDS];
+        float4 acc[VP_GROUPS];
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) acc[r] = 0.f;
+        for (int g = 0; g < VP_GROUPS; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         float wsum = 0.f;
         for (int s = 0; s < P.n_src; ++s) {
             float x_ndc, y_ndc, vw, w, dx, dy, dz;
-            view_geometry(P, s, px, py, pz, x_ndc, y_ndc, vw, w, dx, dy, dz);
+            view_geometry(P, cam + s * CAM_FLOATS, s, px, py, pz, x_ndc, y_ndc, vw, w, dx, dy, dz);
             const size_t row = ((size_t)s * P.rows_per_view + (size_t)p) * P.Kpad;
 #pragma unroll
-            for (int r = 0; r < ROUNDS; ++r) {
-                const int j = r * 32 + lane;
-                if (j < P.Kpad) {
-                    float v = 0.f;
-                    if (j < P.F) {
-                        v = sample_column(P, s, j, x_ndc, y_ndc) * vw;
-                    } else if (j < P.Kx) {
-                        // HarmonicEmbedding(append_input): [sin(d_i 2^f)] (i major, f minor), [cos(...)], d
-                        const int e = j - P.F, nh3 = 3 * P.n_harm;
-                        if (e < 2 * nh3) {
-                            const int q = e < nh3 ? e : e - nh3;
-                            const int comp = q / P.n_harm, f = q - comp * P.n_harm;
-                            const float d = comp == 0 ? dx : (comp == 1 ? dy : dz);
-                            const float a = d * (float)(1 << f);
-                            v = e < nh3 ? sinf(a) : cosf(a);
-                        } else {
-                            const int comp = e - 2 * nh3;
-                            v = comp == 0 ? dx : (comp == 1 ? dy : dz);
-                        }
-                    }
-                    v *= w;
-                    acc[r] += v * w;
-                    uint16_t h, l;
-                    holo_split1(v, P.pair_f16 != 0, h, l);
-                    P.x_hi[row + j] = h, P.x_lo[row + j] = l;
-                    if (P.x_f32 && j < P.Kx) P.x_f32[((size_t)s * P.n_pts + (size_t)p) * P.Kx + j] = v;
+            for (int g = 0; g < VP_GROUPS; ++g) {
+                if (grp[g].kind == 3) continue;
+                const int j0 = (g * 32 + lane) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grp[g].kind == 0) {
+                    v = sample_group(grp[g], s, x_ndc, y_ndc);
+                    v.x *= vw, v.y *= vw, v.z *= vw, v.w *= vw;
+                } else if (grp[g].kind == 1) {
+                    const int e = j0 - P.F;
+                    v.x = embed_column(e, P.n_harm, dx, dy, dz);
+                    v.y = e + 1 < P.E ? embed_column(e + 1, P.n_harm, dx, dy, dz) : 0.f;
+                    v.z = e + 2 < P.E ? embed_column(e + 2, P.n_harm, dx, dy, dz) : 0.f;
+                    v.w = e + 3 < P.E ? embed_column(e + 3, P.n_harm, dx, dy, dz) : 0.f;
+                }
+                v.x *= w, v.y *= w, v.z *= w, v.w *= w;
+                acc[g].x += v.x * w, acc[g].y += v.y * w, acc[g].z += v.z * w, acc[g].w += v.w * w;
+                store_pair4(P.x_hi, P.x_lo, row + j0, v, f16);
+                if (P.x_f32) {
+                    float* o = P.x_f32 + ((size_t)s * P.n_pts + (size_t)p) * P.Kx;
+                    if (j0 < P.Kx) o[j0] = v.x;
+                    if (j0 + 1 < P.Kx) o[j0 + 1] = v.y;
+                    if (j0 + 2 < P.Kx) o[j0 + 2] = v.z;
+                    if (j0 + 3 < P.Kx) o[j0 + 3] = v.w;
                 }
             }
             wsum += w;
         }
         const float invw = 1.f / fmaxf(wsum, 1e-2f);   // wmean(..., eps=1e-2)
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            const int j = r * 32 + lane;
-            if (j < P.Kpad) {
-                const float m = acc[r] * invw;
-                uint16_t h, l;
-                holo_split1(m, P.pair_f16 != 0, h, l);
-                P.m_hi[(size_t)p * P.Kpad + j] = h, P.m_lo[(size_t)p * P.Kpad + j] = l;
-                if (P.m_f32 && j < P.Kx) P.m_f32[(size_t)p * P.Kx + j] = m;
+        for (int g = 0; g < VP_GROUPS; ++g) {
+            if (grp[g].kind == 3) continue;
+            const int j0 = (g * 32 + lane) * 4;
+            const float4 m = make_float4(acc[g].x * invw, acc[g].y * invw, acc[g].z * invw, acc[g].w * invw);
+            store_pair4(P.m_hi, P.m_lo, (size_t)p * P.Kpad + j0, m, f16);
+            if (P.m_f32) {
+                float* o = P.m_f32 + (size_t)p * P.Kx;
+                if (j0 < P.Kx) o[j0] = m.x;
+                if (j0 + 1 < P.Kx) o[j0 + 1] = m.y;
+                if (j0 + 2 < P.Kx) o[j0 + 2] = m.z;
+                if (j0 + 3 < P.Kx) o[j0 + 3] = m.w;
             }
         }
     }
@@ -189,63 +256,71 @@ __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) 
 //   row layout [mu_k | std_k] per feature map k.  Two passes over the views (the second re-gathers: the maps are L2 resident).
 __global__ void __launch_bounds__(256) viewpool_angle_kernel(const VpParams P, float gamma, float min_weight, int with_std,
                                                              float* __restrict__ out_f32) {
+    extern __shared__ float cam[];
+    stage_cameras(P, cam);
     const int lane = threadIdx.x & 31;
+    const bool f16 = P.pair_f16 != 0;
+    const int per = with_std ? 2 : 1;
+    ColGroup grp[VP_GROUPS];
+    int col_mu[VP_GROUPS];
+#pragma unroll
+    for (int g = 0; g < VP_GROUPS; ++g) {
+        const int j0 = (g * 32 + lane) * 4;
+        grp[g] = make_group(P, j0, P.F);
+        VpMap m = P.maps[0];
+#pragma unroll
+        for (int k = 1; k < VP_MAX_MAPS; ++k)
+            if (k < P.n_maps && j0 >= P.maps[k].c0) m = P.maps[k];
+        col_mu[g] = per * m.c0 + (j0 - m.c0);
+    }
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    constexpr int ROUNDS = VP_MAX_K / 32;
-    const int per = with_std ? 2 : 1;
     for (long long p = warp0; p < P.n_pts; p += n_warps) {
         const float px = __ldg(P.pts + p * 3), py = __ldg(P.pts + p * 3 + 1), pz = __ldg(P.pts + p * 3 + 2);
-        float mu[ROUNDS], var[ROUNDS];
+        float4 mu[VP_GROUPS], var[VP_GROUPS];
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) mu[r] = 0.f, var[r] = 0.f;
+        for (int g = 0; g < VP_GROUPS; ++g) mu[g] = var[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         float wsum = 0.f, d0x = 0.f, d0y = 0.f, d0z = 0.f;
         for (int pass = 0; pass < per; ++pass) {
             for (int s = 0; s < P.n_src; ++s) {
                 float x_ndc, y_ndc, vw, w, dx, dy, dz;
-                view_geometry(P, s, px, py, pz, x_ndc, y_ndc, vw, w, dx, dy, dz);
+                view_geometry(P, cam + s * CAM_FLOATS, s, px, py, pz, x_ndc, y_ndc, vw, w, dx, dy, dz);
                 if (s == 0) d0x = dx, d0y = dy, d0z = dz;
                 const float a01 = 0.5f * (dx * d0x + dy * d0y + dz * d0z + 1.f);
                 w *= (gamma == 1.f ? a01 : powf(a01, gamma)) + min_weight;
                 if (pass == 0) wsum += w;
 #pragma unroll
-                for (int r = 0; r < ROUNDS; ++r) {
-                    const int j = r * 32 + lane;
-                    if (j < P.F) {
-                        const float v = sample_column(P, s, j, x_ndc, y_ndc) * vw;
-                        if (pass == 0) mu[r] += v * w;
-                        else var[r] += (v - mu[r]) * (v - mu[r]) * w;
+                for (int g = 0; g < VP_GROUPS; ++g) {
+                    if (grp[g].kind != 0) continue;
+                    float4 v = sample_group(grp[g], s, x_ndc, y_ndc);
+                    v.x *= vw, v.y *= vw, v.z *= vw, v.w *= vw;
+                    if (pass == 0) {
+                        mu[g].x += v.x * w, mu[g].y += v.y * w, mu[g].z += v.z * w, mu[g].w += v.w * w;
+                    } else {
+                        const float ex = v.x - mu[g].x, ey = v.y - mu[g].y, ez = v.z - mu[g].z, ew = v.w - mu[g].w;
+                        var[g].x += ex * ex * w, var[g].y += ey * ey * w, var[g].z += ez * ez * w, var[g].w += ew * ew * w;
                     }
                 }
             }
             if (pass == 0) {
                 const float invw = 1.f / fmaxf(wsum, 1e-2f);
 #pragma unroll
-                for (int r = 0; r < ROUNDS; ++r) mu[r] *= invw;
+                for (int g = 0; g < VP_GROUPS; ++g) mu[g].x *= invw, mu[g].y *= invw, mu[g].z *= invw, mu[g].w *= invw;
             }
         }
         const float invw = 1.f / fmaxf(wsum, 1e-2f);
         // zero the padding columns, then scatter [mu_k | std_k]
         for (int j = per * P.F + lane; j < P.Kpad; j += 32) P.m_hi[(size_t)p * P.Kpad + j] = 0, P.m_lo[(size_t)p * P.Kpad + j] = 0;
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            const int j = r * 32 + lane;
-            if (j < P.F) {
-                VpMap m = P.maps[0];
-#pragma unroll
-                for (int k = 1; k < VP_MAX_MAPS; ++k)
-                    if (k < P.n_maps && j >= P.maps[k].c0) m = P.maps[k];
-                const int col_mu = per * m.c0 + (j - m.c0), col_sd = col_mu + m.C;
-                uint16_t h, l;
-                holo_split1(mu[r], P.pair_f16 != 0, h, l);
-                P.m_hi[(size_t)p * P.Kpad + col_mu] = h, P.m_lo[(size_t)p * P.Kpad + col_mu] = l;
-                if (out_f32) out_f32[(size_t)p * per * P.F + col_mu] = mu[r];
-                if (with_std) {
-                    const float sd = sqrtf(fmaxf(var[r] * invw, 1e-4f));
-                    holo_split1(sd, P.pair_f16 != 0, h, l);
-                    P.m_hi[(size_t)p * P.Kpad + col_sd] = h, P.m_lo[(size_t)p * P.Kpad + col_sd] = l;
-                    if (out_f32) out_f32[(size_t)p * per * P.F + col_sd] = sd;
-                }
+        for (int g = 0; g < VP_GROUPS; ++g) {
+            if (grp[g].kind != 0) continue;
+            store_pair4(P.m_hi, P.m_lo, (size_t)p * P.Kpad + col_mu[g], mu[g], f16);
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)p * per * P.F + col_mu[g]) = mu[g];
+            if (with_std) {
+                const float4 sd = make_float4(sqrtf(fmaxf(var[g].x * invw, 1e-4f)), sqrtf(fmaxf(var[g].y * invw, 1e-4f)),
+                                              sqrtf(fmaxf(var[g].z * invw, 1e-4f)), sqrtf(fmaxf(var[g].w * invw, 1e-4f)));
+                store_pair4(P.m_hi, P.m_lo, (size_t)p * P.Kpad + col_mu[g] + grp[g].C, sd, f16);
+                if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)p * per * P.F + col_mu[g] + grp[g].C) = sd;
             }
         }
     }
@@ -327,8 +402,8 @@ static int fill_params(const char* who, VpParams& P, const float* pts, long long
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
     }
-    if (!(n_pts > 0 && n_src > 0 && n_maps > 0 && n_maps <= VP_MAX_MAPS) || (mask_map && (Hm <= 0 || Wm <= 0))) {
-        holo_set_error("%s: n_pts=%lld n_src=%d n_maps=%d (1..%d), mask map %dx%d", who, n_pts, n_src, n_maps, VP_MAX_MAPS, Hm, Wm);
+    if (!(n_pts > 0 && n_src > 0 && n_src <= 512 && n_maps > 0 && n_maps <= VP_MAX_MAPS) || (mask_map && (Hm <= 0 || Wm <= 0))) {
+        holo_set_error("%s: n_pts=%lld n_src=%d (1..512) n_maps=%d (1..%d), mask map %dx%d", who, n_pts, n_src, n_maps, VP_MAX_MAPS, Hm, Wm);
         return HOLO_ERR_ARG;
     }
     P.pts = pts, P.n_pts = n_pts, P.R = R, P.T = T, P.focal = focal, P.pp = pp, P.n_src = n_src;
@@ -337,6 +412,11 @@ static int fill_params(const char* who, VpParams& P, const float* pts, long long
         if (!(maps[k].data && maps[k].channels > 0 && maps[k].height > 0 && maps[k].width > 0)) {
             holo_set_error("%s: feature map %d is empty", who, k);
             return HOLO_ERR_ARG;
+        }
+        if (maps[k].channels % 4 || ((uintptr_t)maps[k].data & 15)) {
+            holo_set_error("%s: feature map %d has %d channels: pad to a multiple of 4 (zero channels) and align to 16 "
+                           "bytes -- a lane reads the 4 channels of its column group as one float4", who, k, maps[k].channels);
+            return HOLO_ERR_UNSUPPORTED;
         }
         P.maps[k].data = maps[k].data, P.maps[k].C = maps[k].channels, P.maps[k].H = maps[k].height;
         P.maps[k].W = maps[k].width, P.maps[k].c0 = c0;
@@ -373,7 +453,7 @@ extern "C" int holo_viewpool_sample(const float* pts, long long n_pts, const flo
     P.x_f32 = x_f32, P.m_f32 = mean_f32, P.pair_f16 = pair_f16;
     long long blocks = (n_pts + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    viewpool_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P);
+    viewpool_sample_kernel<<<(unsigned)blocks, 256, (size_t)n_src * CAM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(P);
     HOLO_CHECK_LAUNCH("holo_viewpool_sample");
     return HOLO_OK;
 }
@@ -397,8 +477,8 @@ extern "C" int holo_viewpool_angle_reduce(const float* pts, long long n_pts, con
     P.Kpad = Kpad, P.m_hi = (uint16_t*)out_hi, P.m_lo = (uint16_t*)out_lo, P.pair_f16 = pair_f16;
     long long blocks = (n_pts + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    viewpool_angle_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, gamma, min_ray_angle_weight, with_std ? 1 : 0,
-                                                                              out_f32);
+    viewpool_angle_kernel<<<(unsigned)blocks, 256, (size_t)n_src * CAM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(
+        P, gamma, min_ray_angle_weight, with_std ? 1 : 0, out_f32);
     HOLO_CHECK_LAUNCH("holo_viewpool_angle_reduce");
     return HOLO_OK;
 }

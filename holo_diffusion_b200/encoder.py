@@ -176,7 +176,15 @@ def _param_key(mods: Sequence[Optional[nn.Module]], extra) -> tuple:
     return (tuple((-1, id(p)) if isinstance(p, lazy) else (p._version, p.data_ptr()) for p in ps), extra)
 
 
-def _build_mlp_mean_plan(agg, mapper: Optional[nn.Linear], Kx: int, Kpad: int, pair_dtype, device) -> dict:
+def _scatter_cols(w: torch.Tensor, cols: torch.Tensor, k: int) -> torch.Tensor:
+    """(N, len(cols)) weights -> (N, k) with the columns moved to `cols` and zeros elsewhere."""
+    out = torch.zeros(w.shape[0], k, device=w.device, dtype=w.dtype)
+    out[:, cols.to(w.device)] = w
+    return out
+
+
+def _build_mlp_mean_plan(agg, mapper: Optional[nn.Linear], Kx: int, cols: torch.Tensor, Kx_pad: int, Kpad: int, pair_dtype,
+                         device) -> dict:
     _materialize(agg._first_sampled, Kx, device)
     _materialize(agg._first_mean, Kx, device)
     layers = [seq[0] for seq in agg._mlp.mlp]
@@ -184,8 +192,8 @@ def _build_mlp_mean_plan(agg, mapper: Optional[nn.Linear], Kx: int, Kpad: int, p
     w0, b0 = layers[0].weight.detach().to(d), layers[0].bias.detach().to(d)
     # mlp_in = first_sampled(x) + first_mean(mean) feeds the MLP's first Linear directly (custom_modules.py:263-264 with
     # MLPWithInputSkips.forward :133-160): the three Linear layers fold into two matrices and one bias (fp64 products)
-    A = w0 @ agg._first_sampled.weight.detach().to(d)
-    Bm = w0 @ agg._first_mean.weight.detach().to(d)
+    A = _scatter_cols(w0 @ agg._first_sampled.weight.detach().to(d), cols, Kx_pad)
+    Bm = _scatter_cols(w0 @ agg._first_mean.weight.detach().to(d), cols, Kx_pad)
     bias0 = w0 @ (agg._first_sampled.bias.detach().to(d) + agg._first_mean.bias.detach().to(d)) + b0
     H = _ceil(A.shape[0], 64)
     plan = {"first": _Gemm(A, None, Kpad, pair_dtype), "mean": _Gemm(Bm, bias0, Kpad, pair_dtype), "hidden": [], "acts": []}
@@ -276,8 +284,18 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
     pts = pts.contiguous().float()
     P = pts.shape[0]
     n_src = camera.R.shape[0]
-    maps = [f.detach().float().permute(0, 2, 3, 1).contiguous() for f in feats.values()]   # channels-last: 64-byte taps
-    F_ = sum(m.shape[3] for m in maps)
+    # channels-last maps (a tap = contiguous channels), every map zero-padded to a multiple of 4 channels: a lane of the
+    # gather kernels owns 4 columns of ONE map and reads a tap as one float4.  `cols`: where the reference's columns sit
+    # in the padded row -- the weight matrices get zero columns at the padding, nothing else changes.
+    maps, chans, starts = [], [], []
+    for f in feats.values():
+        m = f.detach().float().permute(0, 2, 3, 1)
+        c = m.shape[3]
+        starts.append(sum(mm.shape[3] for mm in maps))
+        chans.append(c)
+        maps.append((nn.functional.pad(m, (0, _ceil(c, 4) - c)) if c % 4 else m).contiguous())
+    F_ = sum(chans)
+    F_pad = sum(m.shape[3] for m in maps)
     mask_map = None
     if getattr(pooler.view_sampler, "masked_sampling", False):
         if masks is None:
@@ -290,27 +308,35 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
         raise NotImplementedError(f"feature aggregator {kind} is not built")
     if mlp_mean:
         n_harm = agg.n_harmonic_functions_ray
-        Kx = F_ + 3 * (2 * n_harm + 1)
+        E = 3 * (2 * n_harm + 1)
+        Kx, Kx_pad = F_ + E, F_pad + E
+        cols = [st + c for st, ch in zip(starts, chans) for c in range(ch)] + [F_pad + e for e in range(E)]
     else:
         red = _reductions(agg)
         if red not in (("AVG",), ("AVG", "STD")):
             raise NotImplementedError(f"reduction functions {red}: AVG and AVG+STD are built")
-        Kx = F_ * len(red)
-    Kpad = _ceil(Kx, 64)
+        per = len(red)
+        Kx, Kx_pad = F_ * per, F_pad * per
+        # pooled row of the reference: [mu_k | std_k] per feature; padded: the same with C_k rounded up
+        cols = [per * st + r * maps[k].shape[3] + c for k, (st, ch) in enumerate(zip(starts, chans)) for r in range(per)
+                for c in range(ch)]
+    cols_t = torch.tensor(cols, device=dev, dtype=torch.long)
+    Kpad = _ceil(Kx_pad, 64)
     if Kpad > 256:
-        raise NotImplementedError(f"{Kx} pooled columns: the kernels hold rows of up to 256")
+        raise NotImplementedError(f"{Kx_pad} pooled columns: the kernels hold rows of up to 256")
     plans = pooler.__dict__.setdefault("_holo_plans", {})
-    key = _param_key([agg, mapper], (Kx, pair_dtype, str(dev)))
+    extra = (tuple(cols), pair_dtype, str(dev))
+    key = _param_key([agg, mapper], extra)
     plan = plans.get("plan")
     if plan is None or plan["key"] != key:
         if mlp_mean:
-            plan = _build_mlp_mean_plan(agg, mapper, Kx, Kpad, pair_dtype, dev)
+            plan = _build_mlp_mean_plan(agg, mapper, Kx, cols_t, Kx_pad, Kpad, pair_dtype, dev)
         else:
             if mapper is not None:
                 _materialize(mapper, Kx, dev)
-            plan = {"mapper": None if mapper is None else _Gemm(mapper.weight.detach(), mapper.bias.detach(), Kpad,
-                                                                pair_dtype, n_mult=16), "D": Kx}
-        plan["key"] = _param_key([agg, mapper], (Kx, pair_dtype, str(dev)))   # lazy layers materialised: new pointers
+            plan = {"mapper": None if mapper is None else _Gemm(_scatter_cols(mapper.weight.detach(), cols_t, Kx_pad),
+                                                                mapper.bias.detach(), Kpad, pair_dtype, n_mult=16), "D": Kx}
+        plan["key"] = _param_key([agg, mapper], extra)   # lazy layers materialised: new pointers
         plans["plan"] = plan
     mp = plan["mapper"]
     n_out = plan["D"] if mp is None else mp.n
@@ -332,14 +358,14 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
         pooled = torch.empty(chunk, Dp, device=dev) if (mp is None or debug is not None) else None
     else:
         g_hi, g_lo = e16(chunk, Kpad)
-        pooled = torch.empty(chunk, Kx, device=dev) if (mp is None or debug is not None) else None
+        pooled = torch.empty(chunk, Kx_pad, device=dev) if (mp is None or debug is not None) else None
     for c0 in range(0, P, chunk):
         n = min(chunk, P - c0)
         pc = pts[c0:c0 + n]
         if mlp_mean:
             dbg_x = dbg_m = None
             if debug is not None and c0 == 0:
-                dbg_x, dbg_m = torch.empty(n_src, n, Kx, device=dev), torch.empty(n, Kx, device=dev)
+                dbg_x, dbg_m = torch.empty(n_src, n, Kx_pad, device=dev), torch.empty(n, Kx_pad, device=dev)
             ops.viewpool_sample(pc, *cam, maps, n_harm, Kpad, chunk, x_hi, x_lo, m_hi, m_lo, mask_map=mask_map,
                                 view_weight=view_weight, x_f32=dbg_x, mean_f32=dbg_m)
             rows = n_src * chunk
@@ -349,7 +375,8 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
             hh, hl = h_hi.view(-1)[: rows * Hp].view(rows, Hp), h_lo.view(-1)[: rows * Hp].view(rows, Hp)
             ops.viewpool_act_split(y0, mterm, n_src, chunk, Hp, plan["acts"][0], hh, hl)
             if debug is not None and c0 == 0:
-                debug.update(x=dbg_x, mean=dbg_m, y0=y0[:, : plan["first"].n].clone(), mterm=mterm[:, : plan["first"].n].clone())
+                debug.update(x=dbg_x[..., cols_t], mean=dbg_m[..., cols_t], y0=y0[:, : plan["first"].n].clone(),
+                             mterm=mterm[:, : plan["first"].n].clone())
             for li, g in enumerate(plan["hidden"]):
                 yi = y.view(-1)[: rows * g.n_pad].view(rows, g.n_pad)
                 g(hh, hl, rows, yi)
@@ -366,9 +393,9 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
                                       min_ray_angle_weight=float(agg.min_ray_angle_weight), with_std=len(red) == 2,
                                       out_f32=None if pooled is None else pooled[:n])
             if debug is not None and c0 == 0:
-                debug.update(pooled=pooled[:n].clone())
+                debug.update(pooled=pooled[:n][:, cols_t])
         if mp is None:
-            rows_out[c0:c0 + n, : plan["D"]] = pooled[:n, : plan["D"]]
+            rows_out[c0:c0 + n, : plan["D"]] = pooled[:n, : plan["D"]] if mlp_mean else pooled[:n][:, cols_t]
         else:
             mp(g_hi, g_lo, chunk, rows_out[c0:c0 + chunk])
     if direct:

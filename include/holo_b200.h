@@ -401,7 +401,9 @@ typedef struct holo_feature_map {
  * custom_modules.py:241-260,283-334.  Rows: X[(s * rows_per_view + p) * Kpad + j] as a 16-bit hi/lo pair (pair_f16 as
  * for holo_conv3d_tc), columns [features of map 0 | map 1 | ... | sin | cos | dir | zero padding to Kpad];
  * mean[p * Kpad + j] = sum_s X w / max(sum_s w, 1e-2) (wmean of _avgmaxstd_reduction_function, AVG).
- * x_f32 (n_src, n_pts, F + E) / mean_f32 (n_pts, F + E): optional fp32 copies.  maps: HOST array. Kpad <= 256. */
+ * x_f32 (n_src, n_pts, F + E) / mean_f32 (n_pts, F + E): optional fp32 copies.  maps: HOST array. Kpad <= 256.
+ * Every map's channel count must be a multiple of 4 (pad with zero channels; data 16-byte aligned): one lane owns four
+ * consecutive columns of one map and reads each bilinear tap as a float4. */
 int holo_viewpool_sample(const float* pts, long long n_pts, const float* R, const float* T, const float* focal,
                          const float* pp, int n_src, const holo_feature_map* maps, int n_maps, const float* mask_map,
                          int Hm, int Wm, const float* view_weight, int n_harmonic, float eps, int Kpad,

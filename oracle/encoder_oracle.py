@@ -69,12 +69,12 @@ def sample_views(cams: ro.OracleCameras, pts: torch.Tensor, feats: Dict[str, tor
     view_weight (n_cam) is the camera_pts_mask (sequence id of the camera == sequence id of the points)."""
     xy = project_ndc(cams, pts, eps)
     n = xy.shape[0]
-    vw = torch.ones(n, dtype=pts.dtype) if view_weight is None else view_weight.to(pts.dtype)
+    vw = torch.ones(n, dtype=pts.dtype, device=pts.device) if view_weight is None else view_weight.to(pts)
     out = {k: ndc_grid_sample(f, xy, sampling_mode).permute(0, 2, 1)[None] * vw[None, :, None, None] for k, f in feats.items()}
     if masked_sampling:
         m = ndc_grid_sample(masks, xy, "nearest").permute(0, 2, 1)[None]
     else:
-        m = torch.ones(1, n, pts.shape[0], 1, dtype=pts.dtype)
+        m = torch.ones(1, n, pts.shape[0], 1, dtype=pts.dtype, device=pts.device)
     return out, m * vw[None, :, None, None]
 
 
