@@ -159,17 +159,35 @@ __device__ __forceinline__ float4 sample_group(const ColGroup& g, int s, float x
     return v;
 }
 
-// HarmonicEmbedding(append_input): [sin(d_i 2^f)] (i major, f minor), [cos(...)], d ; e = column within the embedding
-__device__ __forceinline__ float embed_column(int e, int n_harm, float dx, float dy, float dz) {
+// HarmonicEmbedding(append_input): [sin(d_i 2^f)] (i major, f minor), [cos(...)], d.  Column e of the embedding is
+// decoded ONCE per thread (EmbSlot); in the view loop lane e evaluates its own column and the lanes that own embedding
+// column groups collect their four values with shuffles -- one sinf/cosf per lane instead of four on six lanes.
+struct EmbSlot {
+    int comp;      // 0..2: component of the direction; -1: no column
+    int fn;        // 0 sin, 1 cos, 2 identity
+    float scale;   // 2^f
+};
+
+__device__ __forceinline__ EmbSlot make_emb_slot(int e, int n_harm, int E) {
+    EmbSlot t;
+    t.comp = -1, t.fn = 2, t.scale = 1.f;
+    if (e >= E) return t;
     const int nh3 = 3 * n_harm;
     if (e < 2 * nh3) {
         const int q = e < nh3 ? e : e - nh3;
-        const int comp = q / n_harm, f = q - comp * n_harm;
-        const float a = (comp == 0 ? dx : (comp == 1 ? dy : dz)) * (float)(1 << f);
-        return e < nh3 ? sinf(a) : cosf(a);
+        t.comp = q / n_harm;
+        t.scale = (float)(1 << (q - t.comp * n_harm));
+        t.fn = e < nh3 ? 0 : 1;
+    } else {
+        t.comp = e - 2 * nh3;
     }
-    const int comp = e - 2 * nh3;
-    return comp == 0 ? dx : (comp == 1 ? dy : (comp == 2 ? dz : 0.f));
+    return t;
+}
+
+__device__ __forceinline__ float eval_emb(const EmbSlot& t, float dx, float dy, float dz) {
+    if (t.comp < 0) return 0.f;
+    const float a = (t.comp == 0 ? dx : (t.comp == 1 ? dy : dz)) * t.scale;
+    return t.fn == 0 ? sinf(a) : (t.fn == 1 ? cosf(a) : a);
 }
 
 __device__ __forceinline__ void store_pair4(uint16_t* hi, uint16_t* lo, size_t at, float4 v, bool f16) {
@@ -180,10 +198,11 @@ __device__ __forceinline__ void store_pair4(uint16_t* hi, uint16_t* lo, size_t a
     *reinterpret_cast<uint2*>(lo + at) = l;
 }
 
-constexpr int VP_GROUPS = VP_MAX_K / 128;   // 4-column groups per lane
+constexpr int VP_GROUPS = VP_MAX_K / 128;   // 4-column groups per lane (template parameter of the kernels: 1 for rows <= 128)
 
 // One warp per point; every lane owns up to two 4-column groups of the row; the view loop is inside (the mean needs
 // all views).  Rows: [features of map 0 | map 1 | ... | sin | cos | dir | zero padding to Kpad].
+template <int VP_GROUPS>
 __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) {
     extern __shared__ float cam[];
     stage_cameras(P, cam);
@@ -192,6 +211,8 @@ __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) 
     ColGroup grp[VP_GROUPS];
 #pragma unroll
     for (int g = 0; g < VP_GROUPS; ++g) grp[g] = make_group(P, (g * 32 + lane) * 4, P.Kpad);
+    const EmbSlot slot0 = make_emb_slot(lane, P.n_harm, P.E), slot1 = make_emb_slot(32 + lane, P.n_harm, P.E);
+    const bool two_slots = P.E > 32;   // E = 3 (2 n + 1) <= 64 (host check)
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long p = warp0; p < P.n_pts; p += n_warps) {
@@ -204,20 +225,27 @@ __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) 
             float x_ndc, y_ndc, vw, w, dx, dy, dz;
             view_geometry(P, cam + s * CAM_FLOATS, s, px, py, pz, x_ndc, y_ndc, vw, w, dx, dy, dz);
             const size_t row = ((size_t)s * P.rows_per_view + (size_t)p) * P.Kpad;
+            const float ev0 = eval_emb(slot0, dx, dy, dz), ev1 = two_slots ? eval_emb(slot1, dx, dy, dz) : 0.f;
 #pragma unroll
             for (int g = 0; g < VP_GROUPS; ++g) {
-                if (grp[g].kind == 3) continue;
                 const int j0 = (g * 32 + lane) * 4;
+                // every lane takes part in the shuffles; lanes without an embedding group read column 0
+                const int e = grp[g].kind == 1 ? j0 - P.F : 0;
+                float em[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ei = e + i;
+                    const float a = __shfl_sync(0xffffffffu, ev0, ei & 31);
+                    const float b = two_slots ? __shfl_sync(0xffffffffu, ev1, ei & 31) : 0.f;
+                    em[i] = ei < P.E ? (ei < 32 ? a : b) : 0.f;
+                }
+                if (grp[g].kind == 3) continue;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (grp[g].kind == 0) {
                     v = sample_group(grp[g], s, x_ndc, y_ndc);
                     v.x *= vw, v.y *= vw, v.z *= vw, v.w *= vw;
                 } else if (grp[g].kind == 1) {
-                    const int e = j0 - P.F;
-                    v.x = embed_column(e, P.n_harm, dx, dy, dz);
-                    v.y = e + 1 < P.E ? embed_column(e + 1, P.n_harm, dx, dy, dz) : 0.f;
-                    v.z = e + 2 < P.E ? embed_column(e + 2, P.n_harm, dx, dy, dz) : 0.f;
-                    v.w = e + 3 < P.E ? embed_column(e + 3, P.n_harm, dx, dy, dz) : 0.f;
+                    v = make_float4(em[0], em[1], em[2], em[3]);
                 }
                 v.x *= w, v.y *= w, v.z *= w, v.w *= w;
                 acc[g].x += v.x * w, acc[g].y += v.y * w, acc[g].z += v.z * w, acc[g].w += v.w * w;
@@ -254,6 +282,7 @@ __global__ void __launch_bounds__(256) viewpool_sample_kernel(const VpParams P) 
 //   w[s] = mask[s] * ((0.5 (d_s . d_0 + 1))^gamma + min_weight),  d_s = unit vector camera s -> point (camera 0 = the
 //   first camera of the point batch), mu = sum w x / max(sum w, 1e-2), std = sqrt(max(sum w (x - mu)^2 / max(sum w, 1e-2), 1e-4));
 //   row layout [mu_k | std_k] per feature map k.  Two passes over the views (the second re-gathers: the maps are L2 resident).
+template <int VP_GROUPS>
 __global__ void __launch_bounds__(256) viewpool_angle_kernel(const VpParams P, float gamma, float min_weight, int with_std,
                                                              float* __restrict__ out_f32) {
     extern __shared__ float cam[];
@@ -436,7 +465,8 @@ extern "C" int holo_viewpool_sample(const float* pts, long long n_pts, const flo
                                     float eps, int Kpad, long long rows_per_view, void* x_hi, void* x_lo, void* mean_hi,
                                     void* mean_lo, float* x_f32, float* mean_f32, int pair_f16, void* stream) {
     HOLO_CHECK_ARG(x_hi && x_lo && mean_hi && mean_lo, "holo_viewpool_sample: null output");
-    HOLO_CHECK_ARG(n_harmonic >= 0 && n_harmonic <= 16, "holo_viewpool_sample: n_harmonic=%d", n_harmonic);
+    HOLO_CHECK_ARG(n_harmonic >= 0 && n_harmonic <= 10, "holo_viewpool_sample: n_harmonic=%d (0..10: 3 (2 n + 1) <= 64 columns)",
+                   n_harmonic);
     HOLO_CHECK_ARG(rows_per_view >= n_pts, "holo_viewpool_sample: rows_per_view %lld < n_pts %lld", rows_per_view, n_pts);
     VpParams P;
     const int rc = fill_params("holo_viewpool_sample", P, pts, n_pts, R, T, focal, pp, n_src, maps, n_maps, mask_map, Hm, Wm,
@@ -453,7 +483,9 @@ extern "C" int holo_viewpool_sample(const float* pts, long long n_pts, const flo
     P.x_f32 = x_f32, P.m_f32 = mean_f32, P.pair_f16 = pair_f16;
     long long blocks = (n_pts + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    viewpool_sample_kernel<<<(unsigned)blocks, 256, (size_t)n_src * CAM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(P);
+    const size_t smem = (size_t)n_src * CAM_FLOATS * sizeof(float);
+    if (Kpad <= 128) viewpool_sample_kernel<1><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(P);
+    else viewpool_sample_kernel<2><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(P);
     HOLO_CHECK_LAUNCH("holo_viewpool_sample");
     return HOLO_OK;
 }
@@ -477,8 +509,13 @@ extern "C" int holo_viewpool_angle_reduce(const float* pts, long long n_pts, con
     P.Kpad = Kpad, P.m_hi = (uint16_t*)out_hi, P.m_lo = (uint16_t*)out_lo, P.pair_f16 = pair_f16;
     long long blocks = (n_pts + 7) / 8;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    viewpool_angle_kernel<<<(unsigned)blocks, 256, (size_t)n_src * CAM_FLOATS * sizeof(float), (cudaStream_t)stream>>>(
-        P, gamma, min_ray_angle_weight, with_std ? 1 : 0, out_f32);
+    const size_t smem = (size_t)n_src * CAM_FLOATS * sizeof(float);
+    if (P.F <= 128)
+        viewpool_angle_kernel<1><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(P, gamma, min_ray_angle_weight,
+                                                                                         with_std ? 1 : 0, out_f32);
+    else
+        viewpool_angle_kernel<2><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(P, gamma, min_ray_angle_weight,
+                                                                                         with_std ? 1 : 0, out_f32);
     HOLO_CHECK_LAUNCH("holo_viewpool_angle_reduce");
     return HOLO_OK;
 }
