@@ -5,7 +5,12 @@ voxel_features=...)`` -> images from preds -> videos), with the per-view post-pr
 (``holo_depth_image`` / ``holo_shade_depth`` / ``holo_frame_u8``) and ONE device-to-host copy of all 8-bit frames per
 key at the end instead of a blocking ``.cpu()`` per key per view.
 
-Reconstruction mode (sample_mode=False) needs the dataset and the view-pooling encoder: a "next" row.
+Reconstruction mode (``sample_mode=False``, flyaround.py:148-171): the sequence's frames come from `dataset`
+(``sequence_indices_in_order`` + ``__getitem__``; collated with the frame type's own ``collate`` when it has one), the
+source views are drawn with the reference's seeded ``randperm``, and the voxel grid comes from the view-pooling encoder
+(``holo_diffusion_b200/encoder.py``).  The reference re-encodes the SAME source views for every pose of the trajectory
+(only camera 0, the target, changes and it is not a source); here the grid is encoded once and passed to the remaining
+poses as ``voxel_features`` -- same images, one encoder pass per fly-around instead of one per frame.
 """
 from __future__ import annotations
 
@@ -70,6 +75,40 @@ def _get_dummy_test_batch_for_sampling(batch_size: int, device=torch.device("cpu
     return FrameData(camera=cam.to(device))
 
 
+def _collate_frames(frames: Sequence[Any]) -> Any:
+    """FrameData.collate for a list of single frames (flyaround.py:386-396 goes through a DataLoader for it)."""
+    collate = getattr(type(frames[0]), "collate", None)
+    if collate is not None:
+        return collate(list(frames))
+    out = FrameData()
+    for k in out.keys():
+        vals = [getattr(f, k, None) for f in frames]
+        if all(v is None for v in vals):
+            continue
+        if k == "camera":
+            cat = lambda a: torch.cat([getattr(c, a) for c in vals], 0)   # noqa: E731  (one camera per frame, batch dim 1)
+            out.camera = PerspectiveCameras(cat("focal_length"), cat("principal_point"), cat("R"), cat("T"))
+        elif torch.is_tensor(vals[0]):
+            setattr(out, k, torch.stack(vals, 0))
+        else:
+            setattr(out, k, list(vals))
+    return out
+
+
+def _stack_images(ims: torch.Tensor, size: Optional[Tuple[int, int]]) -> torch.Tensor:
+    """flyaround.py:485-503: the source views tiled into a ceil(sqrt(n))^2 mosaic."""
+    ba = ims.shape[0]
+    H = W = int(np.ceil(np.sqrt(ba)))
+    n_add = H * W - ba
+    if n_add > 0:
+        ims = torch.cat((ims, torch.zeros_like(ims[:1]).repeat(n_add, 1, 1, 1)))
+    ims = ims.view(H, W, *ims.shape[1:])
+    cated = torch.cat([torch.cat(list(row), dim=2) for row in ims], dim=1)
+    if size is not None:
+        cated = torch.nn.functional.interpolate(cated[None], size=size, mode="bilinear")[0]
+    return cated.clamp(0.0, 1.0)
+
+
 def _images_from_preds(preds: Dict[str, Any], extract_keys: Sequence[str] = (
         "image_rgb", "images_render", "fg_probability", "masks_render", "depths_render", "depth_map",
         "_all_source_images")) -> Dict[str, torch.Tensor]:
@@ -77,7 +116,10 @@ def _images_from_preds(preds: Dict[str, Any], extract_keys: Sequence[str] = (
     imout: Dict[str, torch.Tensor] = {}
     for k in extract_keys:
         if k == "_all_source_images":
-            continue   # sampling mode has no source images (image_rgb is None)
+            if preds.get("image_rgb") is None:
+                continue   # sampling mode has no source images
+            imout[k] = _stack_images(preds["image_rgb"][1:].detach(), None)[None]
+            continue
         if k == "_shaded_depth_render" and ("normals_render" in preds or "depths_render" in preds):
             d, m = preds["depths_render"][0, 0].contiguous(), preds["masks_render"][0, 0].contiguous()
             cam = preds["camera"]
@@ -157,21 +199,33 @@ def render_flyaround(dataset, sequence_name: str, model: torch.nn.Module, output
                      visualize_preds_keys: Sequence[str] = ("images_render", "masks_render", "depths_render",
                                                             "_all_source_images"),
                      save_voxel_features: bool = False):
-    if not sample_mode:
-        raise NotImplementedError("reconstruction fly-arounds need the dataset and the view-pooling encoder (SURVEY 8f)")
     if visdom_show_preds:
         raise NotImplementedError("visdom output is not part of the built path")
-    batch = _get_dummy_test_batch_for_sampling(n_source_views + 1, device="cpu")
+    if seed is None:
+        seed = hash(sequence_name)
+    if sample_mode:
+        batch = _get_dummy_test_batch_for_sampling(n_source_views + 1, device="cpu")
+    else:   # reconstruction mode (flyaround.py:152-171)
+        logger.info(f"Loading all data of sequence '{sequence_name}'.")
+        seq_idx = list(dataset.sequence_indices_in_order(sequence_name))
+        with torch.random.fork_rng():   # sample the source views reproducibly
+            torch.manual_seed(seed)
+            source_views_i = torch.randperm(len(seq_idx))[:n_source_views]
+        # the first, dummy view gets replaced with the target camera
+        source_views_i = torch.nn.functional.pad(source_views_i, [1, 0])
+        batch = _collate_frames([dataset[seq_idx[i]] for i in source_views_i.tolist()])
+        assert all(batch.sequence_name[0] == sn for sn in batch.sequence_name)
     if trajectory_type.lower() != "simple_360":
-        raise NotImplementedError("sampling mode has no training cameras to fit a trajectory to: use 'simple_360' "
-                                  "(generate_samples.py:46)")
+        raise NotImplementedError("trajectories fitted to the training cameras (pytorch3d generate_eval_video_cameras) "
+                                  "are not built: use 'simple_360' (generate_samples.py:46)")
     test_cameras = get_simple_360_camera_trajectory(max_angle, n_flyaround_poses, camera_elevation,
                                                     hemispherical_radius, up, camera_focal_length)
     EvaluationMode = _b200.EvaluationMode
     voxel_features = None
-    if progressive_sampling_steps_per_render <= 0:
+    if sample_mode and progressive_sampling_steps_per_render <= 0:
         voxel_features = model.sample_random_voxel_features()
     gen = model.sample_random_voxel_features_progressive() if progressive_sampling_steps_per_render > 0 else None
+    encoded = None   # reconstruction: the grid of the (pose-independent) source views, encoded once
     preds_total = []
     for n in range(n_flyaround_poses):
         for k in ("R", "T", "focal_length", "principal_point"):   # the first batch camera becomes the target camera
@@ -184,8 +238,18 @@ def render_flyaround(dataset, sequence_name: str, model: torch.nn.Module, output
                         voxel_features = next(gen)
                     except StopIteration:
                         break
-            preds = model(**{**{k: net_input[k] for k in net_input.keys()}, "evaluation_mode": EvaluationMode.EVALUATION,
-                             "voxel_features": voxel_features})
+            kw = {k: net_input[k] for k in net_input.keys()}
+            kw.update(evaluation_mode=EvaluationMode.EVALUATION, voxel_features=voxel_features)
+            if voxel_features is None and kw.get("image_rgb") is not None:
+                impl = _b200.renderer.impl_of(model)
+                names = kw.get("sequence_name")
+                pose_free = names is not None and sum(1 for s_ in names if s_ == names[0]) > 1   # view 0 is not a source
+                if encoded is None or not pose_free:
+                    encoded = impl.encode_views(image_rgb=kw["image_rgb"], camera=kw["camera"],
+                                                fg_probability=kw.get("fg_probability"), mask_crop=kw.get("mask_crop"),
+                                                sequence_name=names)
+                kw.update(image_rgb=None, voxel_features=encoded)
+            preds = model(**kw)
             assert all(k not in preds for k in net_input.keys())
             preds.update({k: net_input[k] for k in net_input.keys()})
             preds["_camera_intrinsics_host"] = (test_cameras[n].focal_length[0].tolist(),

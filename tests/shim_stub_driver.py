@@ -112,6 +112,50 @@ with tempfile.TemporaryDirectory() as tmp:
         m3._impl.use_cuda_graph = False
     res["encoder_ckpt_roundtrip"] = float((m3(**views)["images_render"] - pe["images_render"]).abs().max())
 
+# ---- reconstruction fly-around (flyaround.py:148-171): frames from a dataset, seeded source views, encoder, renders
+class _Frame:
+    def __init__(self, i):
+        g = torch.Generator().manual_seed(100 + i)
+        self.image_rgb, self.fg_probability = torch.rand(3, 32, 32, generator=g), torch.rand(1, 32, 32, generator=g)
+        self.mask_crop, self.depth_map = torch.ones(1, 32, 32), None
+        self.camera, self.sequence_name, self.frame_number = cams[[i % 4]], "seq", i
+        self.sequence_category = self.frame_timestamp = None
+
+
+class _Dataset:
+    def sequence_indices_in_order(self, name):
+        return iter(range(6))
+
+    def __getitem__(self, i):
+        return _Frame(i)
+
+
+with tempfile.TemporaryDirectory() as tmp:
+    rec = render_flyaround(dataset=_Dataset(), sequence_name="seq", model=enc_model, output_video_path=os.path.join(tmp, "v"),
+                           n_flyaround_poses=2, trajectory_type="simple_360", device="cpu", sample_mode=False,
+                           n_source_views=3, seed=5, up=(-0.0396, -0.8306, -0.5554),
+                           visualize_preds_keys=("images_render", "_all_source_images"))
+    import numpy as np
+    res["reconstruction"] = {k: list(np.load(v).shape) for k, v in rec.items() if v.endswith(".npy")}
+    # the reference's way: every pose calls forward with the images (re-encoding the same sources) -- same frames
+    with torch.random.fork_rng():
+        torch.manual_seed(5)
+        pick = torch.nn.functional.pad(torch.randperm(6)[:3], [1, 0]).tolist()
+    fr = [_Frame(i) for i in pick]
+    traj = hd.get_simple_360_camera_trajectory(2 * math.pi, 2, -30.0 * (2 * math.pi / 360), 10, (-0.0396, -0.8306, -0.5554), 3.2)
+    worst = 0
+    for n in range(2):
+        cam = hd.PerspectiveCameras(torch.cat([traj[[n]].focal_length.expand(1, 2)] + [f.camera.focal_length.expand(1, 2) for f in fr[1:]]),
+                                    torch.cat([traj[[n]].principal_point] + [f.camera.principal_point for f in fr[1:]]),
+                                    torch.cat([traj[[n]].R] + [f.camera.R for f in fr[1:]]),
+                                    torch.cat([traj[[n]].T] + [f.camera.T for f in fr[1:]]))
+        direct = enc_model(image_rgb=torch.stack([f.image_rgb for f in fr]), camera=cam,
+                           fg_probability=torch.stack([f.fg_probability for f in fr]),
+                           mask_crop=torch.stack([f.mask_crop for f in fr]), sequence_name=["seq"] * 4)
+        frame = ops.frame_u8(direct["images_render"][0].contiguous(), (8, 8))
+        worst = max(worst, int((frame.int() - torch.from_numpy(np.load(rec["images_render"]))[n].int()).abs().max()))
+    res["reconstruction_vs_per_pose_forward"] = worst
+
 with tempfile.TemporaryDirectory() as tmp:
     # generate_samples.py:87-138: exp_dir with expconfig.yaml + checkpoint -> load_experiment -> render_flyaround
     cfg = {"model_factory_ImplicitronModelFactory_args": {"model_class_type": "HoloDiffusionModel",

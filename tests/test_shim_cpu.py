@@ -51,3 +51,7 @@ def test_drop_in_package(mode):
     assert {"image_feature_extractor", "view_pooler", "pooled_feature_mapper"} <= set(res["encoder_modules"])
     assert res["encoder_grid"][0] == [1, 16, 8, 8, 8] and 0 < res["encoder_grid"][1] <= 1.0
     assert res["encoder_facade_vs_plain"] == 0.0 and res["encoder_ckpt_roundtrip"] == 0.0
+    # reconstruction fly-around: dataset frames -> seeded source views -> encoder (once) -> renders; the mosaic of the 3
+    # source images is 2 x 2 tiles; frames identical to calling forward with the images for every pose (the reference's loop)
+    assert res["reconstruction"] == {"images_render": [2, 8, 8, 3], "_all_source_images": [2, 64, 64, 3]}
+    assert res["reconstruction_vs_per_pose_forward"] == 0
