@@ -168,9 +168,13 @@ struct TcParams {
                       // written, [7] exit
     int fmt;          // 0 = bf16 pairs, HOLO_FMT_F16 = fp16 pairs (all four operand halves)
     float acc_scale;  // accumulators are multiplied by this before bias / residual (undoes the weights' 2^e scale)
+    // ---- conv_tc_kernel<N, true> only (holo_gemm_tc_act; appended so that the default instantiations' parameter offsets
+    // and code stay what the round's full GPU runs measured)
+    int epi_act;      // activation applied after bias / residual: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 Softplus
+    unsigned res_mod; // the residual is a (res_mod, Cout) table indexed by output row % res_mod; 0 = row for row
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool EPI = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -427,11 +431,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
                 if (P.residual && add_bias_res && row_ok) {
-                    const float4* rp = reinterpret_cast<const float4*>(P.residual + v * P.out_pitch + n);
+                    size_t rrow = v;
+                    if constexpr (EPI) rrow = P.res_mod ? (size_t)((unsigned)v % P.res_mod) : v;
+                    const float4* rp = reinterpret_cast<const float4*>(P.residual + rrow * P.out_pitch + n);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         float4 b = __ldg(rp + j4);
                         vals[j4 * 4 + 0] += b.x, vals[j4 * 4 + 1] += b.y, vals[j4 * 4 + 2] += b.z, vals[j4 * 4 + 3] += b.w;
+                    }
+                }
+                if constexpr (EPI) {   // activation of the consumer folded into this epilogue (holo_gemm_tc_act)
+                    if (P.epi_act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vals[j] = fmaxf(vals[j], 0.f);
+                    } else if (P.epi_act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vals[j] = holo_leaky(vals[j]);
+                    } else if (P.epi_act == 3) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vals[j] = vals[j] > 20.f ? vals[j] : log1pf(expf(vals[j]));
                     }
                 }
                 if (row_ok) {
@@ -614,10 +632,10 @@ int make_w_map(CUtensorMap* m, const void* base, int Ktot, long long pitch, int 
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool EPI = false>
 int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
            const CUtensorMap& a2h, const CUtensorMap& a2l, const TcParams& P, int tiles, int nsplit, cudaStream_t st) {
-    auto k = conv_tc_kernel<BLOCK_N>;
+    auto k = conv_tc_kernel<BLOCK_N, EPI>;
     HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
               "holo_conv3d_tc");
     TcParams Q = P;
@@ -658,7 +676,8 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
                         const float* bias, const float* residual, int Cout, long long out_pitch, float* out,
                         void* out_hi_bf16, void* out_lo_bf16, void* stream, int out_is_zeroed = 0,
                         double* stats = nullptr, int fmt = 0, float acc_scale = 1.0f, const void* x2_hi = nullptr,
-                        const void* x2_lo = nullptr, int Cin2 = 0, float* splitk_partials = nullptr) {
+                        const void* x2_lo = nullptr, int Cin2 = 0, float* splitk_partials = nullptr, int epi_act = 0,
+                        long long res_mod = 0) {
     if (!(x_hi && x_lo && w_hi && w_lo && (out || out_hi_bf16))) {
         holo_set_error("%s: null arg", who);
         return HOLO_ERR_ARG;
@@ -701,7 +720,8 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     // gridDim.z and accumulate with fp32 atomics into a zeroed output (>= 4 iterations per slice)
     int nsplit = 1, per = k_total;
     const int base = tiles * (Cout / block_n);
-    if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && (out_pitch == Cout || out_is_zeroed)) {
+    const bool epi = epi_act != 0 || res_mod != 0;   // activation / row-table epilogue: one slice owns the whole K loop
+    if (base < 120 && k_total >= 8 && out && !out_hi_bf16 && !epi && (out_pitch == Cout || out_is_zeroed)) {
         static const int target = [] {   // work items aimed at (2 per SM); HOLO_SPLITK_TARGET for tuning
             const char* e = getenv("HOLO_SPLITK_TARGET");
             const int v = e ? atoi(e) : 296;
@@ -753,6 +773,13 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     P.trace = g_conv_trace;
     P.stats = (nsplit == 1 && out_pitch == Cout) ? stats : nullptr;
     P.fmt = fmt, P.acc_scale = acc_scale, P.k2_slabs = Cin2 / SLAB;
+    P.epi_act = epi_act, P.res_mod = (unsigned)res_mod;
+    if (epi && (block_n < 64 || nsplit > 1 || epi_act < 0 || epi_act > 3 || res_mod < 0 || res_mod >= (1LL << 31) ||
+                (long long)D * H * W >= (1LL << 32))) {
+        holo_set_error("%s: the fused activation / row-table epilogue takes Cout %% 64 == 0, un-split K, act 0..3 (got Cout=%d "
+                       "act=%d slices=%d)", who, Cout, epi_act, nsplit);
+        return HOLO_ERR_UNSUPPORTED;
+    }
     // chunked accumulation (see the MMA issuer): chains of ~HOLO_CONV_CHUNK (tap, slab) iterations, 0 = one chain per item
     // (default 9 = three chains for a 27-tap x 1-slab item), balanced so that no short tail chain is left: every chain
     // boundary costs ~0.3 us of tensor-pipe time (the TMEM -> register flush shares the TMEM port, profiles/r02b)
@@ -770,7 +797,10 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     if (nsplit > 1 && !ws && !out_is_zeroed)
         HOLO_CUDA(cudaMemsetAsync(out, 0, (size_t)D * H * W * Cout * sizeof(float), st), who);
     int rc;
-    switch (block_n) {
+    if (epi) {
+        rc = block_n == 128 ? launch<128, true>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st)
+                            : launch<64, true>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st);
+    } else switch (block_n) {
         case 128: rc = launch<128>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
         case 64: rc = launch<64>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
         case 32: rc = launch<32>(ah, al, bh, bl, a2h, a2l, P, tiles, nsplit, st); break;
@@ -850,6 +880,30 @@ extern "C" int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitc
     return conv_tc_impl("holo_gemm_tc", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
                         residual, N, out_pitch, out, out_hi_bf16, out_lo_bf16, stream, out_is_zeroed, nullptr, operand_fmt,
                         acc_scale);
+}
+
+// holo_gemm_tc with the consumer's elementwise work folded into the epilogue:
+//   out[m][n] = act(acc_scale * sum_k a[m][k] b[n][k] + bias[n] + row_term[m % row_term_rows][n])
+// written as fp32 and / or as the next GEMM's operand pair.  The view-pooling encoder's Linear layers use it
+// (custom_modules.py:255-264: the per-point mean term is shared by the point's rows of every view).
+extern "C" int holo_gemm_tc_act(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
+                                const void* b_lo, long long b_pitch, int N, const float* bias, const float* row_term,
+                                long long row_term_rows, int act, long long out_pitch, float* out, void* out_hi,
+                                void* out_lo, int operand_fmt, float acc_scale, void* stream) {
+    if (M % BLOCK_M) {
+        holo_set_error("holo_gemm_tc_act: M=%d must be a multiple of 128", M);
+        return HOLO_ERR_UNSUPPORTED;
+    }
+    if (row_term && row_term_rows <= 0) {
+        holo_set_error("holo_gemm_tc_act: row_term needs row_term_rows > 0");
+        return HOLO_ERR_ARG;
+    }
+    if (!row_term && !act)   // nothing to fold: the plain kernel
+        return conv_tc_impl("holo_gemm_tc_act", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
+                            nullptr, N, out_pitch, out, out_hi, out_lo, stream, 0, nullptr, operand_fmt, acc_scale);
+    return conv_tc_impl("holo_gemm_tc_act", a_hi, a_lo, K, a_pitch, M / 32, TILE_H, TILE_W, 1, 1, b_hi, b_lo, b_pitch, bias,
+                        row_term, N, out_pitch, out, out_hi, out_lo, stream, 0, nullptr, operand_fmt, acc_scale,
+                        nullptr, nullptr, 0, nullptr, act, row_term ? row_term_rows : 0);
 }
 
 // Debug: subsequent convolution launches make CTA 0 write 8 clock64 stamps (TcParams::trace) into dev_buf8 (8 int64 on

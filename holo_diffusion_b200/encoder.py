@@ -92,9 +92,15 @@ class _Gemm:
         self.hi, self.lo, self.scale = _pack_pair(w, self.n_pad, k_pad, pair_dtype)
         self.bias = None if b is None else _pad_bias(b, self.n_pad)
 
-    def __call__(self, a_hi, a_lo, rows: int, out, out_hi=None, out_lo=None):
-        rc = ops.gemm_tc(a_hi, a_lo, 0, self.k_pad, rows, self.k_pad, self.hi, self.lo, 0, self.k_pad, self.n_pad,
-                         self.bias, None, self.n_pad, out, 0, out_hi, out_lo, acc_scale=1.0 / self.scale)
+    def __call__(self, a_hi, a_lo, rows: int, out, out_hi=None, out_lo=None, act: Optional[str] = None, row_term=None,
+                 row_term_rows: int = 0):
+        if act is not None or row_term is not None:   # activation / per-point term folded into the epilogue
+            rc = ops.gemm_tc_act(a_hi, a_lo, self.k_pad, rows, self.k_pad, self.hi, self.lo, self.k_pad, self.n_pad, self.bias,
+                                 row_term, row_term_rows, act or "identity", self.n_pad, out, out_hi, out_lo,
+                                 acc_scale=1.0 / self.scale)
+        else:
+            rc = ops.gemm_tc(a_hi, a_lo, 0, self.k_pad, rows, self.k_pad, self.hi, self.lo, 0, self.k_pad, self.n_pad,
+                             self.bias, None, self.n_pad, out, 0, out_hi, out_lo, acc_scale=1.0 / self.scale)
         if rc != 0:
             raise ops.HoloError(f"holo_gemm_tc rejected a {rows} x {self.k_pad} x {self.n_pad} Linear layer: "
                                 f"{ops.lib().cdll.holo_last_error().decode()}")
@@ -275,6 +281,7 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
     dev = pts.device
     ops.require_cuda(dev, "pool_views")
     pair_dtype = PAIR_DTYPE if pair_dtype is None else pair_dtype
+    fuse_act = os.environ.get("HOLO_VIEWPOOL_FUSE_ACT", "1") != "0"   # activations in the GEMM epilogues (default)
     agg = pooler.feature_aggregator
     kind = type(agg).__name__
     if getattr(agg, "exclude_target_view", False) or getattr(agg, "exclude_target_view_mask_features", False):
@@ -345,20 +352,28 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
     P_pad = _ceil(P, chunk)
     direct = out_cl is not None and mp is not None and out_cl.shape == (P_pad, n_out_pad) and out_cl.is_contiguous()
     rows_out = out_cl if direct else torch.empty(P_pad, n_out_pad, device=dev)
-    e16 = lambda r, c: (torch.zeros(r, c, device=dev, dtype=pair_dtype), torch.zeros(r, c, device=dev, dtype=pair_dtype))  # noqa: E731
+    # work buffers of one chunk, kept on the pooler between calls (zero-filled once: rows / columns that no kernel
+    # writes -- the tail of a ragged last chunk -- must hold finite values for the GEMMs)
+    ws_key = (n_src, chunk, Kpad, pair_dtype, str(dev), mlp_mean, key[1] if not mlp_mean else tuple(
+        [plan["first"].n_pad, plan["last"].n_pad] + [g.n_pad for g in plan["hidden"]]))
+    ws = pooler.__dict__.get("_holo_ws")
+    if ws is None or ws["key"] != ws_key:
+        z16 = lambda r, c: (torch.zeros(r, c, device=dev, dtype=pair_dtype), torch.zeros(r, c, device=dev, dtype=pair_dtype))  # noqa: E731
+        ws = {"key": ws_key}
+        if mlp_mean:
+            Hp, Dp = plan["first"].n_pad, plan["last"].n_pad
+            widths = [Hp] + [g.n_pad for g in plan["hidden"]]
+            ws["x"], ws["m"], ws["h"], ws["g"] = z16(n_src * chunk, Kpad), z16(chunk, Kpad), z16(n_src * chunk, max(widths)), z16(chunk, Dp)
+            ws["h2"] = z16(n_src * chunk, max(widths)) if plan["hidden"] else None   # a GEMM cannot write its own operand
+            ws["y"] = torch.zeros(n_src * chunk, max(widths + [Dp]), device=dev)
+            ws["mterm"], ws["pooled"] = torch.zeros(chunk, Hp, device=dev), torch.zeros(chunk, Dp, device=dev)
+        else:
+            ws["g"], ws["pooled"] = z16(chunk, Kpad), torch.zeros(chunk, Kx_pad, device=dev)
+        pooler.__dict__["_holo_ws"] = ws
+    (g_hi, g_lo), pooled = ws["g"], ws["pooled"] if (mp is None or debug is not None) else None
     if mlp_mean:
         Hp, Dp = plan["first"].n_pad, plan["last"].n_pad
-        x_hi, x_lo = e16(n_src * chunk, Kpad)
-        m_hi, m_lo = e16(chunk, Kpad)
-        widths = [Hp] + [g.n_pad for g in plan["hidden"]]
-        y = torch.empty(n_src * chunk, max(widths + [Dp]), device=dev)
-        mterm = torch.empty(chunk, Hp, device=dev)
-        h_hi, h_lo = e16(n_src * chunk, max(widths))
-        g_hi, g_lo = e16(chunk, Dp)
-        pooled = torch.empty(chunk, Dp, device=dev) if (mp is None or debug is not None) else None
-    else:
-        g_hi, g_lo = e16(chunk, Kpad)
-        pooled = torch.empty(chunk, Kx_pad, device=dev) if (mp is None or debug is not None) else None
+        (x_hi, x_lo), (m_hi, m_lo), (h_hi, h_lo), y, mterm = ws["x"], ws["m"], ws["h"], ws["y"], ws["mterm"]
     for c0 in range(0, P, chunk):
         n = min(chunk, P - c0)
         pc = pts[c0:c0 + n]
@@ -369,19 +384,27 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
             ops.viewpool_sample(pc, *cam, maps, n_harm, Kpad, chunk, x_hi, x_lo, m_hi, m_lo, mask_map=mask_map,
                                 view_weight=view_weight, x_f32=dbg_x, mean_f32=dbg_m)
             rows = n_src * chunk
-            y0 = y.view(-1)[: rows * Hp].view(rows, Hp)
-            plan["first"](x_hi, x_lo, rows, y0)
             plan["mean"](m_hi, m_lo, chunk, mterm)
             hh, hl = h_hi.view(-1)[: rows * Hp].view(rows, Hp), h_lo.view(-1)[: rows * Hp].view(rows, Hp)
-            ops.viewpool_act_split(y0, mterm, n_src, chunk, Hp, plan["acts"][0], hh, hl)
+            if fuse_act:   # H = act(X A^T + M[p]) straight out of the GEMM epilogue as the next operand pair
+                plan["first"](x_hi, x_lo, rows, None, hh, hl, act=plan["acts"][0], row_term=mterm, row_term_rows=chunk)
+            else:
+                y0 = y.view(-1)[: rows * Hp].view(rows, Hp)
+                plan["first"](x_hi, x_lo, rows, y0)
+                ops.viewpool_act_split(y0, mterm, n_src, chunk, Hp, plan["acts"][0], hh, hl)
             if debug is not None and c0 == 0:
-                debug.update(x=dbg_x[..., cols_t], mean=dbg_m[..., cols_t], y0=y0[:, : plan["first"].n].clone(),
-                             mterm=mterm[:, : plan["first"].n].clone())
+                debug.update(x=dbg_x[..., cols_t], mean=dbg_m[..., cols_t], mterm=mterm[:, : plan["first"].n].clone())
             for li, g in enumerate(plan["hidden"]):
-                yi = y.view(-1)[: rows * g.n_pad].view(rows, g.n_pad)
-                g(hh, hl, rows, yi)
-                hh, hl = h_hi.view(-1)[: rows * g.n_pad].view(rows, g.n_pad), h_lo.view(-1)[: rows * g.n_pad].view(rows, g.n_pad)
-                ops.viewpool_act_split(yi, None, n_src, chunk, g.n_pad, plan["acts"][li + 1], hh, hl)
+                # ping-pong between the two halves of the operand buffer (hidden widths are equal: n_hidden)
+                nh, nl = (ws["h2"][0], ws["h2"][1]) if li % 2 == 0 else (h_hi, h_lo)
+                nh, nl = nh.view(-1)[: rows * g.n_pad].view(rows, g.n_pad), nl.view(-1)[: rows * g.n_pad].view(rows, g.n_pad)
+                if fuse_act:
+                    g(hh, hl, rows, None, nh, nl, act=plan["acts"][li + 1])
+                else:
+                    yi = y.view(-1)[: rows * g.n_pad].view(rows, g.n_pad)
+                    g(hh, hl, rows, yi)
+                    ops.viewpool_act_split(yi, None, n_src, chunk, g.n_pad, plan["acts"][li + 1], nh, nl)
+                hh, hl = nh, nl
             z = y.view(-1)[: rows * Dp].view(rows, Dp)
             plan["last"](hh, hl, rows, z)
             ops.viewpool_reduce(z, n_src, chunk, n, Dp, out=pooled, out_hi=g_hi, out_lo=g_lo)

@@ -277,6 +277,18 @@ def gemm_tc(a_hi, a_lo, a_off, a_pitch, M, K, b_hi, b_lo, b_off, b_pitch, N, bia
     return rc
 
 
+def gemm_tc_act(a_hi, a_lo, a_pitch, M, K, b_hi, b_lo, b_pitch, N, bias, row_term, row_term_rows: int, act: str, out_pitch,
+                out=None, out_hi=None, out_lo=None, acc_scale: float = 1.0) -> int:
+    """out[m][n] = act(acc_scale * a b^T + bias[n] + row_term[m % row_term_rows][n]) as fp32 and / or an operand pair."""
+    f16 = _pair_f16(a_hi, a_lo, b_hi, b_lo, out_hi, out_lo)
+    rc = lib().try_call("holo_gemm_tc_act", _ptr16(a_hi), _ptr16(a_lo), a_pitch, M, K, _ptr16(b_hi), _ptr16(b_lo), b_pitch, N,
+                        _ptr(bias), _ptr(row_term), int(row_term_rows), VP_ACT[act], out_pitch, _ptr(out), _ptr16(out_hi),
+                        _ptr16(out_lo), FMT_F16 * f16, float(acc_scale), _stream())
+    if rc not in (0, -3):
+        raise HoloError(f"holo_gemm_tc_act failed ({rc}): {lib().cdll.holo_last_error().decode()}")
+    return rc
+
+
 P_SCALE_F16 = 4096.0   # fp16 probability pairs are written as 4096 P; the P V GEMM takes acc_scale = 1 / 4096
 
 

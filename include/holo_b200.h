@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HOLO_B200_VERSION 121
+#define HOLO_B200_VERSION 122
 
 int holo_version(void);
 const char* holo_last_error(void);
@@ -217,6 +217,16 @@ int holo_gemm_tc(const void* a_hi, const void* a_lo, long long a_pitch, int M, i
                  const void* b_lo, long long b_pitch, int N, const float* bias, const float* residual,
                  long long out_pitch, float* out, void* out_hi, void* out_lo, int out_is_zeroed, int operand_fmt,
                  float acc_scale, void* stream);
+/* The same GEMM with the consumer's elementwise work in its epilogue:
+ *   out[m][n] = act(acc_scale * sum_k a[m][k] b[n][k] + bias[n] + row_term[m % row_term_rows][n]),
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 Softplus; row_term (row_term_rows, N) fp32 with the output's pitch, or NULL;
+ * fp32 `out` and / or the operand pair out_hi / out_lo of the next GEMM.  N % 64 == 0, K is never split.
+ * Carries the Linear layers of MLPMeanFeatureAggregator (custom_modules.py:255-264): the mean term of a point is
+ * shared by that point's row in every view (rows are view-major), the hidden activations never visit HBM as fp32. */
+int holo_gemm_tc_act(const void* a_hi, const void* a_lo, long long a_pitch, int M, int K, const void* b_hi,
+                     const void* b_lo, long long b_pitch, int N, const float* bias, const float* row_term,
+                     long long row_term_rows, int act, long long out_pitch, float* out, void* out_hi, void* out_lo,
+                     int operand_fmt, float acc_scale, void* stream);
 /* P = p_scale * softmax(scale2 * S): with fp16 halves pass p_scale = 4096 (normalised probabilities of long rows sit
  * in fp16's subnormal range) and give the P V GEMM acc_scale = 1 / 4096; 1 otherwise. */
 int holo_softmax_split(const float* S, int n_rows, int T, float scale2, void* P_hi, void* P_lo, int pair_f16,

@@ -72,7 +72,25 @@ def viewpool_reduce(z, n_views, rows_per_view, n_pts, C, out=None, out_hi=None, 
         out_lo[:n_pts] = 0
 
 
-ALL = dict(viewpool_sample=viewpool_sample, viewpool_angle_reduce=viewpool_angle_reduce, viewpool_act_split=viewpool_act_split,
+def gemm_tc_act(a_hi, a_lo, a_pitch, M, K, b_hi, b_lo, b_pitch, N, bias, row_term, row_term_rows, act, out_pitch, out=None,
+                out_hi=None, out_lo=None, acc_scale=1.0):
+    a = fake_unet_ops._view(a_hi, 0, a_pitch, M, K) + fake_unet_ops._view(a_lo, 0, a_pitch, M, K)
+    b = fake_unet_ops._view(b_hi, 0, b_pitch, N, K) + fake_unet_ops._view(b_lo, 0, b_pitch, N, K)
+    y = (a @ b.t()) * acc_scale
+    if bias is not None:
+        y = y + bias
+    if row_term is not None:
+        y = y + row_term[torch.arange(M) % row_term_rows]
+    y = ACTS[act](y)
+    if out is not None:
+        fake_unet_ops._view(out, 0, out_pitch, M, N).copy_(y)
+    if out_hi is not None:
+        fake_unet_ops._view(out_hi, 0, out_pitch, M, N).copy_(y)
+        out_lo.zero_()
+    return 0
+
+
+ALL = dict(gemm_tc_act=gemm_tc_act, viewpool_sample=viewpool_sample, viewpool_angle_reduce=viewpool_angle_reduce, viewpool_act_split=viewpool_act_split,
            viewpool_reduce=viewpool_reduce, gemm_tc=fake_unet_ops.gemm_tc, act_range=fake_model_ops.act_range,
            require_cuda=lambda device, who: None)
 

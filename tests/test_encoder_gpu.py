@@ -178,3 +178,57 @@ def test_full_size_grid_with_resnet_features():
     print(f"full-size view pooling (64^3 points x {n_src} views): {ms:.2f} ms, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
           f"rel err {e:.2e}")
     assert e < 1e-4
+
+
+@pytest.mark.parametrize("N,act,rows_mod", [(128, "leakyrelu", 256), (64, "softplus", 0), (128, "relu", 128), (64, "identity", 384)])
+def test_gemm_with_activation_epilogue(N, act, rows_mod):
+    """holo_gemm_tc_act: act(a b^T / s + bias + row_term[m % rows]) against fp64, fp32 output and operand-pair output."""
+    from holo_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(N + rows_mod)
+    M, K = 768, 192
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1
+    bias = torch.randn(N, generator=g)
+    term = torch.randn(rows_mod, N, generator=g) if rows_mod else None
+    scale = 1024.0
+
+    def pair(x):
+        hi = x.cuda().half()
+        return hi, (x.cuda() - hi.float()).half()
+
+    a_hi, a_lo = pair(a)
+    w_hi, w_lo = pair(w * scale)
+    out = torch.empty(M, N, device="cuda")
+    o_hi, o_lo = torch.empty(M, N, device="cuda", dtype=torch.half), torch.empty(M, N, device="cuda", dtype=torch.half)
+    rc = ops.gemm_tc_act(a_hi, a_lo, K, M, K, w_hi, w_lo, K, N, bias.cuda(), None if term is None else term.cuda(), rows_mod,
+                         act, N, out, o_hi, o_lo, acc_scale=1.0 / scale)
+    assert rc == 0
+    y = a.double() @ w.double().t() + bias.double()
+    if term is not None:
+        y = y + term.double()[torch.arange(M) % rows_mod]
+    ref = {"identity": lambda t: t, "relu": torch.relu, "leakyrelu": lambda t: torch.nn.functional.leaky_relu(t, 0.2),
+           "softplus": torch.nn.functional.softplus}[act](y)
+    e1, e2 = rel_err(out, ref), rel_err(o_hi.float() + o_lo.float(), ref)
+    print(f"gemm + {act} epilogue N={N} rows_mod={rows_mod}: fp32 out {e1:.2e}, pair out {e2:.2e}")
+    assert e1 < 5e-6 and e2 < 5e-6
+
+
+def test_fused_activation_epilogue_matches_separate_pass():
+    """pool_views with the activations folded into the GEMM epilogues (default) == GEMM + holo_viewpool_act_split."""
+    from holo_diffusion_b200 import encoder as en
+    cams, feats, mask_crop = eo.make_views(4, (40, 48), seed=41)
+    sd = eo.make_aggregator_params(64 + 1 + 3 + 21, 128, 128, 3, seed=42)
+    pts = _points(700, 43).cuda()
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["HOLO_VIEWPOOL_FUSE_ACT"], os.environ["HOLO_VIEWPOOL_CHUNK"] = flag, "384"
+        try:
+            pooler = _mlp_pooler(sd, 128, 128, 3, True)
+            rows = en.pool_views(pooler, pts, _cams_gpu(cams), _gpu(feats), mask_crop.cuda(), None, mapper=None)
+            outs.append(rows.clone())
+        finally:
+            os.environ.pop("HOLO_VIEWPOOL_FUSE_ACT", None), os.environ.pop("HOLO_VIEWPOOL_CHUNK", None)
+    e = rel_err(outs[0], outs[1])
+    fs, ms = eo.sample_views(cams, pts.cpu(), feats, mask_crop, True)
+    ref = eo.mlp_mean_aggregate(sd, fs, ms, cams, pts.cpu())[0, 0]
+    print(f"fused vs separate activation pass: {e:.2e}; fused vs oracle {rel_err(outs[0], ref):.2e}")
+    assert e < 2e-6 and rel_err(outs[0], ref) < 1e-4
