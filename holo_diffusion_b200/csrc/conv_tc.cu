@@ -636,8 +636,12 @@ template <int BLOCK_N, bool EPI = false>
 int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
            const CUtensorMap& a2h, const CUtensorMap& a2l, const TcParams& P, int tiles, int nsplit, cudaStream_t st) {
     auto k = conv_tc_kernel<BLOCK_N, EPI>;
-    HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
-              "holo_conv3d_tc");
+    static bool attr_set = false;   // per instantiation; the driver calls below cost ~10 us of host time per launch
+    if (!attr_set) {
+        HOLO_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES),
+                  "holo_conv3d_tc");
+        attr_set = true;
+    }
     TcParams Q = P;
     Q.m_tiles = tiles, Q.n_blocks = P.Cout / BLOCK_N, Q.nsplit = nsplit;
     Q.stages = Q.iters_per_split < Cfg<BLOCK_N>::STAGES ? Q.iters_per_split : Cfg<BLOCK_N>::STAGES;
@@ -653,10 +657,13 @@ int launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, 
     int occ_smem = (227 * 1024) / (smem + 1024);
     int occ_tmem = 512 / (2 * Cfg<BLOCK_N>::TMEM_COLS);
     int occ = occ_smem < occ_tmem ? occ_smem : occ_tmem;
-    int occ_api = 0;   // registers bound the residency too (the epilogue keeps BLOCK_N partial sums per thread)
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_api, k, NUM_THREADS, (size_t)smem) == cudaSuccess && occ_api > 0 &&
-        occ_api < occ)
-        occ = occ_api;
+    // registers bound the residency too (the epilogue keeps BLOCK_N partial sums per thread); one query per pipeline depth
+    static int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int& occ_api = occ_cache[Q.stages & 7];
+    if (occ_api == 0 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_api, k, NUM_THREADS, (size_t)smem) != cudaSuccess)
+        occ_api = -1;
+    if (occ_api > 0 && occ_api < occ) occ = occ_api;
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
     const long long items = (long long)Q.m_tiles * Q.n_blocks * Q.nsplit;

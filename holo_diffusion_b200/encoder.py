@@ -263,11 +263,13 @@ def coord_grid(resol: int, volume_extent: float, device) -> torch.Tensor:
 
 
 def _chunk_points(n_src: int) -> int:
-    """Points per chunk: ~160k (view, point) rows keep one intermediate at 84 MB, i.e. producer and consumer in L2."""
+    """Points per chunk.  Measured on B200 (profiles/r02j-r02l): bigger is faster -- the (view, point) activations do
+    not stay in L2 at any useful chunk size, while every chunk costs six launches of host time -- so the default takes up
+    to 4 Mi (view, point) rows at once: the whole 64^3 grid for up to 16 views, ~6.5 GB of operand / activation buffers."""
     env = os.environ.get("HOLO_VIEWPOOL_CHUNK")
     if env:
         return max(128, _ceil(int(env), 128))
-    return max(1024, _ceil(163840 // max(n_src, 1), 128))
+    return max(1024, ((1 << 22) // max(n_src, 1)) // 128 * 128)
 
 
 @torch.no_grad()
@@ -327,7 +329,11 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
         # pooled row of the reference: [mu_k | std_k] per feature; padded: the same with C_k rounded up
         cols = [per * st + r * maps[k].shape[3] + c for k, (st, ch) in enumerate(zip(starts, chans)) for r in range(per)
                 for c in range(ch)]
-    cols_t = torch.tensor(cols, device=dev, dtype=torch.long)
+    cols_cache = pooler.__dict__.setdefault("_holo_cols", {})
+    cols_t = cols_cache.get((tuple(cols), str(dev)))
+    if cols_t is None:   # a host -> device copy: once per layout, not per call
+        cols_cache.clear()
+        cols_t = cols_cache[(tuple(cols), str(dev))] = torch.tensor(cols, device=dev, dtype=torch.long)
     Kpad = _ceil(Kx_pad, 64)
     if Kpad > 256:
         raise NotImplementedError(f"{Kx_pad} pooled columns: the kernels hold rows of up to 256")
