@@ -283,7 +283,11 @@ def pool_views(pooler, pts: torch.Tensor, camera, feats: Dict[str, torch.Tensor]
     dev = pts.device
     ops.require_cuda(dev, "pool_views")
     pair_dtype = PAIR_DTYPE if pair_dtype is None else pair_dtype
-    fuse_act = os.environ.get("HOLO_VIEWPOOL_FUSE_ACT", "1") != "0"   # activations in the GEMM epilogues (default)
+    # HOLO_VIEWPOOL_FUSE_ACT=1 folds the activations (and the per-point mean term) into the GEMM epilogues
+    # (holo_gemm_tc_act).  Validated, bit-identical -- and SLOWER on B200 (4.25 vs 3.60 ms per 64^3 grid,
+    # profiles/r02l): with K = 128 these GEMMs are epilogue-bound, and the epilogue is 4 warps per SM, so the hi/lo
+    # conversion of 128 columns per row costs more there than as a full-occupancy pass at 0.8 of the HBM copy rate.
+    fuse_act = os.environ.get("HOLO_VIEWPOOL_FUSE_ACT", "0") == "1"
     agg = pooler.feature_aggregator
     kind = type(agg).__name__
     if getattr(agg, "exclude_target_view", False) or getattr(agg, "exclude_target_view_mask_features", False):

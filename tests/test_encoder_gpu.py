@@ -213,7 +213,8 @@ def test_gemm_with_activation_epilogue(N, act, rows_mod):
 
 
 def test_fused_activation_epilogue_matches_separate_pass():
-    """pool_views with the activations folded into the GEMM epilogues (default) == GEMM + holo_viewpool_act_split."""
+    """pool_views with the activations folded into the GEMM epilogues (HOLO_VIEWPOOL_FUSE_ACT=1) == GEMM +
+    holo_viewpool_act_split (the default: faster, see encoder.py)."""
     from holo_diffusion_b200 import encoder as en
     cams, feats, mask_crop = eo.make_views(4, (40, 48), seed=41)
     sd = eo.make_aggregator_params(64 + 1 + 3 + 21, 128, 128, 3, seed=42)

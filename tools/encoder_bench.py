@@ -71,7 +71,8 @@ def main():
     torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1) / a.iters
     # ---- per entry point
-    names = ["viewpool_sample", "viewpool_angle_reduce", "gemm_tc", "viewpool_act_split", "viewpool_reduce", "act_range"]
+    names = ["viewpool_sample", "viewpool_angle_reduce", "gemm_tc", "gemm_tc_act", "viewpool_act_split", "viewpool_reduce",
+             "act_range"]
     spans = {k: [] for k in names}
     orig = {k: getattr(ops, k) for k in names}
 
@@ -96,7 +97,7 @@ def main():
     rows_total = n * R ** 3
     lin_flops = (rows_total * 2.0 * (128 * 128 + 128 * 128) + R ** 3 * 2.0 * (128 * 128 + 128 * C)) if a.aggregator == "mlp_mean" \
         else R ** 3 * 2.0 * 192 * C
-    gemm_ms = split.get("gemm_tc", {}).get("ms", 0.0)
+    gemm_ms = split.get("gemm_tc", {}).get("ms", 0.0) + split.get("gemm_tc_act", {}).get("ms", 0.0)
     print(json.dumps({
         "workload": f"view pooling: {R}^3 grid x {C}ch from {n} views, feature maps "
                     + ", ".join(f"{k} {tuple(v.shape[1:])}" for k, v in feats.items()),
