@@ -717,6 +717,14 @@ static int conv_tc_impl(const char* who, const void* x_hi, const void* x_lo, int
     // small volumes: prefer more CTAs over wider tiles
     const int tiles = (D / td) * (H / th) * (W / tw);
     if (block_n == 128 && tiles * (Cout / 128) < 148) block_n = 64;
+    // short-K plain GEMMs (the view-pooling encoder's Linear layers: 2 K-steps per output tile) are bound by the epilogue;
+    // N = 64 tiles would leave TMEM and registers for two CTAs per SM.  Measured SLOWER (four GEMMs of the encoder: 1.78 vs
+    // 1.53 ms, profiles/r02l/encoder_gemm_n64.json): twice the A-operand traffic outweighs the extra epilogue warps.  Off.
+    static const int gemm_n64 = [] {
+        const char* e = getenv("HOLO_GEMM_SHORTK_N64");
+        return e ? atoi(e) : 0;
+    }();
+    if (gemm_n64 && block_n == 128 && ksize == 1 && Cin2 == 0 && Cin <= 256 && strncmp(who, "holo_gemm", 9) == 0) block_n = 64;
     const int taps = ksize * ksize * ksize;
     if (Cin2 && (!x2_hi || !x2_lo || Cin2 % SLAB || stride != 1)) {
         holo_set_error("%s: the fused skip operand needs both halves, Cin_skip %% 64 == 0 and stride 1", who);
