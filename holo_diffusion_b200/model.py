@@ -323,9 +323,11 @@ class HoloDiffusionModel(nn.Module):
 
         feats = self.image_feature_extractor(src(image_rgb), src(fg_probability))
         C, R = self.feature_size, self.resol
-        pts = self.__dict__.get("_grid_pts")
-        if pts is None or pts.device != dev or pts.shape[0] != R ** 3:
-            pts = self.__dict__["_grid_pts"] = _enc.coord_grid(R, self.volume_extent, dev)
+        cached = self.__dict__.get("_grid_pts")
+        if cached is None or cached[0] != (R, float(self.volume_extent), str(dev)):
+            cached = self.__dict__["_grid_pts"] = ((R, float(self.volume_extent), str(dev)),
+                                                   _enc.coord_grid(R, self.volume_extent, dev))
+        pts = cached[1]
         cams = camera[sel]
         cams = PerspectiveCameras(cams.focal_length, cams.principal_point, cams.R, cams.T).to(dev)
         vw = None if sequence_name is None else _enc.view_weights(sequence_name[:1], [sequence_name[i] for i in sel], dev)
