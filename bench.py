@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager GPU comparator (N=1 only)")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the view-pooling encoder evidence (N=1 only)")
     ap.add_argument("--e2e-first", action="store_true", help="debug: run the end-to-end timing loop before the device one")
     return ap.parse_args()
 
@@ -371,6 +372,12 @@ def run_ours(a):
                 eager = _gpu_eager_baseline(a, dev)
             except Exception as exc:  # noqa: BLE001
                 eager = {"error": f"{type(exc).__name__}: {exc}"}
+    encoder = None
+    if rank == 0 and world == 1 and not a.no_encoder:
+        try:
+            encoder = _encoder_evidence(a, dev)
+        except Exception as exc:  # noqa: BLE001
+            encoder = {"error": f"{type(exc).__name__}: {exc}"}
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         cpu_reference_step(a, max(4, a.image // 32))  # warm-up (builds the fixtures, pages in the weights)
@@ -386,7 +393,7 @@ def run_ours(a):
                "e2e": {"value": e2e, "unit": "views/s", "ms_per_step": ms_e2e / a.steps,
                        "h2d_bytes_per_step": grid_host.numel() * 4 + 4 * (9 + 3 + 2 + 2), "d2h_bytes_per_step": img_host.numel() * 4 + 16},
                "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_other_kernels": others,
-               "cpu_baseline": cpu, "gpu_eager_baseline": eager,
+               "cpu_baseline": cpu, "gpu_eager_baseline": eager, "view_pooling_encoder": encoder,
                "parity_note": "1e-4 is asserted per stage on matched inputs (two-pass rendering is ill-conditioned in fp32: "
                               "DESIGN.md section 4); end to end the image is within 3x the fp32 oracle's own distance to its fp64 twin"}
         print(json.dumps(out))
@@ -593,6 +600,74 @@ def _gpu_eager_baseline(a, dev):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
     return res
+
+
+def _encoder_evidence(a, dev, n_views: int = 10):
+    """Additive evidence for the row next to the hot path (source views -> voxel grid), NOT
+    part of the metric: device time of the view pooling that fills this workload's grid from `n_views` source views
+    (feature maps shaped like configs/base.yaml's ResNet34 extractor output; MLPMean aggregator) on the kernels, next to
+    the oracle's restatement as PyTorch-eager ops on the same GPU (a baseline leg like gpu_eager_baseline), and their
+    distance.  A failure in here never touches the headline."""
+    import math as _m
+
+    import holo_diffusion_b200 as hd
+    from holo_diffusion_b200 import encoder as en, ops
+    from oracle import encoder_oracle as eo
+    from oracle import render_oracle as ro
+    C, R = a.channels, a.resol
+    g = torch.Generator().manual_seed(5)
+    feats = {}
+    for i, s_ in enumerate((64, 32, 16, 8)):
+        f = torch.randn(n_views, 16, s_, s_, generator=g)
+        feats[f"res_layer_{i + 1}"] = (torch.nn.functional.normalize(f, dim=1) * 0.5).to(dev)
+    up = lambda t: torch.nn.functional.interpolate(t, size=(256, 256), mode="bilinear")   # noqa: E731
+    feats["mask"], feats["image"] = up(torch.rand(n_views, 1, 32, 32, generator=g)).to(dev), up(torch.randn(n_views, 3, 32, 32, generator=g)).to(dev)
+    oc = ro.simple_360_cameras(n_views, focal_length=3.2)
+    ocd = ro.OracleCameras(oc.R.to(dev), oc.T.to(dev), oc.focal.to(dev), oc.pp.to(dev))
+    cams = hd.PerspectiveCameras(oc.focal.clone(), oc.pp.clone(), oc.R.clone(), oc.T.clone()).to(dev)
+    sd = {k: v.to(dev) for k, v in eo.make_aggregator_params(68 + 21, seed=31).items()}
+    pooler = hd.ViewPooler(feature_aggregator_class_type="MLPMeanFeatureAggregator").to(dev)
+    pooler.feature_aggregator.load_state_dict(sd)
+    pooler.feature_aggregator.exclude_target_view = pooler.feature_aggregator.exclude_target_view_mask_features = False
+    mapper = en.LazyLinearWithXavierInit(C).to(dev)
+    pts = en.coord_grid(R, 8.0, dev)
+    grid_cf = torch.empty(C * R ** 3, device=dev)
+
+    def ours():
+        rows = en.pool_views(pooler, pts, cams, feats, None, None, mapper=mapper)
+        ops.act_range(rows, R ** 3, C, 1, None, grid_cf, None)
+        return grid_cf.view(1, C, R, R, R)
+
+    def eager(chunk=32768):
+        rows = []
+        for i in range(0, pts.shape[0], chunk):
+            pc = pts[i:i + chunk]
+            fs, ms = eo.sample_views(ocd, pc, feats, None, False)
+            rows.append(eo.mlp_mean_aggregate(sd, fs, ms, ocd, pc))
+        v = torch.nn.functional.linear(torch.cat(rows, 2), mapper.weight.detach(), mapper.bias.detach()).permute(0, 3, 1, 2)
+        return torch.tanh(v.reshape(1, -1, R, R, R))
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, out
+
+    with torch.no_grad():
+        t_ours, g_ours = timed(ours, 5)
+        g_ours = g_ours.clone()
+        t_eager, g_eager = timed(eager, 2)
+    err = float((g_ours - g_eager).abs().max() / g_eager.abs().max())
+    pooler.__dict__.pop("_holo_ws", None)   # give the ~4 GB of work buffers back
+    return {"what": f"view pooling of the {R}^3 x {C}ch grid from {n_views} source views (ResNet34-shaped feature maps, MLPMean "
+                    "aggregator, mapper, tanh): kernels vs the oracle restatement as PyTorch-eager ops on the same GPU; not part "
+                    "of the metric", "ms_per_grid": t_ours, "eager_gpu_ms": t_eager, "speedup_vs_eager": t_eager / t_ours,
+            "rel_err_vs_eager": err, "rows": n_views * R ** 3, "kind": "port"}
 
 
 def main():
