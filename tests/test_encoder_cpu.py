@@ -248,3 +248,48 @@ def test_host_source_selection():
     assert select_sources(None, 3, 1) == [1, 2]
     assert view_weights(["a"], ["a", "a"], "cpu") is None
     assert view_weights(["a"], ["a", "b"], "cpu").tolist() == [1.0, 0.0]
+
+
+def test_host_resnet_feature_extractor_contract():
+    """ResNetFeatureExtractor (library network, torch ops): the feature dict the pooling consumes -- names and order,
+    stage resolutions (1/4 ... 1/32 of the rescaled image), proj_dim channels L2-normalised to 1 / sqrt(n_stages),
+    the un-touched masks, the normalised + rescaled image, and the reference's parameter names."""
+    import holo_diffusion_b200  # noqa: F401
+    from holo_diffusion_b200.encoder import ResNetFeatureExtractor
+    torch.manual_seed(0)
+    ext = ResNetFeatureExtractor(proj_dim=16, image_rescale=0.32).eval()    # configs/base.yaml:162-164
+    imgs, fg = torch.rand(2, 3, 400, 400), torch.rand(2, 1, 400, 400)
+    feats = ext(imgs, fg)
+    assert list(feats) == ["res_layer_1", "res_layer_2", "res_layer_3", "res_layer_4", "mask", "image"]
+    assert [tuple(f.shape[1:]) for f in feats.values()] == [(16, 32, 32), (16, 16, 16), (16, 8, 8), (16, 4, 4), (1, 400, 400),
+                                                             (3, 128, 128)]
+    for k in ("res_layer_1", "res_layer_4"):
+        assert torch.allclose(feats[k].norm(dim=1), torch.full_like(feats[k][:, 0], 0.5), atol=1e-5)
+    assert feats["mask"] is fg
+    mean, std = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1), torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    assert torch.allclose(feats["image"], F.interpolate((imgs - mean) / std, scale_factor=0.32, mode="bilinear"), atol=1e-6)
+    keys = list(ext.state_dict())
+    assert "stem.0.weight" in keys and "layers.3.2.bn2.running_var" in keys and "proj_layers.0.weight" in keys
+    assert ext.get_feat_dims() == 4 * 16 + 1 + 3
+    # stages can be dropped, the projection switched off
+    few = ResNetFeatureExtractor(stages=(1, 3), proj_dim=0, add_images=False, image_rescale=1.0).eval()
+    f2 = few(torch.rand(1, 3, 64, 64), torch.rand(1, 1, 64, 64))
+    assert list(f2) == ["res_layer_1", "res_layer_3", "mask"] and f2["res_layer_3"].shape == (1, 256, 4, 4)
+
+
+def test_host_pool_views_rejects_what_is_not_built(enc):
+    cams, feats, mask_crop = eo.make_views(2, (16, 16), stage_channels=(8,), seed=1)
+    pts = torch.zeros(10, 3)
+    pooler = enc.ViewPooler()
+    with pytest.raises(NotImplementedError, match="target-view exclusion"):      # pytorch3d's default flags (:115-116 clear them)
+        enc.pool_views(pooler, pts, _b200_cams(cams), feats, mask_crop, None, mapper=None)
+    pooler.feature_aggregator.exclude_target_view = pooler.feature_aggregator.exclude_target_view_mask_features = False
+    pooler.view_sampler.sampling_mode = "nearest"
+    with pytest.raises(NotImplementedError, match="bilinear"):
+        enc.pool_views(pooler, pts, _b200_cams(cams), feats, mask_crop, None, mapper=None)
+    with pytest.raises(NotImplementedError, match="not built"):
+        enc.ViewPooler(feature_aggregator_class_type="ReductionFeatureAggregator")
+    wide = {f"m{i}": torch.randn(2, 64, 4, 4) for i in range(5)}                  # 320 columns > the kernels' 256
+    pooler.view_sampler.sampling_mode = "bilinear"
+    with pytest.raises(NotImplementedError, match="rows of up to 256"):
+        enc.pool_views(pooler, pts, _b200_cams(cams), wide, None, None, mapper=None)
