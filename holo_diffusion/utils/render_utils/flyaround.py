@@ -96,17 +96,16 @@ def _collate_frames(frames: Sequence[Any]) -> Any:
 
 
 def _stack_images(ims: torch.Tensor, size: Optional[Tuple[int, int]]) -> torch.Tensor:
-    """flyaround.py:485-503: the source views tiled into a ceil(sqrt(n))^2 mosaic."""
-    ba = ims.shape[0]
-    H = W = int(np.ceil(np.sqrt(ba)))
-    n_add = H * W - ba
-    if n_add > 0:
-        ims = torch.cat((ims, torch.zeros_like(ims[:1]).repeat(n_add, 1, 1, 1)))
-    ims = ims.view(H, W, *ims.shape[1:])
-    cated = torch.cat([torch.cat(list(row), dim=2) for row in ims], dim=1)
+    """The source views as one mosaic, row-major tiles on the smallest square grid that holds them, black where the grid
+    is not filled (what flyaround.py:485-503 builds with nested concatenations)."""
+    n, c, h, w = ims.shape
+    side = int(math.ceil(math.sqrt(n)))
+    canvas = ims.new_zeros(side * side, c, h, w)
+    canvas[:n] = ims
+    mosaic = canvas.view(side, side, c, h, w).permute(2, 0, 3, 1, 4).reshape(c, side * h, side * w)
     if size is not None:
-        cated = torch.nn.functional.interpolate(cated[None], size=size, mode="bilinear")[0]
-    return cated.clamp(0.0, 1.0)
+        mosaic = torch.nn.functional.interpolate(mosaic[None], size=size, mode="bilinear")[0]
+    return mosaic.clamp(0.0, 1.0)
 
 
 def _images_from_preds(preds: Dict[str, Any], extract_keys: Sequence[str] = (
