@@ -608,8 +608,6 @@ def _encoder_evidence(a, dev, n_views: int = 10):
     (feature maps shaped like configs/base.yaml's ResNet34 extractor output; MLPMean aggregator) on the kernels, next to
     the oracle's restatement as PyTorch-eager ops on the same GPU (a baseline leg like gpu_eager_baseline), and their
     distance.  A failure in here never touches the headline."""
-    import math as _m
-
     import holo_diffusion_b200 as hd
     from holo_diffusion_b200 import encoder as en, ops
     from oracle import encoder_oracle as eo

@@ -1,6 +1,5 @@
 """View-pooling encoder (views -> voxel grid) on the GPU: every stage of the fused pooling against the oracle, the
 model's encoder branch against the reference-forward golden vectors, and the full-size grid (64^3, 10 source views)."""
-import math
 import os
 
 import numpy as np
